@@ -1,0 +1,202 @@
+/* semadb_b200.h — C ABI of the B200-native vector-search hot path for SemaDB.
+ *
+ * This is the drop-in boundary: the entry points a Go shard binds through cgo in
+ * place of its CPU implementation of shard/index/vamana (IndexVamana),
+ * shard/index/flat (IndexFlat), shard/vectorstore (VectorStore + quantizers) and
+ * distance (DistFunc family). Plain pointers and sizes only; no CUDA/torch types.
+ * See INTEGRATION.md for the cgo stub. All reference citations are relative to
+ * the semadb repository root.
+ *
+ * Conventions (precedent: internal/shardpy/shardpy.go:165-197)
+ *  - caller allocates every output buffer, callee fills it;
+ *  - no pointer is retained after a call returns (cgo pointer-passing rule):
+ *    inputs are copied to pinned/device memory before return;
+ *  - every function returns 0 on success or an SDB_ERR_* code; the message is
+ *    available from sdb_last_error() on the calling thread. Nothing aborts or
+ *    panics (CONTRIBUTING.md:150). There is NO CPU fallback: without a CUDA
+ *    device every compute call fails with SDB_ERR_CUDA.
+ *  - node ids are the reference's uint64 node ids (0 invalid, 1 = start node,
+ *    user points from 2: vamana.go:28,150-157; idcounter.go:52-54). They must be
+ *    dense small integers (< 2^31) because device rows are indexed by id.
+ *  - a handle is internally serialised by a mutex; calls may come from any OS
+ *    thread (cgo) and set the CUDA device on entry.
+ *  - *_device variants take DEVICE pointers (same process, same device) and a
+ *    cudaStream_t passed as void*; they enqueue work and do not synchronise.
+ */
+#ifndef SEMADB_B200_H
+#define SEMADB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDB_ABI_VERSION 1
+
+/* error codes */
+#define SDB_OK 0
+#define SDB_ERR_INVALID 1    /* bad argument / parameter out of the reference's range */
+#define SDB_ERR_CUDA 2       /* CUDA runtime failure (incl. no device) */
+#define SDB_ERR_OOM 3        /* host or device allocation failed */
+#define SDB_ERR_STATE 4      /* call not valid in the current state (e.g. PQ not fitted) */
+#define SDB_ERR_SEARCHSIZE 5 /* searchSize < k (search.go:23-25) */
+#define SDB_ERR_RESERVED_ID 6 /* id 0 or 1 in an insert (vamana.go:150-157) */
+#define SDB_ERR_NOTFOUND 7   /* a referenced node id does not exist */
+#define SDB_ERR_INTERNAL 8
+
+/* distance metrics — models/constants.go:7-14, distance/distance.go:70-97 */
+#define SDB_METRIC_EUCLIDEAN 0 /* squared L2 (distance.go:14-16) */
+#define SDB_METRIC_DOT 1       /* -dot (distance.go:19-21) */
+#define SDB_METRIC_COSINE 2    /* 1-dot, caller normalises (distance.go:23-25) */
+#define SDB_METRIC_HAMMING 3   /* distance.go:45-54, binary store forced on (vectorstore.go:56-66) */
+#define SDB_METRIC_JACCARD 4   /* distance.go:56-67 */
+#define SDB_METRIC_HAVERSINE 5 /* distance.go:33-43, dim must be 2 */
+
+/* quantizers — models/quantizer.go:5-9 */
+#define SDB_QUANT_NONE 0
+#define SDB_QUANT_BINARY 1
+#define SDB_QUANT_PRODUCT 2
+
+/* Mirrors models.IndexVectorVamanaParameters (models/index.go:275-282) plus
+ * models.Quantizer (models/quantizer.go:5-76). Ranges are validated like the
+ * reference: searchSize 25..75, degreeBound 32..64, alpha 1.1..1.5, dim 1..4096,
+ * PQ centroids 2..256, PQ subvectors >= 2 and dividing dim. Set `relaxed` to skip
+ * the lower bounds (tests use tiny graphs; upper bounds always hold). */
+typedef struct sdb_params {
+  uint32_t dim;
+  int32_t metric;
+  uint32_t search_size;  /* L */
+  uint32_t degree_bound; /* R */
+  float alpha;
+  int32_t quantizer;
+  float bq_threshold;      /* NaN = unset: fit from the per-dimension mean (binary.go:145-185) */
+  int32_t bq_metric;       /* SDB_METRIC_HAMMING or _JACCARD */
+  uint32_t bq_trigger;     /* TriggerThreshold (models/quantizer.go:36) */
+  uint32_t pq_subvectors;  /* M */
+  uint32_t pq_centroids;   /* K */
+  uint32_t pq_trigger;     /* TriggerThreshold (models/quantizer.go:62) */
+  int32_t device;          /* CUDA ordinal */
+  int32_t relaxed;         /* 0 = enforce the reference's parameter ranges */
+} sdb_params;
+
+typedef struct sdb_index sdb_index;
+
+/* Thread-local message of the last failing call on this thread. */
+const char* sdb_last_error(void);
+int sdb_abi_version(void);
+/* Number of visible CUDA devices (0 if none / driver missing). */
+int sdb_device_count(void);
+
+/* ---- lifecycle: replaces vamana.NewIndexVamana (vamana.go:54-81) / flat.NewIndexFlat
+ * (flat.go:21-32). The index owns all device memory. ------------------------ */
+int sdb_index_create(const sdb_params* params, sdb_index** out);
+void sdb_index_destroy(sdb_index* ix);
+/* cache.Cachable.SizeInMemory (vamana.go:83-85): device bytes held. */
+int64_t sdb_index_size_bytes(const sdb_index* ix);
+/* Pre-size device arrays for node ids <= max_node_id. */
+int sdb_index_reserve(sdb_index* ix, uint64_t max_node_id);
+uint64_t sdb_index_max_node_id(const sdb_index* ix); /* vamana.go:47 */
+uint64_t sdb_index_count(const sdb_index* ix);       /* stored points incl. start node */
+
+/* ---- hydrate / flush: the GPU index mirrors the bucket keys n<id>v / n<id>e
+ * (node.go:85-135, plain.go:125-147); the diskstore stays in Go. -------------- */
+/* setupStartNode (vamana.go:93-120): the caller supplies node 1's vector. */
+int sdb_index_set_start(sdb_index* ix, const float* vec);
+/* VectorStore.Set for n points (plain.go:58-66, binary.go:131-139, product.go:161-169):
+ * stores raw vectors and, if the quantizer is fitted, their codes. No graph work. */
+int sdb_index_set_vectors(sdb_index* ix, uint64_t n, const uint64_t* ids, const float* vectors);
+/* Replace the edge lists of n nodes. edges = concatenated lists (the u64 payload of
+ * n<id>e, conversion.go:110-124), degrees[i] = length of list i (<= degreeBound). */
+int sdb_index_set_edges(sdb_index* ix, uint64_t n, const uint64_t* ids, const uint32_t* degrees,
+                        const uint64_t* edges);
+/* Read back edge lists; edges_out has n*degreeBound slots, list i at i*degreeBound. */
+int sdb_index_get_edges(sdb_index* ix, uint64_t n, const uint64_t* ids, uint32_t* degrees_out,
+                        uint64_t* edges_out);
+/* Read back raw vectors (n x dim). */
+int sdb_index_get_vectors(sdb_index* ix, uint64_t n, const uint64_t* ids, float* out);
+/* VectorStore.Delete + nodeStore.Delete bookkeeping (vamana.go:233-238): marks ids absent
+ * (edges pointing at them must already be gone). */
+int sdb_index_delete(sdb_index* ix, uint64_t n, const uint64_t* ids);
+
+/* ---- search: replaces IndexVamana.Search (vamana.go:278-310) for a batch of B queries.
+ * queries: B x dim. k = Limit, search_size = SearchSize (error if < k).
+ * filter_ids: optional ascending node ids shared by the batch (search.go:33-51,93-95).
+ * out_ids/out_dists: B x k, row b holds out_counts[b] results (start node removed,
+ * vamana.go:294-296), remaining slots id 0 / +inf. HybridScore = -dist*weight is left
+ * to the caller (vamana.go:303). */
+int sdb_search_batch(sdb_index* ix, uint32_t B, const float* queries, uint32_t k, uint32_t search_size,
+                     const uint64_t* filter_ids, uint64_t n_filter, uint64_t* out_ids, float* out_dists,
+                     uint32_t* out_counts);
+/* Same with device-resident queries/outputs; enqueues on `stream` (cudaStream_t). */
+int sdb_search_batch_device(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k, uint32_t search_size,
+                            uint64_t* d_out_ids, float* d_out_dists, uint32_t* d_out_counts, void* stream);
+/* Per-query counters of the most recent search on this handle (nodes expanded, distances
+ * evaluated): the terms of the algorithmic-bytes formula, SURVEY.md §8d. Synchronises. */
+int sdb_last_search_stats(sdb_index* ix, uint32_t B, uint32_t* hops_out, uint32_t* ndist_out);
+/* Total kernel launches issued by this handle so far (bench.py's gpu_launches). */
+uint64_t sdb_launch_count(const sdb_index* ix);
+/* Diagnostic twin of greedySearch's second return value (search.go:100): the visited
+ * list (expanded nodes, stably sorted by distance) for each query. vis_cap slots/query. */
+int sdb_search_visited(sdb_index* ix, uint32_t B, const float* queries, uint32_t search_size, uint32_t vis_cap,
+                       uint64_t* out_vis_ids, float* out_vis_dists, uint32_t* out_vis_len);
+
+/* ---- flat: replaces IndexFlat.Search (flat.go:76-132) for a batch. Scans ids >= 2 in
+ * ascending id order (the reference's Go-map order is unspecified; ties: lower id wins). */
+int sdb_flat_search_batch(sdb_index* ix, uint32_t B, const float* queries, uint32_t k, const uint64_t* filter_ids,
+                          uint64_t n_filter, uint64_t* out_ids, float* out_dists, uint32_t* out_counts);
+
+/* ---- insert: replaces IndexVamana.InsertUpdateDelete's insert branch (vamana.go:136-201,
+ * insert.go:16-68): greedySearch + robustPrune + back-edges for n new points, batched. */
+int sdb_insert_batch(sdb_index* ix, uint64_t n, const uint64_t* ids, const float* vectors);
+/* Mini-batch schedule of the batched insert: batch b has min(max_batch, max(min_batch,
+ * inserted_so_far / growth_div)) points. 0 keeps a field's default. */
+int sdb_insert_config(sdb_index* ix, uint32_t min_batch, uint32_t max_batch, uint32_t growth_div);
+
+/* ---- quantizers: replaces VectorStore.Fit (vamana.go:258): binaryQuantizer.Fit
+ * (binary.go:145-185) / productQuantizer.Fit (product.go:175-236). pq_first_row = index
+ * (in ascending id order) of the first k-means centre (kmeans.go:61 draws it at random).
+ * Returns via *fitted whether a fit happened (0 = skipped: already fitted / below trigger). */
+int sdb_index_fit(sdb_index* ix, uint64_t pq_first_row, int32_t* fitted);
+/* PQ state (product.go:36-37): flatCentroids M*K*sub, centroidDists M*K*K. */
+int sdb_index_get_pq(sdb_index* ix, float* flat_centroids, float* centroid_dists);
+int sdb_index_set_pq(sdb_index* ix, const float* flat_centroids, const float* centroid_dists);
+/* BQ threshold vector (binary.go:28), dim floats. */
+int sdb_index_get_bq_threshold(sdb_index* ix, float* threshold);
+int sdb_index_set_bq_threshold(sdb_index* ix, const float* threshold);
+/* Stored codes of n points: PQ -> M bytes each; BQ -> ceil(dim/64) u64 each (LE bytes). */
+int sdb_index_get_codes(sdb_index* ix, uint64_t n, const uint64_t* ids, uint8_t* out);
+
+/* ---- distance family (distance/distance.go:11-12 FloatDistFunc / BitDistFunc), batched:
+ * out[i] = dist(x[i], y[i]) for n pairs of dim floats / `words` u64 words. */
+int sdb_distance_float(int32_t metric, int32_t device, uint64_t n, uint32_t dim, const float* x, const float* y,
+                       float* out);
+int sdb_distance_bits(int32_t metric, int32_t device, uint64_t n, uint32_t words, const uint64_t* x,
+                      const uint64_t* y, float* out);
+/* Store-level closures, batched: DistanceFromFloat(query)(ids[i]) (plain.go:76, binary.go:187,
+ * product.go:238) and DistanceFromPoint(x)(ids[i]) (plain.go:87, binary.go:213, product.go:279). */
+int sdb_index_query_dists(sdb_index* ix, const float* query, uint64_t n, const uint64_t* ids, float* out);
+int sdb_index_point_dists(sdb_index* ix, uint64_t x, uint64_t n, const uint64_t* ids, float* out);
+/* binaryQuantizer.encode (binary.go:103-129) for n vectors; out n x ceil(dim/64) u64. */
+int sdb_bq_encode(int32_t device, uint64_t n, uint32_t dim, const float* vectors, const float* threshold,
+                  uint64_t* out);
+/* ADC table of DistanceFromFloat (product.go:255-263) for B queries: B x M x K floats. */
+int sdb_pq_adc_tables(sdb_index* ix, uint32_t B, const float* queries, float* out);
+
+/* ---- cross-shard merge: replaces the sort+truncate of ClusterNode.SearchPoints
+ * (cluster/actions.go:357-376). in_*: S x B x k (shard-major), counts S x B. Sorted by
+ * distance ascending (= HybridScore descending); ties: lower shard, then lower rank. */
+int sdb_merge_topk(int32_t device, uint32_t S, uint32_t B, uint32_t k, const uint64_t* in_ids,
+                   const float* in_dists, const uint32_t* in_counts, uint64_t* out_ids, float* out_dists,
+                   uint32_t* out_counts);
+int sdb_merge_topk_device(int32_t device, uint32_t S, uint32_t B, uint32_t k, const uint64_t* d_in_ids,
+                          const float* d_in_dists, const uint32_t* d_in_counts, uint64_t* d_out_ids,
+                          float* d_out_dists, uint32_t* d_out_counts, void* stream);
+/* Per-shard request limit (cluster/actions.go:291-299). Pure host arithmetic. */
+uint32_t sdb_shard_limit(uint32_t limit, uint32_t n_shards, uint32_t max_search_limit);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEMADB_B200_H */

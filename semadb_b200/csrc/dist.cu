@@ -1,0 +1,418 @@
+// dist.cu — the distance family as batched C-ABI calls (distance/distance.go:11-97), the
+// store-level closures DistanceFromFloat / DistanceFromPoint evaluated for id lists
+// (shard/vectorstore/plain.go:76-97, binary.go:187-234, product.go:238-305), the binary
+// encoder (binary.go:103-129), the PQ encoder (product.go:136-159), the ADC table builder
+// (product.go:255-263, K4) and the cross-shard top-k merge (cluster/actions.go:357-376, K6).
+#include "common.cuh"
+#include "index.cuh"
+
+namespace sdb {
+
+namespace {
+
+template <int METRIC>
+__global__ void pair_dist_kernel(const float* x, const float* y, uint32_t dim, uint64_t n, float* out) {
+  uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* a = x + i * dim;
+  const float* b = y + i * dim;
+  out[i] = (METRIC == METRIC_HAVERSINE) ? haversine_thread(a, b) : float_dist_thread<METRIC>(a, b, int(dim));
+}
+
+__global__ void pair_bits_kernel(int metric, const uint64_t* x, const uint64_t* y, uint32_t words, uint64_t n,
+                                 float* out) {
+  uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int a = 0, u = 0;
+  for (uint32_t w = 0; w < words; ++w) {
+    uint64_t xv = x[i * words + w], yv = y[i * words + w];
+    if (metric == METRIC_JACCARD) { a += __popcll(xv & yv); u += __popcll(xv | yv); }
+    else a += __popcll(xv ^ yv);
+  }
+  out[i] = bits_finish(metric, a, u);
+}
+
+// One warp per row: bit i%64 of word i/64 = v[i] > thr[i] (binary.go:123-127).
+__global__ void bq_encode_kernel(const float* src, size_t src_pitch, const uint32_t* row_ids /*or null*/,
+                                 const float* thr, uint32_t dim, uint32_t words, uint64_t* dst, size_t dst_pitch,
+                                 uint64_t n, bool dst_by_id) {
+  uint64_t r = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  uint64_t srow = row_ids ? row_ids[r] : r;
+  uint64_t drow = dst_by_id ? srow : r;
+  const float* v = src + srow * src_pitch;
+  for (uint32_t w = 0; w < dst_pitch; ++w) {
+    uint64_t word = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t i = w * 64 + h * 32 + lane;
+      bool on = (i < dim) && (v[i] > thr[i]);
+      word |= uint64_t(__ballot_sync(SDB_FULL, on)) << (32 * h);
+    }
+    if (lane == 0 && (w < words || dst_by_id)) dst[drow * dst_pitch + w] = word;
+  }
+}
+
+// productQuantizer.encode (product.go:136-159): one thread per (row, sub-vector); argmin
+// over K centroids with the index metric, strict '<' from MaxFloat32 (lowest index wins).
+template <int METRIC>
+__global__ void pq_encode_kernel(const float* vec, uint32_t pitch, const uint32_t* row_ids, uint32_t n,
+                                 const float* cent, uint32_t M, uint32_t K, uint32_t sub, uint8_t* codes,
+                                 uint32_t codes_pitch) {
+  uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= uint64_t(n) * M) return;
+  uint32_t r = uint32_t(t / M), m = uint32_t(t % M);
+  uint32_t id = row_ids[r];
+  const float* sv = vec + size_t(id) * pitch + m * sub;
+  float best = 3.402823466e+38f;
+  uint32_t bid = 0;
+  for (uint32_t j = 0; j < K; ++j) {
+    float d = float_dist_thread<METRIC>(sv, cent + (size_t(m) * K + j) * sub, int(sub));
+    if (d < best) { best = d; bid = j; }
+  }
+  codes[size_t(id) * codes_pitch + m] = uint8_t(bid);
+}
+
+// K4: ADC tables, dists[i*K+j] = distFn(x[i*sub:(i+1)*sub], centroid_ij) (product.go:255-263).
+template <int METRIC>
+__global__ void adc_table_kernel(const float* queries, uint32_t dim, uint32_t B, const float* cent, uint32_t M,
+                                 uint32_t K, uint32_t sub, float* out) {
+  uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  uint64_t per = uint64_t(M) * K;
+  if (t >= uint64_t(B) * per) return;
+  uint32_t b = uint32_t(t / per);
+  uint32_t mk = uint32_t(t % per);
+  uint32_t m = mk / K;
+  out[t] = float_dist_thread<METRIC>(queries + size_t(b) * dim + m * sub, cent + size_t(mk) * sub, int(sub));
+}
+
+// DistanceFromFloat(query)(id) for a list of ids; mode 0 float, 1 bits, 2 adc.
+template <int METRIC>
+__global__ void query_dists_float_kernel(const float* vec, uint32_t pitch, const float* q, uint32_t dim,
+                                         const uint32_t* ids, uint64_t n, float* out) {
+  uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* y = vec + size_t(ids[i]) * pitch;
+  out[i] = (METRIC == METRIC_HAVERSINE) ? haversine_thread(q, y) : float_dist_thread<METRIC>(q, y, int(dim));
+}
+__global__ void query_dists_bits_kernel(int metric, const uint64_t* bits, uint32_t pitch, uint32_t words,
+                                        const uint64_t* qb, const uint32_t* ids, uint64_t n, float* out) {
+  uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t* y = bits + size_t(ids[i]) * pitch;
+  int a = 0, u = 0;
+  for (uint32_t w = 0; w < words; ++w) {
+    if (metric == METRIC_JACCARD) { a += __popcll(qb[w] & y[w]); u += __popcll(qb[w] | y[w]); }
+    else a += __popcll(qb[w] ^ y[w]);
+  }
+  out[i] = bits_finish(metric, a, u);
+}
+__global__ void query_dists_adc_kernel(const uint8_t* codes, uint32_t pitch, const float* table, uint32_t M,
+                                       uint32_t K, const uint32_t* ids, uint64_t n, float* out) {
+  uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* c = codes + size_t(ids[i]) * pitch;
+  float d = 0.0f;
+  for (uint32_t m = 0; m < M; ++m) d = __fadd_rn(d, table[m * K + c[m]]);
+  out[i] = d;
+}
+// DistanceFromPoint(x)(id): SDC for fitted PQ (product.go:299-303)
+__global__ void point_dists_sdc_kernel(const uint8_t* codes, uint32_t pitch, const float* cdist, uint32_t M,
+                                       uint32_t K, uint32_t x, const uint32_t* ids, uint64_t n, float* out) {
+  uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* cx = codes + size_t(x) * pitch;
+  const uint8_t* cy = codes + size_t(ids[i]) * pitch;
+  float d = 0.0f;
+  for (uint32_t m = 0; m < M; ++m) d = __fadd_rn(d, cdist[(size_t(m) * K + cx[m]) * K + cy[m]]);
+  out[i] = d;
+}
+
+// K6: one thread per query merges S sorted lists; stable by (dist asc, shard asc, rank asc).
+__global__ void merge_topk_kernel(uint32_t S, uint32_t B, uint32_t k, const uint64_t* in_ids, const float* in_d,
+                                  const uint32_t* in_c, uint64_t* out_ids, float* out_d, uint32_t* out_c) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  uint32_t heads[64];  // S <= 64 (checked by launch_merge)
+  for (uint32_t s = 0; s < S; ++s) heads[s] = 0;
+  uint32_t n = 0;
+  for (; n < k; ++n) {
+    int best = -1;
+    float bd = 0.0f;
+    for (uint32_t s = 0; s < S; ++s) {
+      uint32_t c = min(in_c[size_t(s) * B + b], k);
+      if (heads[s] >= c) continue;
+      float d = in_d[(size_t(s) * B + b) * k + heads[s]];
+      // HybridScore = -d descending == d ascending; strict '<' keeps the lower shard on ties
+      if (best < 0 || d < bd) { best = int(s); bd = d; }
+    }
+    if (best < 0) break;
+    out_ids[size_t(b) * k + n] = in_ids[(size_t(best) * B + b) * k + heads[best]];
+    out_d[size_t(b) * k + n] = bd;
+    heads[best]++;
+  }
+  out_c[b] = n;
+  for (uint32_t j = n; j < k; ++j) {
+    out_ids[size_t(b) * k + j] = 0;
+    out_d[size_t(b) * k + j] = __int_as_float(0x7f800000);
+  }
+}
+
+int set_device_checked(int device) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(SDB_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  }
+  if (device < 0 || device >= ndev) return fail(SDB_ERR_INVALID, "device ordinal out of range");
+  SDB_CUDA(cudaSetDevice(device));
+  return SDB_OK;
+}
+
+struct TmpDev {
+  void* p = nullptr;
+  ~TmpDev() { if (p) cudaFree(p); }
+  int alloc(size_t bytes) {
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(tmp)");
+    return SDB_OK;
+  }
+};
+
+}  // namespace
+
+int launch_encode_rows(sdb_index* ix, uint32_t n, const uint32_t* d_ids, cudaStream_t stream) {
+  if (n == 0) return SDB_OK;
+  if (ix->p.quantizer == SDB_QUANT_BINARY && ix->bq_fitted) {
+    uint32_t threads = 128, rows_per_block = threads / 32;
+    bq_encode_kernel<<<(n + rows_per_block - 1) / rows_per_block, threads, 0, stream>>>(
+        ix->d_vec, ix->vec_pitch, d_ids, ix->d_bq_thr, ix->p.dim, ix->words, ix->d_bits, ix->bits_pitch, n, true);
+    ix->launches++;
+    SDB_CUDA(cudaGetLastError());
+  } else if (ix->p.quantizer == SDB_QUANT_PRODUCT && ix->pq_fitted) {
+    uint64_t total = uint64_t(n) * ix->pqM;
+    uint32_t blocks = uint32_t((total + 127) / 128);
+    switch (ix->store_metric) {
+      case SDB_METRIC_EUCLIDEAN:
+        pq_encode_kernel<METRIC_EUCLIDEAN><<<blocks, 128, 0, stream>>>(ix->d_vec, ix->vec_pitch, d_ids, n, ix->d_pq_centroids, ix->pqM, ix->pqK, ix->pqSub, ix->d_codes, ix->codes_pitch);
+        break;
+      case SDB_METRIC_DOT:
+        pq_encode_kernel<METRIC_DOT><<<blocks, 128, 0, stream>>>(ix->d_vec, ix->vec_pitch, d_ids, n, ix->d_pq_centroids, ix->pqM, ix->pqK, ix->pqSub, ix->d_codes, ix->codes_pitch);
+        break;
+      default: return fail(SDB_ERR_INTERNAL, "unexpected PQ metric");
+    }
+    ix->launches++;
+    SDB_CUDA(cudaGetLastError());
+  }
+  return SDB_OK;
+}
+
+int launch_adc_tables(sdb_index* ix, uint32_t B, const float* d_queries, float* d_out, cudaStream_t stream) {
+  uint64_t total = uint64_t(B) * ix->pqM * ix->pqK;
+  uint32_t blocks = uint32_t((total + 255) / 256);
+  if (ix->store_metric == SDB_METRIC_EUCLIDEAN)
+    adc_table_kernel<METRIC_EUCLIDEAN><<<blocks, 256, 0, stream>>>(d_queries, ix->p.dim, B, ix->d_pq_centroids, ix->pqM, ix->pqK, ix->pqSub, d_out);
+  else if (ix->store_metric == SDB_METRIC_DOT)
+    adc_table_kernel<METRIC_DOT><<<blocks, 256, 0, stream>>>(d_queries, ix->p.dim, B, ix->d_pq_centroids, ix->pqM, ix->pqK, ix->pqSub, d_out);
+  else return fail(SDB_ERR_INTERNAL, "unexpected PQ metric");
+  ix->launches++;
+  SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+
+int launch_merge(uint32_t S, uint32_t B, uint32_t k, const uint64_t* in_ids, const float* in_d, const uint32_t* in_c,
+                 uint64_t* out_ids, float* out_d, uint32_t* out_c, cudaStream_t stream) {
+  if (S == 0 || S > 64) return fail(SDB_ERR_INVALID, "merge supports 1..64 shards");
+  merge_topk_kernel<<<(B + 127) / 128, 128, 0, stream>>>(S, B, k, in_ids, in_d, in_c, out_ids, out_d, out_c);
+  SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+
+}  // namespace sdb
+
+using namespace sdb;
+
+extern "C" {
+
+int sdb_distance_float(int32_t metric, int32_t device, uint64_t n, uint32_t dim, const float* x, const float* y,
+                       float* out) {
+  if (n == 0) return SDB_OK;
+  if (!x || !y || !out || dim == 0) return fail(SDB_ERR_INVALID, "null argument");
+  if (metric == SDB_METRIC_HAVERSINE && dim != 2) return fail(SDB_ERR_INVALID, "haversine needs dim 2");
+  int rc = set_device_checked(device);
+  if (rc) return rc;
+  TmpDev dx, dy, dout;
+  size_t bytes = size_t(n) * dim * sizeof(float);
+  if ((rc = dx.alloc(bytes)) || (rc = dy.alloc(bytes)) || (rc = dout.alloc(n * sizeof(float)))) return rc;
+  SDB_CUDA(cudaMemcpy(dx.p, x, bytes, cudaMemcpyHostToDevice));
+  SDB_CUDA(cudaMemcpy(dy.p, y, bytes, cudaMemcpyHostToDevice));
+  uint32_t blocks = uint32_t((n + 127) / 128);
+  const float* a = static_cast<const float*>(dx.p);
+  const float* b = static_cast<const float*>(dy.p);
+  float* o = static_cast<float*>(dout.p);
+  switch (metric) {
+    case SDB_METRIC_EUCLIDEAN: pair_dist_kernel<METRIC_EUCLIDEAN><<<blocks, 128>>>(a, b, dim, n, o); break;
+    case SDB_METRIC_DOT: pair_dist_kernel<METRIC_DOT><<<blocks, 128>>>(a, b, dim, n, o); break;
+    case SDB_METRIC_COSINE: pair_dist_kernel<METRIC_COSINE><<<blocks, 128>>>(a, b, dim, n, o); break;
+    case SDB_METRIC_HAVERSINE: pair_dist_kernel<METRIC_HAVERSINE><<<blocks, 128>>>(a, b, dim, n, o); break;
+    default: return fail(SDB_ERR_INVALID, "unknown float32 distance function");  // distance.go:82
+  }
+  SDB_CUDA(cudaGetLastError());
+  SDB_CUDA(cudaMemcpy(out, dout.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return SDB_OK;
+}
+
+int sdb_distance_bits(int32_t metric, int32_t device, uint64_t n, uint32_t words, const uint64_t* x,
+                      const uint64_t* y, float* out) {
+  if (n == 0) return SDB_OK;
+  if (!x || !y || !out) return fail(SDB_ERR_INVALID, "null argument");
+  if (metric != SDB_METRIC_HAMMING && metric != SDB_METRIC_JACCARD) return fail(SDB_ERR_INVALID, "unknown bit distance function");  // distance.go:95
+  int rc = set_device_checked(device);
+  if (rc) return rc;
+  TmpDev dx, dy, dout;
+  size_t bytes = size_t(n) * words * 8;
+  if ((rc = dx.alloc(bytes)) || (rc = dy.alloc(bytes)) || (rc = dout.alloc(n * sizeof(float)))) return rc;
+  SDB_CUDA(cudaMemcpy(dx.p, x, bytes, cudaMemcpyHostToDevice));
+  SDB_CUDA(cudaMemcpy(dy.p, y, bytes, cudaMemcpyHostToDevice));
+  pair_bits_kernel<<<uint32_t((n + 127) / 128), 128>>>(metric, static_cast<const uint64_t*>(dx.p), static_cast<const uint64_t*>(dy.p), words, n, static_cast<float*>(dout.p));
+  SDB_CUDA(cudaGetLastError());
+  SDB_CUDA(cudaMemcpy(out, dout.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return SDB_OK;
+}
+
+int sdb_bq_encode(int32_t device, uint64_t n, uint32_t dim, const float* vectors, const float* threshold,
+                  uint64_t* out) {
+  if (n == 0) return SDB_OK;
+  if (!vectors || !threshold || !out || dim == 0) return fail(SDB_ERR_INVALID, "null argument");
+  int rc = set_device_checked(device);
+  if (rc) return rc;
+  uint32_t words = (dim + 63) / 64;
+  TmpDev dv, dt, dout;
+  if ((rc = dv.alloc(size_t(n) * dim * 4)) || (rc = dt.alloc(size_t(dim) * 4)) || (rc = dout.alloc(size_t(n) * words * 8))) return rc;
+  SDB_CUDA(cudaMemcpy(dv.p, vectors, size_t(n) * dim * 4, cudaMemcpyHostToDevice));
+  SDB_CUDA(cudaMemcpy(dt.p, threshold, size_t(dim) * 4, cudaMemcpyHostToDevice));
+  bq_encode_kernel<<<uint32_t((n + 3) / 4), 128>>>(static_cast<const float*>(dv.p), dim, nullptr, static_cast<const float*>(dt.p), dim, words, static_cast<uint64_t*>(dout.p), words, n, false);
+  SDB_CUDA(cudaGetLastError());
+  SDB_CUDA(cudaMemcpy(out, dout.p, size_t(n) * words * 8, cudaMemcpyDeviceToHost));
+  return SDB_OK;
+}
+
+static int stage_id_list(sdb_index* ix, uint64_t n, const uint64_t* ids) {
+  std::vector<uint32_t> h(n);
+  for (uint64_t i = 0; i < n; ++i) {
+    // a point of the wrong type yields MaxFloat32 in the reference (plain.go:78-82); an id
+    // that is not stored is an error here
+    if (ids[i] >= ix->rows || !ix->h_exists[ids[i]]) return fail(SDB_ERR_NOTFOUND, "node id does not exist: " + std::to_string(ids[i]));
+    h[i] = uint32_t(ids[i]);
+  }
+  int rc = ix->d_tmp32.ensure(n + 1);
+  if (rc) return rc;
+  SDB_CUDA(cudaMemcpy(ix->d_tmp32.p, h.data(), n * 4, cudaMemcpyHostToDevice));
+  return SDB_OK;
+}
+
+int sdb_index_query_dists(sdb_index* ix, const float* query, uint64_t n, const uint64_t* ids, float* out) {
+  if (!ix || !query || (n && (!ids || !out))) return fail(SDB_ERR_INVALID, "null argument");
+  if (n == 0) return SDB_OK;
+  std::lock_guard<std::mutex> g(ix->mu);
+  SDB_CUDA(cudaSetDevice(ix->device));
+  int rc = stage_id_list(ix, n, ids);
+  if (rc) return rc;
+  if ((rc = ix->d_q.ensure(ix->p.dim))) return rc;
+  if ((rc = ix->d_tmpf.ensure(n))) return rc;
+  SDB_CUDA(cudaMemcpyAsync(ix->d_q.p, query, ix->p.dim * 4, cudaMemcpyHostToDevice, ix->stream));
+  uint32_t blocks = uint32_t((n + 127) / 128);
+  if (ix->p.quantizer == SDB_QUANT_BINARY && ix->bq_fitted) {
+    if ((rc = ix->d_ids64.ensure(ix->bits_pitch))) return rc;
+    bq_encode_kernel<<<1, 32, 0, ix->stream>>>(ix->d_q.p, ix->p.dim, nullptr, ix->d_bq_thr, ix->p.dim, ix->words, ix->d_ids64.p, ix->bits_pitch, 1, true);
+    query_dists_bits_kernel<<<blocks, 128, 0, ix->stream>>>(ix->bq_metric, ix->d_bits, ix->bits_pitch, ix->words, ix->d_ids64.p, ix->d_tmp32.p, n, ix->d_tmpf.p);
+    ix->launches += 2;
+  } else if (ix->p.quantizer == SDB_QUANT_PRODUCT && ix->pq_fitted) {
+    if ((rc = ix->d_adc.ensure(size_t(ix->pqM) * ix->pqK))) return rc;
+    if ((rc = launch_adc_tables(ix, 1, ix->d_q.p, ix->d_adc.p, ix->stream))) return rc;
+    query_dists_adc_kernel<<<blocks, 128, 0, ix->stream>>>(ix->d_codes, ix->codes_pitch, ix->d_adc.p, ix->pqM, ix->pqK, ix->d_tmp32.p, n, ix->d_tmpf.p);
+    ix->launches++;
+  } else {
+    switch (ix->store_metric) {
+      case SDB_METRIC_EUCLIDEAN: query_dists_float_kernel<METRIC_EUCLIDEAN><<<blocks, 128, 0, ix->stream>>>(ix->d_vec, ix->vec_pitch, ix->d_q.p, ix->p.dim, ix->d_tmp32.p, n, ix->d_tmpf.p); break;
+      case SDB_METRIC_DOT: query_dists_float_kernel<METRIC_DOT><<<blocks, 128, 0, ix->stream>>>(ix->d_vec, ix->vec_pitch, ix->d_q.p, ix->p.dim, ix->d_tmp32.p, n, ix->d_tmpf.p); break;
+      case SDB_METRIC_COSINE: query_dists_float_kernel<METRIC_COSINE><<<blocks, 128, 0, ix->stream>>>(ix->d_vec, ix->vec_pitch, ix->d_q.p, ix->p.dim, ix->d_tmp32.p, n, ix->d_tmpf.p); break;
+      case SDB_METRIC_HAVERSINE: query_dists_float_kernel<METRIC_HAVERSINE><<<blocks, 128, 0, ix->stream>>>(ix->d_vec, ix->vec_pitch, ix->d_q.p, ix->p.dim, ix->d_tmp32.p, n, ix->d_tmpf.p); break;
+      default: return fail(SDB_ERR_INVALID, "metric has no float distance");
+    }
+    ix->launches++;
+  }
+  SDB_CUDA(cudaGetLastError());
+  SDB_CUDA(cudaMemcpyAsync(out, ix->d_tmpf.p, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+  SDB_CUDA(cudaStreamSynchronize(ix->stream));
+  return SDB_OK;
+}
+
+int sdb_index_point_dists(sdb_index* ix, uint64_t x, uint64_t n, const uint64_t* ids, float* out) {
+  if (!ix || (n && (!ids || !out))) return fail(SDB_ERR_INVALID, "null argument");
+  if (n == 0) return SDB_OK;
+  std::lock_guard<std::mutex> g(ix->mu);
+  SDB_CUDA(cudaSetDevice(ix->device));
+  if (x >= ix->rows || !ix->h_exists[x]) return fail(SDB_ERR_NOTFOUND, "node id does not exist: " + std::to_string(x));
+  int rc = stage_id_list(ix, n, ids);
+  if (rc) return rc;
+  if ((rc = ix->d_tmpf.ensure(n))) return rc;
+  uint32_t blocks = uint32_t((n + 127) / 128);
+  if (ix->p.quantizer == SDB_QUANT_BINARY && ix->bq_fitted) {
+    query_dists_bits_kernel<<<blocks, 128, 0, ix->stream>>>(ix->bq_metric, ix->d_bits, ix->bits_pitch, ix->words, ix->d_bits + size_t(x) * ix->bits_pitch, ix->d_tmp32.p, n, ix->d_tmpf.p);
+  } else if (ix->p.quantizer == SDB_QUANT_PRODUCT && ix->pq_fitted) {
+    point_dists_sdc_kernel<<<blocks, 128, 0, ix->stream>>>(ix->d_codes, ix->codes_pitch, ix->d_pq_cdist, ix->pqM, ix->pqK, uint32_t(x), ix->d_tmp32.p, n, ix->d_tmpf.p);
+  } else {
+    const float* xv = ix->d_vec + size_t(x) * ix->vec_pitch;
+    switch (ix->store_metric) {
+      case SDB_METRIC_EUCLIDEAN: query_dists_float_kernel<METRIC_EUCLIDEAN><<<blocks, 128, 0, ix->stream>>>(ix->d_vec, ix->vec_pitch, xv, ix->p.dim, ix->d_tmp32.p, n, ix->d_tmpf.p); break;
+      case SDB_METRIC_DOT: query_dists_float_kernel<METRIC_DOT><<<blocks, 128, 0, ix->stream>>>(ix->d_vec, ix->vec_pitch, xv, ix->p.dim, ix->d_tmp32.p, n, ix->d_tmpf.p); break;
+      case SDB_METRIC_COSINE: query_dists_float_kernel<METRIC_COSINE><<<blocks, 128, 0, ix->stream>>>(ix->d_vec, ix->vec_pitch, xv, ix->p.dim, ix->d_tmp32.p, n, ix->d_tmpf.p); break;
+      case SDB_METRIC_HAVERSINE: query_dists_float_kernel<METRIC_HAVERSINE><<<blocks, 128, 0, ix->stream>>>(ix->d_vec, ix->vec_pitch, xv, ix->p.dim, ix->d_tmp32.p, n, ix->d_tmpf.p); break;
+      default: return fail(SDB_ERR_INVALID, "metric has no float distance");
+    }
+  }
+  ix->launches++;
+  SDB_CUDA(cudaGetLastError());
+  SDB_CUDA(cudaMemcpyAsync(out, ix->d_tmpf.p, n * 4, cudaMemcpyDeviceToHost, ix->stream));
+  SDB_CUDA(cudaStreamSynchronize(ix->stream));
+  return SDB_OK;
+}
+
+int sdb_merge_topk_device(int32_t device, uint32_t S, uint32_t B, uint32_t k, const uint64_t* d_in_ids,
+                          const float* d_in_dists, const uint32_t* d_in_counts, uint64_t* d_out_ids,
+                          float* d_out_dists, uint32_t* d_out_counts, void* stream) {
+  if (B == 0) return SDB_OK;
+  if (!d_in_ids || !d_in_dists || !d_in_counts || !d_out_ids || !d_out_dists || !d_out_counts) return fail(SDB_ERR_INVALID, "null argument");
+  if (k < 1 || k > 75) return fail(SDB_ERR_INVALID, "invalid limit");
+  int rc = set_device_checked(device);
+  if (rc) return rc;
+  return launch_merge(S, B, k, d_in_ids, d_in_dists, d_in_counts, d_out_ids, d_out_dists, d_out_counts, static_cast<cudaStream_t>(stream));
+}
+
+int sdb_merge_topk(int32_t device, uint32_t S, uint32_t B, uint32_t k, const uint64_t* in_ids, const float* in_dists,
+                   const uint32_t* in_counts, uint64_t* out_ids, float* out_dists, uint32_t* out_counts) {
+  if (B == 0) return SDB_OK;
+  if (!in_ids || !in_dists || !in_counts || !out_ids || !out_dists || !out_counts) return fail(SDB_ERR_INVALID, "null argument");
+  if (k < 1 || k > 75) return fail(SDB_ERR_INVALID, "invalid limit");
+  int rc = set_device_checked(device);
+  if (rc) return rc;
+  size_t n = size_t(S) * B * k;
+  TmpDev di, dd, dc, oi, od, oc;
+  if ((rc = di.alloc(n * 8)) || (rc = dd.alloc(n * 4)) || (rc = dc.alloc(size_t(S) * B * 4)) ||
+      (rc = oi.alloc(size_t(B) * k * 8)) || (rc = od.alloc(size_t(B) * k * 4)) || (rc = oc.alloc(size_t(B) * 4))) return rc;
+  SDB_CUDA(cudaMemcpy(di.p, in_ids, n * 8, cudaMemcpyHostToDevice));
+  SDB_CUDA(cudaMemcpy(dd.p, in_dists, n * 4, cudaMemcpyHostToDevice));
+  SDB_CUDA(cudaMemcpy(dc.p, in_counts, size_t(S) * B * 4, cudaMemcpyHostToDevice));
+  rc = launch_merge(S, B, k, static_cast<uint64_t*>(di.p), static_cast<float*>(dd.p), static_cast<uint32_t*>(dc.p),
+                    static_cast<uint64_t*>(oi.p), static_cast<float*>(od.p), static_cast<uint32_t*>(oc.p), nullptr);
+  if (rc) return rc;
+  SDB_CUDA(cudaMemcpy(out_ids, oi.p, size_t(B) * k * 8, cudaMemcpyDeviceToHost));
+  SDB_CUDA(cudaMemcpy(out_dists, od.p, size_t(B) * k * 4, cudaMemcpyDeviceToHost));
+  SDB_CUDA(cudaMemcpy(out_counts, oc.p, size_t(B) * 4, cudaMemcpyDeviceToHost));
+  return SDB_OK;
+}
+
+}  // extern "C"

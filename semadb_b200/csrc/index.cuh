@@ -1,0 +1,149 @@
+// index.cuh — the device-resident index behind an sdb_index handle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cmath>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/semadb_b200.h"
+
+namespace sdb {
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define SDB_CUDA(expr)                                         \
+  do {                                                         \
+    cudaError_t _e = (expr);                                   \
+    if (_e != cudaSuccess) return ::sdb::cuda_fail(_e, #expr); \
+  } while (0)
+
+template <class T>
+struct DevBuf {  // grow-only device scratch
+  T* p = nullptr;
+  size_t n = 0;
+  int ensure(size_t want) {
+    if (want <= n) return SDB_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    size_t cap = want + want / 4 + 64;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), cap * sizeof(T));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)");
+    n = cap;
+    return SDB_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+template <class T>
+struct PinBuf {  // grow-only pinned host staging
+  T* p = nullptr;
+  size_t n = 0;
+  int ensure(size_t want) {
+    if (want <= n) return SDB_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
+    size_t cap = want + want / 4 + 64;
+    cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&p), cap * sizeof(T));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost(staging)");
+    n = cap;
+    return SDB_OK;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+}  // namespace sdb
+
+// Data layout in HBM (all row-indexed by node id; row 0 unused, row 1 = start node):
+//   vec   [rows][vec_pitch]   f32, vec_pitch = dim rounded up to 4 floats (16-byte rows;
+//                              512-byte aligned rows when dim = 128)
+//   bits  [rows][bits_pitch]  u64, bits_pitch = ceil(dim/64) rounded up to 2 (binary store)
+//   codes [rows][codes_pitch] u8,  codes_pitch = M rounded up to 16 (product store)
+//   adj   [rows][R]           u32, unused slots = 0xFFFFFFFF
+//   deg   [rows]              u32
+//   exists[rows]              u8
+struct sdb_index {
+  sdb_params p{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+  mutable std::mutex mu;
+
+  uint32_t rows = 0;  // allocated rows
+  uint32_t vec_pitch = 0, bits_pitch = 0, words = 0, codes_pitch = 0;
+  float* d_vec = nullptr;
+  uint64_t* d_bits = nullptr;
+  uint8_t* d_codes = nullptr;
+  uint32_t* d_adj = nullptr;
+  uint32_t* d_deg = nullptr;
+  uint8_t* d_exists = nullptr;
+  std::vector<uint8_t> h_exists;
+  uint64_t count = 0;
+  uint32_t max_node_id = 0;
+
+  // quantizer state
+  int store_metric = 0;  // metric used by float distances of the store (PQ: cosine -> euclidean)
+  bool bq_fitted = false;
+  float* d_bq_thr = nullptr;
+  int bq_metric = SDB_METRIC_HAMMING;
+  uint32_t pqM = 0, pqK = 0, pqSub = 0;
+  bool pq_fitted = false;
+  float* d_pq_centroids = nullptr;  // [M][K][sub]
+  float* d_pq_cdist = nullptr;      // [M][K][K]
+
+  // scratch
+  sdb::DevBuf<float> d_q;
+  sdb::DevBuf<uint64_t> d_oid;
+  sdb::DevBuf<float> d_od;
+  sdb::DevBuf<uint32_t> d_oc, d_hops, d_ndist;
+  sdb::DevBuf<uint32_t> d_work;
+  sdb::DevBuf<float> d_adc;
+  sdb::DevBuf<uint32_t> d_filter_seed, d_filter_bits;
+  sdb::DevBuf<uint32_t> d_vis_ids, d_vis_len;
+  sdb::DevBuf<float> d_vis_d;
+  sdb::DevBuf<uint64_t> d_ids64;
+  sdb::DevBuf<uint32_t> d_tmp32;
+  sdb::DevBuf<float> d_tmpf;
+  sdb::DevBuf<uint8_t> d_tmp8;
+  sdb::PinBuf<uint8_t> h_stage;
+  uint32_t last_B = 0;
+  uint64_t launches = 0;
+
+  // insert schedule
+  uint32_t ins_min_batch = 1, ins_max_batch = 4096, ins_growth_div = 16;
+
+  bool quant_active() const {
+    return (p.quantizer == SDB_QUANT_BINARY && bq_fitted) || (p.quantizer == SDB_QUANT_PRODUCT && pq_fitted);
+  }
+};
+
+namespace sdb {
+int index_reserve_locked(sdb_index* ix, uint64_t max_node_id);
+int launch_search(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k, uint32_t L, uint64_t* d_out_ids,
+                  float* d_out_dists, uint32_t* d_out_counts, uint32_t* d_vis_ids, float* d_vis_dists,
+                  uint32_t* d_vis_len, uint32_t vis_cap, const uint32_t* d_filter_seed, uint32_t n_filter_seed,
+                  const uint32_t* d_filter_bits, cudaStream_t stream);
+int launch_flat(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k, const uint32_t* d_filter_bits,
+                uint64_t* d_out_ids, float* d_out_dists, uint32_t* d_out_counts, cudaStream_t stream);
+int launch_encode_rows(sdb_index* ix, uint32_t n, const uint32_t* d_ids, cudaStream_t stream);
+int launch_adc_tables(sdb_index* ix, uint32_t B, const float* d_queries, float* d_out, cudaStream_t stream);
+int launch_merge(uint32_t S, uint32_t B, uint32_t k, const uint64_t* in_ids, const float* in_d, const uint32_t* in_c,
+                 uint64_t* out_ids, float* out_d, uint32_t* out_c, cudaStream_t stream);
+int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const float* vectors);
+int fit_locked(sdb_index* ix, uint64_t pq_first_row, int32_t* fitted);
+}  // namespace sdb

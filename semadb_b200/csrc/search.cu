@@ -1,0 +1,150 @@
+// search.cu — dispatch of the beam-search kernel variants (search.cuh).
+#include "search.cuh"
+
+#include "index.cuh"
+
+namespace sdb {
+
+namespace {
+
+struct LaunchPlan {
+  int warps_per_cta = 1;
+  int ctas_per_sm = 1;
+  size_t smem = 0;
+};
+
+template <int KIND, int METRIC, int TRIPS, int UNROLL, int HBITS, bool FILTER, bool RETRY>
+int launch_variant(sdb_index* ix, const SearchArgs& a, cudaStream_t stream) {
+  auto kern = beam_search_kernel<KIND, METRIC, TRIPS, UNROLL, HBITS, FILTER, RETRY>;
+  const uint32_t qfloats = (KIND == EVAL_ADC) ? 0 : (a.dim + 3) / 4 * 4;
+  const uint32_t qwords = (KIND == EVAL_BITS) ? a.bits_pitch : 0;
+  const size_t per_warp = warp_smem_bytes<HBITS>(qfloats, qwords);
+  static thread_local int cached_dev = -1;
+  static thread_local LaunchPlan plan;
+  static thread_local size_t plan_per_warp = 0;
+  if (cached_dev != ix->device || plan_per_warp != per_warp) {
+    LaunchPlan best;
+    int best_warps = 0;
+    for (int w : {1, 2, 4}) {
+      size_t smem = per_warp * w;
+      if (smem > ix->smem_optin) continue;
+      SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      int nb = 0;
+      SDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32 * w, smem));
+      if (nb * w > best_warps) {
+        best_warps = nb * w;
+        best.warps_per_cta = w;
+        best.ctas_per_sm = nb;
+        best.smem = smem;
+      }
+    }
+    if (best_warps == 0) return fail(SDB_ERR_INTERNAL, "beam search kernel does not fit in shared memory");
+    SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(best.smem)));
+    plan = best;
+    plan_per_warp = per_warp;
+    cached_dev = ix->device;
+  }
+  uint32_t resident = uint32_t(ix->sm_count) * plan.ctas_per_sm;
+  uint32_t need = RETRY ? uint32_t(ix->sm_count) : (a.B + plan.warps_per_cta - 1) / plan.warps_per_cta;
+  uint32_t grid = need < resident ? need : resident;
+  if (grid == 0) grid = 1;
+  kern<<<grid, 32 * plan.warps_per_cta, plan.smem, stream>>>(a, qfloats, qwords);
+  ix->launches++;
+  SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
+}
+
+template <int KIND, int METRIC, int TRIPS, int UNROLL, bool FILTER>
+int launch_with_retry(sdb_index* ix, SearchArgs a, cudaStream_t stream) {
+  int rc = launch_variant<KIND, METRIC, TRIPS, UNROLL, 13, FILTER, false>(ix, a, stream);
+  if (rc) return rc;
+  // second pass over queries whose visited table overflowed (normally none): 32768 slots
+  a.work_counter = a.work_counter + 2;
+  constexpr int RK = (KIND == EVAL_FLOAT_FIXED) ? EVAL_FLOAT_GENERIC : KIND;
+  return launch_variant<RK, METRIC, 1, 1, 15, FILTER, true>(ix, a, stream);
+}
+
+template <int METRIC>
+int launch_float(sdb_index* ix, const SearchArgs& a, bool filtered, cudaStream_t stream) {
+  if (filtered) return launch_with_retry<EVAL_FLOAT_GENERIC, METRIC, 1, 1, true>(ix, a, stream);
+  if (a.dim % 32 == 0) {
+    switch (a.dim / 32) {
+      case 4: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 4, 8, false>(ix, a, stream);
+      case 8: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 8, 4, false>(ix, a, stream);
+      case 12: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 12, 3, false>(ix, a, stream);
+      case 24: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 24, 1, false>(ix, a, stream);
+      default: break;
+    }
+  }
+  return launch_with_retry<EVAL_FLOAT_GENERIC, METRIC, 1, 1, false>(ix, a, stream);
+}
+
+}  // namespace
+
+int launch_search(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k, uint32_t L, uint64_t* d_out_ids,
+                  float* d_out_dists, uint32_t* d_out_counts, uint32_t* d_vis_ids, float* d_vis_dists,
+                  uint32_t* d_vis_len, uint32_t vis_cap, const uint32_t* d_filter_seed, uint32_t n_filter_seed,
+                  const uint32_t* d_filter_bits, cudaStream_t stream) {
+  int rc;
+  if ((rc = ix->d_hops.ensure(B))) return rc;
+  if ((rc = ix->d_ndist.ensure(B))) return rc;
+  if ((rc = ix->d_work.ensure(4 + size_t(B)))) return rc;
+  SDB_CUDA(cudaMemsetAsync(ix->d_work.p, 0, 4 * sizeof(uint32_t), stream));
+  SearchArgs a{};
+  a.vec = ix->d_vec;
+  a.vec_pitch = ix->vec_pitch;
+  a.bits = ix->d_bits;
+  a.bits_pitch = ix->bits_pitch;
+  a.words = ix->words;
+  a.codes = ix->d_codes;
+  a.codes_pitch = ix->codes_pitch;
+  a.pqM = ix->pqM;
+  a.pqK = ix->pqK;
+  a.bq_thr = ix->d_bq_thr;
+  a.bit_metric = ix->bq_metric;
+  a.adj = ix->d_adj;
+  a.R = ix->p.degree_bound;
+  a.rows = ix->rows;
+  a.queries = d_queries;
+  a.dim = ix->p.dim;
+  a.B = B;
+  a.L = L;
+  a.k = k;
+  a.out_ids = d_out_ids;
+  a.out_dists = d_out_dists;
+  a.out_counts = d_out_counts;
+  a.out_hops = ix->d_hops.p;
+  a.out_ndist = ix->d_ndist.p;
+  a.vis_ids = d_vis_ids;
+  a.vis_dists = d_vis_dists;
+  a.vis_len = d_vis_len;
+  a.vis_cap = vis_cap;
+  a.filter_seed = d_filter_seed;
+  a.n_filter_seed = n_filter_seed;
+  a.filter_bits = d_filter_bits;
+  a.work_counter = ix->d_work.p;
+  a.retry_count = ix->d_work.p + 1;
+  a.retry_list = ix->d_work.p + 4;
+  ix->last_B = B;
+  const bool filtered = d_filter_bits != nullptr;
+
+  if (ix->p.quantizer == SDB_QUANT_BINARY && ix->bq_fitted) {
+    return filtered ? launch_with_retry<EVAL_BITS, 0, 1, 1, true>(ix, a, stream)
+                    : launch_with_retry<EVAL_BITS, 0, 1, 1, false>(ix, a, stream);
+  }
+  if (ix->p.quantizer == SDB_QUANT_PRODUCT && ix->pq_fitted) {
+    if ((rc = ix->d_adc.ensure(size_t(B) * ix->pqM * ix->pqK))) return rc;
+    if ((rc = launch_adc_tables(ix, B, d_queries, ix->d_adc.p, stream))) return rc;
+    a.adc = ix->d_adc.p;
+    return filtered ? launch_with_retry<EVAL_ADC, 0, 1, 1, true>(ix, a, stream)
+                    : launch_with_retry<EVAL_ADC, 0, 1, 1, false>(ix, a, stream);
+  }
+  switch (ix->store_metric) {
+    case SDB_METRIC_EUCLIDEAN: return launch_float<METRIC_EUCLIDEAN>(ix, a, filtered, stream);
+    case SDB_METRIC_DOT: return launch_float<METRIC_DOT>(ix, a, filtered, stream);
+    case SDB_METRIC_COSINE: return launch_float<METRIC_COSINE>(ix, a, filtered, stream);
+    default: return fail(SDB_ERR_INVALID, "metric not supported by the Vamana search kernel");
+  }
+}
+
+}  // namespace sdb

@@ -1,0 +1,558 @@
+// search.cuh — K1/K2/K3: batched Vamana greedy beam search, one warp per query.
+//
+// Restates greedySearch (shard/index/vamana/search.go:9-102) + DistSet.AddWithLimit
+// (distset.go:166-200) for a whole batch of queries:
+//   * persistent CTAs; each warp pulls query indices from a global counter;
+//   * the searchSize-bounded candidate list, the exact visited set (open-addressed hash
+//     of node ids) and the per-hop neighbour staging live in shared memory;
+//   * per hop: one coalesced 256-byte adjacency-row load, parallel visited test-and-set,
+//     ballot compaction in adjacency order, neighbour vector rows gathered with 128-bit
+//     streaming loads (an 8-lane group per row, up to 32+ rows in flight per warp),
+//     distances in the reference's exact summation order (common.cuh), then the
+//     insertions applied sequentially in adjacency order with ballot/shift steps so
+//     every tie behaves like the reference (reject only d > worst, overwrite the last
+//     slot, bubble while strictly smaller).
+// Algorithmic bytes per query = n_dist*row_bytes + n_hops*R*4; the
+// kernel reports n_hops and n_dist per query.
+#pragma once
+#include "common.cuh"
+
+namespace sdb {
+
+constexpr int LIST_SLOTS = 96;   // >= max searchSize (75), 3 per lane
+constexpr int CAND_SLOTS = 64;   // >= max degreeBound (64), 2 per lane
+constexpr uint32_t EXPANDED_FLAG = 0x80000000u;
+constexpr uint32_t ID_MASK = 0x7FFFFFFFu;
+constexpr uint32_t COUNT_OVERFLOW = 0xFFFFFFFFu;  // out_counts marker: visited table overflowed
+
+struct SearchArgs {
+  // store
+  const float* vec;        // [rows][vec_pitch]
+  uint32_t vec_pitch;      // floats per row (multiple of 4)
+  const uint64_t* bits;    // [rows][bits_pitch] (binary store)
+  uint32_t bits_pitch;     // u64 per row (multiple of 2)
+  uint32_t words;          // ceil(dim/64)
+  const uint8_t* codes;    // [rows][codes_pitch] (product store)
+  uint32_t codes_pitch;    // bytes per row (multiple of 16)
+  const float* adc;        // [B][M*K] per-query ADC tables (product store)
+  uint32_t pqM, pqK;
+  const float* bq_thr;     // [dim] binary threshold (query encode)
+  int bit_metric;
+  // graph
+  const uint32_t* adj;     // [rows][R], INVALID_ID padded
+  uint32_t R;
+  uint32_t rows;
+  // batch
+  const float* queries;    // [B][dim]
+  uint32_t dim;
+  uint32_t B;
+  uint32_t L, k;
+  // outputs
+  uint64_t* out_ids;       // [B][k]
+  float* out_dists;        // [B][k]
+  uint32_t* out_counts;    // [B]
+  uint32_t* out_hops;      // [B]
+  uint32_t* out_ndist;     // [B]
+  // optional: visited (expanded) list in expansion order, for the insert path
+  uint32_t* vis_ids;       // [B][vis_cap]
+  float* vis_dists;
+  uint32_t* vis_len;
+  uint32_t vis_cap;
+  // optional filter (search.go:33-51,93-95)
+  const uint32_t* filter_seed;  // first min(L, n) filter ids ascending
+  uint32_t n_filter_seed;
+  const uint32_t* filter_bits;  // bitmask over rows
+  // work distribution: work_counter hands out batch slots; a query whose visited table
+  // overflows is appended to retry_list and re-run by the RETRY launch (bigger table).
+  uint32_t* work_counter;
+  uint32_t* retry_list;
+  uint32_t* retry_count;
+};
+
+// ---- exact visited set: open-addressed u32 hash in shared memory ------------------
+template <int HBITS>
+struct VisitedTable {
+  static constexpr uint32_t SLOTS = 1u << HBITS;
+  static constexpr uint32_t LIMIT = SLOTS - SLOTS / 8;  // refuse beyond 87.5 % load
+  uint32_t* t;
+  __device__ __forceinline__ void clear(int lane) {
+    uint4 e = make_uint4(INVALID_ID, INVALID_ID, INVALID_ID, INVALID_ID);
+    uint4* p = reinterpret_cast<uint4*>(t);
+    for (uint32_t i = lane; i < SLOTS / 4; i += 32) p[i] = e;
+  }
+  // true if id was NOT present (and is now) — CheckAndVisit negated (distset.go:105-111)
+  __device__ __forceinline__ bool test_and_set(uint32_t id) {
+    uint32_t slot = (id * 0x9E3779B1u) >> (32 - HBITS);
+    for (;;) {
+      uint32_t old = atomicCAS(&t[slot], INVALID_ID, id);
+      if (old == INVALID_ID) return true;
+      if (old == id) return false;
+      slot = (slot + 1) & (SLOTS - 1);
+    }
+  }
+};
+
+// ---- bounded candidate list (distset.go:133-200) in shared memory ------------------
+struct CandList {
+  uint32_t* id;  // EXPANDED_FLAG in the top bit
+  float* dist;
+  int len;
+  int cap;
+  // Insert one element with AddWithLimit semantics; caller has already applied the
+  // "full && d > worst" rejection. Warp-synchronous; all lanes call with the same args.
+  __device__ __forceinline__ void insert(uint32_t nid, float d, int lane) {
+    const bool full = (len == cap);
+    const int n_items = full ? cap - 1 : len;  // full: last slot is overwritten first
+    // bubble: new element stops right after the last p with !(d < dist[p])
+    int pos = 0;
+#pragma unroll
+    for (int j = 2; j >= 0; --j) {
+      int p = lane + 32 * j;
+      bool ok = (p < n_items) && !(d < dist[p]);
+      uint32_t b = __ballot_sync(SDB_FULL, ok);
+      if (b && pos == 0) pos = 32 * j + (32 - __clz(b));
+    }
+    // shift [pos, n_items) up by one
+    uint32_t mv_id[3];
+    float mv_d[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      int p = lane + 32 * j;
+      if (p >= pos && p < n_items) { mv_id[j] = id[p]; mv_d[j] = dist[p]; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      int p = lane + 32 * j;
+      if (p >= pos && p < n_items) { id[p + 1] = mv_id[j]; dist[p + 1] = mv_d[j]; }
+    }
+    if (lane == 0) { id[pos] = nid; dist[pos] = d; }
+    if (!full) ++len;
+    __syncwarp();
+  }
+};
+
+// ---- distance evaluators -----------------------------------------------------------
+// Each evaluates cdist[c] = dist(query, row cid[c]) for c in [0, n), warp-cooperatively.
+
+// f32 rows, dim = 32*TRIPS exactly, query slice in registers (TRIPS <= 4) or shared.
+template <int METRIC, int TRIPS, int UNROLL>
+struct FloatEvalFixed {
+  static constexpr bool L2 = (METRIC == METRIC_EUCLIDEAN);
+  static constexpr bool QREG = (TRIPS <= 4);
+  float4 q[QREG ? TRIPS : 1];
+  const float* qs;
+  __device__ __forceinline__ void load_query(const float* qsmem, int lane) {
+    qs = qsmem;
+    if (QREG) {
+#pragma unroll
+      for (int t = 0; t < TRIPS; ++t) q[t] = *reinterpret_cast<const float4*>(qsmem + 32 * t + 4 * (lane & 7));
+    }
+  }
+  __device__ __forceinline__ void eval(const SearchArgs& a, const uint32_t* cid, float* cdist, int n, int lane) {
+    const int g = lane & 7, grp = lane >> 3;
+    for (int base = 0; base < n; base += 4 * UNROLL) {
+      float4 v[UNROLL][TRIPS];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        int ci = base + 4 * u + grp;
+        if (ci < n) {
+          const float* row = a.vec + size_t(cid[ci]) * a.vec_pitch + 4 * g;
+#pragma unroll
+          for (int t = 0; t < TRIPS; ++t) v[u][t] = ldg_f4_stream(row + 32 * t);
+        } else {
+#pragma unroll
+          for (int t = 0; t < TRIPS; ++t) v[u][t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        if (base + 4 * u >= n) break;  // warp-uniform
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < TRIPS; ++t) {
+          float4 x = QREG ? q[t] : *reinterpret_cast<const float4*>(qs + 32 * t + 4 * g);
+          trip_accum<L2>(x, v[u][t], acc);
+        }
+        float r = group_reduce(acc, 0.0f);
+        int ci = base + 4 * u + grp;
+        if (g == 0 && ci < n) cdist[ci] = metric_epilogue<METRIC>(r);
+      }
+    }
+    __syncwarp();
+  }
+};
+
+// f32 rows, any dim: runtime trips + scalar tail, query in shared memory.
+template <int METRIC>
+struct FloatEvalGeneric {
+  static constexpr bool L2 = (METRIC == METRIC_EUCLIDEAN);
+  const float* qs;
+  __device__ __forceinline__ void load_query(const float* qsmem, int) { qs = qsmem; }
+  __device__ __forceinline__ void eval(const SearchArgs& a, const uint32_t* cid, float* cdist, int n, int lane) {
+    const int g = lane & 7, grp = lane >> 3;
+    const int trips = a.dim >> 5;
+    const int tail0 = trips << 5;
+    for (int base = 0; base < n; base += 4) {
+      int ci = base + grp;
+      bool act = ci < n;
+      const float* row = a.vec + size_t(act ? cid[ci] : cid[0]) * a.vec_pitch;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int t = 0;
+      for (; t + 8 <= trips; t += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = ldg_f4_stream(row + 32 * (t + u) + 4 * g);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          trip_accum<L2>(*reinterpret_cast<const float4*>(qs + 32 * (t + u) + 4 * g), v[u], acc);
+      }
+      for (; t < trips; ++t) {
+        float4 v = ldg_f4_stream(row + 32 * t + 4 * g);
+        trip_accum<L2>(*reinterpret_cast<const float4*>(qs + 32 * t + 4 * g), v, acc);
+      }
+      float tail = 0.0f;
+      if (g == 0)
+        for (int i = tail0; i < int(a.dim); ++i) tail = tail_accum<L2>(qs[i], __ldg(row + i), tail);
+      float r = group_reduce(acc, tail);
+      if (g == 0 && act) cdist[ci] = metric_epilogue<METRIC>(r);
+    }
+    __syncwarp();
+  }
+};
+
+// Bit-packed rows (binaryQuantizer.DistanceFromFloat, binary.go:187-201): the query is
+// encoded once (binary.go:103-129) into shared memory; hamming / jaccard by popcount
+// (distance.go:45-67). An 8-lane group covers a row 16 bytes per lane per step.
+struct BitEval {
+  const uint64_t* qb;  // shared: encoded query, padded to bits_pitch words
+  __device__ __forceinline__ void encode_query(const SearchArgs& a, const float* qsmem, uint64_t* qbits, int lane) {
+    // bit i%64 of word i/64 = q[i] > thr[i]
+    for (uint32_t w = 0; w < a.bits_pitch; ++w) {
+      uint64_t word = 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t i = w * 64 + h * 32 + lane;
+        bool on = (i < a.dim) && (qsmem[i] > __ldg(a.bq_thr + i));
+        uint32_t b = __ballot_sync(SDB_FULL, on);
+        word |= uint64_t(b) << (32 * h);
+      }
+      if (lane == 0) qbits[w] = word;
+    }
+    __syncwarp();
+    qb = qbits;
+  }
+  __device__ __forceinline__ void eval(const SearchArgs& a, const uint32_t* cid, float* cdist, int n, int lane) {
+    const int g = lane & 7, grp = lane >> 3;
+    const int steps = (a.bits_pitch + 15) / 16;  // 16 u64 (128 B) per group step
+    for (int base = 0; base < n; base += 8) {    // two rows per group in flight
+      int x0 = 0, u0 = 0, x1 = 0, u1 = 0;
+      int c0 = base + grp, c1 = base + 4 + grp;
+      const uint64_t* r0 = a.bits + size_t(c0 < n ? cid[c0] : cid[0]) * a.bits_pitch;
+      const uint64_t* r1 = a.bits + size_t(c1 < n ? cid[c1] : cid[0]) * a.bits_pitch;
+      for (int s = 0; s < steps; ++s) {
+        uint32_t w = s * 16 + 2 * g;
+        if (w < a.bits_pitch) {
+          uint4 v0 = ldg_u4_stream(r0 + w);
+          uint4 v1 = ldg_u4_stream(r1 + w);
+          uint64_t qa = qb[w], qc = qb[w + 1];
+          uint64_t a0 = (uint64_t(v0.y) << 32) | v0.x, b0 = (uint64_t(v0.w) << 32) | v0.z;
+          uint64_t a1 = (uint64_t(v1.y) << 32) | v1.x, b1 = (uint64_t(v1.w) << 32) | v1.z;
+          if (a.bit_metric == METRIC_JACCARD) {
+            x0 += __popcll(qa & a0) + __popcll(qc & b0);
+            u0 += __popcll(qa | a0) + __popcll(qc | b0);
+            x1 += __popcll(qa & a1) + __popcll(qc & b1);
+            u1 += __popcll(qa | a1) + __popcll(qc | b1);
+          } else {
+            x0 += __popcll(qa ^ a0) + __popcll(qc ^ b0);
+            x1 += __popcll(qa ^ a1) + __popcll(qc ^ b1);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 4; o >= 1; o >>= 1) {
+        x0 += __shfl_down_sync(SDB_FULL, x0, o, 8);
+        u0 += __shfl_down_sync(SDB_FULL, u0, o, 8);
+        x1 += __shfl_down_sync(SDB_FULL, x1, o, 8);
+        u1 += __shfl_down_sync(SDB_FULL, u1, o, 8);
+      }
+      if (g == 0) {
+        if (c0 < n) cdist[c0] = bits_finish(a.bit_metric, x0, u0);
+        if (c1 < n) cdist[c1] = bits_finish(a.bit_metric, x1, u1);
+      }
+    }
+    __syncwarp();
+  }
+};
+
+// PQ codes (productQuantizer.DistanceFromFloat, product.go:238-277): per-query ADC table
+// (built by a separate kernel, product.go:255-263) read through L1/L2; one lane per
+// candidate sums M table entries sequentially in f32 (product.go:271-275).
+struct AdcEval {
+  const float* table;  // [M*K] for this query (global)
+  __device__ __forceinline__ void eval(const SearchArgs& a, const uint32_t* cid, float* cdist, int n, int lane) {
+    for (int c = lane; c < n; c += 32) {
+      const uint8_t* code = a.codes + size_t(cid[c]) * a.codes_pitch;
+      float d = 0.0f;
+      for (uint32_t i0 = 0; i0 < a.pqM; i0 += 16) {
+        uint4 v = ldg_u4_stream(code + i0);
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          uint32_t i = i0 + j;
+          if (i < a.pqM) {
+            uint32_t cj = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+            d = __fadd_rn(d, __ldg(table + i * a.pqK + cj));
+          }
+        }
+      }
+      cdist[c] = d;
+    }
+    __syncwarp();
+  }
+};
+
+enum EvalKind : int { EVAL_FLOAT_FIXED = 0, EVAL_FLOAT_GENERIC = 1, EVAL_BITS = 2, EVAL_ADC = 3 };
+
+// ---- shared-memory layout per warp --------------------------------------------------
+template <int HBITS>
+__host__ __device__ constexpr size_t warp_smem_bytes(uint32_t qfloats, uint32_t qwords) {
+  return (size_t(1) << HBITS) * 4 + LIST_SLOTS * 8 + LIST_SLOTS * 8 /*filter result list*/ + CAND_SLOTS * 8 +
+         ((size_t(qfloats) * 4 + 15) / 16) * 16 + ((size_t(qwords) * 8 + 15) / 16) * 16;
+}
+
+// ---- the kernel ---------------------------------------------------------------------
+template <int KIND, int METRIC, int TRIPS, int UNROLL, int HBITS, bool FILTER, bool RETRY>
+__global__ void __launch_bounds__(128) beam_search_kernel(SearchArgs a, uint32_t qfloats, uint32_t qwords) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  unsigned char* base = smem_raw + size_t(warp) * warp_smem_bytes<HBITS>(qfloats, qwords);
+  VisitedTable<HBITS> vt;
+  vt.t = reinterpret_cast<uint32_t*>(base);
+  base += (size_t(1) << HBITS) * 4;
+  CandList list;
+  list.id = reinterpret_cast<uint32_t*>(base);
+  list.dist = reinterpret_cast<float*>(base + LIST_SLOTS * 4);
+  base += LIST_SLOTS * 8;
+  CandList res;  // filter mode: k-bounded result set (search.go:33-35)
+  res.id = reinterpret_cast<uint32_t*>(base);
+  res.dist = reinterpret_cast<float*>(base + LIST_SLOTS * 4);
+  base += LIST_SLOTS * 8;
+  uint32_t* cid = reinterpret_cast<uint32_t*>(base);
+  float* cdist = reinterpret_cast<float*>(base + CAND_SLOTS * 4);
+  base += CAND_SLOTS * 8;
+  float* qs = reinterpret_cast<float*>(base);
+  base += ((size_t(qfloats) * 4 + 15) / 16) * 16;
+  uint64_t* qbits = reinterpret_cast<uint64_t*>(base);
+
+  for (;;) {
+    uint32_t qi = 0;
+    if (lane == 0) {
+      qi = atomicAdd(a.work_counter, 1u);
+      if (RETRY) qi = qi < *a.retry_count ? a.retry_list[qi] : 0xFFFFFFFFu;
+    }
+    qi = __shfl_sync(SDB_FULL, qi, 0);
+    if (qi >= a.B) break;
+
+    // ---- per-query setup
+    vt.clear(lane);
+    if (KIND != EVAL_ADC) {
+      const float* qg = a.queries + size_t(qi) * a.dim;
+      for (uint32_t i = lane; i < qfloats; i += 32) qs[i] = i < a.dim ? __ldg(qg + i) : 0.0f;
+    }
+    __syncwarp();
+    FloatEvalFixed<METRIC, (KIND == EVAL_FLOAT_FIXED ? TRIPS : 1), (KIND == EVAL_FLOAT_FIXED ? UNROLL : 1)> ev_fixed;
+    FloatEvalGeneric<METRIC> ev_gen;
+    BitEval ev_bits;
+    AdcEval ev_adc;
+    if (KIND == EVAL_FLOAT_FIXED) ev_fixed.load_query(qs, lane);
+    if (KIND == EVAL_FLOAT_GENERIC) ev_gen.load_query(qs, lane);
+    if (KIND == EVAL_BITS) ev_bits.encode_query(a, qs, qbits, lane);
+    if (KIND == EVAL_ADC) ev_adc.table = a.adc + size_t(qi) * a.pqM * a.pqK;
+    auto evaluate = [&](int n) {
+      if (KIND == EVAL_FLOAT_FIXED) ev_fixed.eval(a, cid, cdist, n, lane);
+      if (KIND == EVAL_FLOAT_GENERIC) ev_gen.eval(a, cid, cdist, n, lane);
+      if (KIND == EVAL_BITS) ev_bits.eval(a, cid, cdist, n, lane);
+      if (KIND == EVAL_ADC) ev_adc.eval(a, cid, cdist, n, lane);
+    };
+
+    list.len = 0;
+    list.cap = int(a.L);
+    res.len = 0;
+    res.cap = int(a.k);
+    uint32_t hops = 0, ndist = 0, nvisited = 0;
+    bool overflow = false;
+
+    // AddWithLimit of the staged candidates cid/cdist[0..n) into `dst`, sequentially in
+    // order (distset.go:166-200 after the visited test and the distance evaluation).
+    auto add_with_limit = [&](CandList& dst, int n) {
+      float d0 = lane < n ? cdist[lane] : 0.0f;
+      float d1 = lane + 32 < n ? cdist[lane + 32] : 0.0f;
+      int next = 0;
+      for (;;) {
+        const bool full = dst.len == dst.cap;
+        const float worst = full ? dst.dist[dst.cap - 1] : 0.0f;
+        bool e0 = lane >= next && lane < n && !(full && d0 > worst);
+        bool e1 = lane + 32 >= next && lane + 32 < n && !(full && d1 > worst);
+        uint32_t m0 = __ballot_sync(SDB_FULL, e0), m1 = __ballot_sync(SDB_FULL, e1);
+        int c;
+        if (m0) c = __ffs(m0) - 1;
+        else if (m1) c = 32 + __ffs(m1) - 1;
+        else break;
+        float dc = __shfl_sync(SDB_FULL, c < 32 ? d0 : d1, c & 31);
+        dst.insert(cid[c], dc, lane);
+        next = c + 1;
+      }
+    };
+
+    if (FILTER) {
+      // searchSet.Add(filterPoints...) (plain append, search.go:49) and
+      // resultSet.AddWithLimit(filterPoints...) (search.go:50)
+      int nf = int(min(a.n_filter_seed, a.L));
+      for (int b0 = 0; b0 < nf; b0 += CAND_SLOTS) {
+        int n = min(CAND_SLOTS, nf - b0);
+        // test-and-set in order; seeds are unique ascending ids
+        bool n0 = false, n1 = false;
+        uint32_t i0 = 0, i1 = 0;
+        if (lane < n) { i0 = __ldg(a.filter_seed + b0 + lane); n0 = vt.test_and_set(i0); }
+        if (lane + 32 < n) { i1 = __ldg(a.filter_seed + b0 + lane + 32); n1 = vt.test_and_set(i1); }
+        uint32_t bb0 = __ballot_sync(SDB_FULL, n0), bb1 = __ballot_sync(SDB_FULL, n1);
+        int t0 = __popc(bb0);
+        int nn = t0 + __popc(bb1);
+        uint32_t lt = (1u << lane) - 1;
+        if (n0) cid[__popc(bb0 & lt)] = i0;
+        if (n1) cid[t0 + __popc(bb1 & lt)] = i1;
+        __syncwarp();
+        nvisited += nn;
+        ndist += nn;
+        evaluate(nn);
+        for (int c = lane; c < nn; c += 32) {
+          list.id[list.len + c] = cid[c];
+          list.dist[list.len + c] = cdist[c];
+        }
+        list.len += nn;
+        __syncwarp();
+        add_with_limit(res, nn);  // resultSet has its own visited set; seeds are unique
+      }
+    }
+
+    // searchSet.AddWithLimit(startNode) (search.go:57-61)
+    {
+      bool isnew = false;
+      if (lane == 0) isnew = vt.test_and_set(START_ID);
+      isnew = __shfl_sync(SDB_FULL, isnew, 0);
+      if (isnew) {
+        if (lane == 0) cid[0] = START_ID;
+        __syncwarp();
+        ++nvisited;
+        ++ndist;
+        evaluate(1);
+        add_with_limit(list, 1);
+      }
+    }
+
+    // main loop (search.go:65-98)
+    for (;;) {
+      const int lim = min(list.len, int(a.L));
+      int pos = -1;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        int p = lane + 32 * j;
+        bool un = (p < lim) && !(list.id[p] & EXPANDED_FLAG);
+        uint32_t b = __ballot_sync(SDB_FULL, un);
+        if (b && pos < 0) pos = 32 * j + __ffs(b) - 1;
+      }
+      if (pos < 0) break;
+      const uint32_t e = list.id[pos];
+      const float edist = list.dist[pos];
+      __syncwarp();
+      if (lane == 0) list.id[pos] = e | EXPANDED_FLAG;
+      if (a.vis_ids != nullptr && lane == 0) {
+        if (hops < a.vis_cap) {
+          a.vis_ids[size_t(qi) * a.vis_cap + hops] = e;
+          a.vis_dists[size_t(qi) * a.vis_cap + hops] = edist;
+        }
+      }
+      ++hops;
+      // neighbours, adjacency order c = lane, lane+32
+      const uint32_t* arow = a.adj + size_t(e) * a.R;
+      uint32_t n0 = lane < int(a.R) ? __ldg(arow + lane) : INVALID_ID;
+      uint32_t n1 = lane + 32 < int(a.R) ? __ldg(arow + lane + 32) : INVALID_ID;
+      bool new0 = (n0 != INVALID_ID) && vt.test_and_set(n0);
+      bool new1 = (n1 != INVALID_ID) && vt.test_and_set(n1);
+      uint32_t b0 = __ballot_sync(SDB_FULL, new0), b1 = __ballot_sync(SDB_FULL, new1);
+      const int t0 = __popc(b0);
+      const int nnew = t0 + __popc(b1);
+      const uint32_t lt = (1u << lane) - 1;
+      if (new0) cid[__popc(b0 & lt)] = n0;
+      if (new1) cid[t0 + __popc(b1 & lt)] = n1;
+      __syncwarp();
+      nvisited += nnew;
+      ndist += nnew;
+      if (nvisited > VisitedTable<HBITS>::LIMIT) { overflow = true; break; }
+      if (nnew > 0) {
+        evaluate(nnew);
+        add_with_limit(list, nnew);
+      }
+      if (FILTER) {
+        // resultSet.AddWithLimit(distElem.Point) if the expanded node passes the filter
+        // (search.go:93-95). resultSet dedupes with its own visited set: a node is
+        // expanded at most once and seeds were added up front, so test membership.
+        bool in_filter = (__ldg(a.filter_bits + (e >> 5)) >> (e & 31)) & 1u;
+        if (in_filter) {
+          bool dup = false;
+          for (int p = lane; p < res.len; p += 32) dup |= ((res.id[p] & ID_MASK) == e);
+          // seeds that were rejected/evicted from res are still "visited" in its set
+          bool seeded = false;
+          for (uint32_t s = lane; s < min(a.n_filter_seed, a.L); s += 32) seeded |= (__ldg(a.filter_seed + s) == e);
+          if (!__any_sync(SDB_FULL, dup || seeded)) {
+            if (lane == 0) { cid[0] = e; cdist[0] = edist; }
+            __syncwarp();
+            add_with_limit(res, 1);
+          }
+        }
+      }
+    }
+
+    // ---- results (vamana.go:285-307): drop STARTID, first k items
+    CandList& out = FILTER ? res : list;
+    if (overflow) {
+      if (lane == 0) {
+        a.out_counts[qi] = COUNT_OVERFLOW;
+        a.out_hops[qi] = hops;
+        a.out_ndist[qi] = ndist;
+        if (!RETRY) a.retry_list[atomicAdd(a.retry_count, 1u)] = qi;
+      }
+    } else {
+      int written = 0;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        int p = lane + 32 * j;
+        uint32_t nid = p < out.len ? (out.id[p] & ID_MASK) : START_ID;
+        bool keep = (p < out.len) && (nid != START_ID);
+        uint32_t b = __ballot_sync(SDB_FULL, keep);
+        int r = written + __popc(b & ((1u << lane) - 1));
+        if (keep && r < int(a.k)) {
+          a.out_ids[size_t(qi) * a.k + r] = uint64_t(nid);
+          a.out_dists[size_t(qi) * a.k + r] = out.dist[p];
+        }
+        written += __popc(b);
+      }
+      int cnt = min(written, int(a.k));
+      for (int r = cnt + lane; r < int(a.k); r += 32) {
+        a.out_ids[size_t(qi) * a.k + r] = 0;
+        a.out_dists[size_t(qi) * a.k + r] = __int_as_float(0x7f800000);
+      }
+      if (lane == 0) {
+        a.out_counts[qi] = uint32_t(cnt);
+        a.out_hops[qi] = hops;
+        a.out_ndist[qi] = ndist;
+        if (a.vis_len) a.vis_len[qi] = hops;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace sdb

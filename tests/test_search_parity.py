@@ -1,0 +1,127 @@
+"""K1 parity: CUDA beam search vs the oracle on the oracle-built graph, through the C ABI.
+Bit-exact ids, distances, hop and distance-evaluation counts (SURVEY.md §7.3-①/②)."""
+import numpy as np
+import pytest
+
+from semadb_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_search(oix, g, Q, k=10, L=75):
+    ref = oix.search(Q, k=k, search_size=L, threads=8, diagnostics=True)
+    ids, d, cnt = g.search_batch(Q, k, L)
+    hops, nd = g.last_search_stats(len(Q))
+    assert (cnt == ref["counts"]).all()
+    assert (ids == ref["ids"].astype(np.uint64)).all()
+    assert d.tobytes() == ref["dists"].tobytes()
+    assert (hops == ref["hops"]).all()
+    assert (nd == ref["ndist"]).all()
+    return ref
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "dot", "cosine"])
+@pytest.mark.parametrize("dim", [128, 2, 100, 384])
+def test_search_matches_oracle(metric, dim):
+    from tests.helpers import mirror_to_gpu, oracle_graph
+    n = 4000 if dim > 128 else 8000
+    X = synth.latent_gaussian(n, dim, seed=dim, latent=min(8, dim), normalize=(metric == "cosine"))
+    Q = synth.latent_gaussian(300, dim, seed=dim + 1, w_seed=dim, latent=min(8, dim), normalize=(metric == "cosine"))
+    oix, ids, start = oracle_graph(X, metric)
+    g = mirror_to_gpu(oix, X, ids, start, metric)
+    _check_search(oix, g, Q)
+    _check_search(oix, g, Q[:50], k=1, L=25)
+    _check_search(oix, g, Q[:50], k=75, L=75)
+
+
+def test_search_c1_shape_small():
+    """C1-shaped (uniform 128-d, saturated degrees) at 20k points."""
+    from tests.helpers import mirror_to_gpu, oracle_graph
+    X = synth.uniform(20000, 128, 1)
+    Q = synth.uniform(1000, 128, 2)
+    oix, ids, start = oracle_graph(X)
+    g = mirror_to_gpu(oix, X, ids, start)
+    _check_search(oix, g, Q)
+
+
+def test_search_sift_shaped_100k():
+    from tests.helpers import mirror_to_gpu, oracle_graph, recall_at_k
+    X = synth.sift_shaped(100_000, 128, 3)
+    Q = synth.sift_shaped(2000, 128, 4, w_seed=3)
+    oix, ids, start = oracle_graph(X)
+    g = mirror_to_gpu(oix, X, ids, start)
+    ref = _check_search(oix, g, Q)
+    gt = oix.flat_search(Q[:500], k=10, threads=8)
+    assert recall_at_k(ref["ids"][:500], gt["ids"]) >= 0.95
+    # GPU flat (K5) must agree bit-exactly with the oracle's brute force
+    fi, fd, fc = g.flat_search_batch(Q[:500], 10)
+    assert (fi == gt["ids"].astype(np.uint64)).all()
+    assert fd.tobytes() == gt["dists"].tobytes()
+
+
+def test_search_empty_and_tiny():
+    """vamana_test.go:213-228 (empty) and graphs smaller than k."""
+    from tests.helpers import mirror_to_gpu, oracle_graph
+    from semadb_b200.vamana import IndexVamana, IndexVectorVamanaParameters
+    g = IndexVamana("empty", IndexVectorVamanaParameters(2), start_seed=1)
+    ids, d, cnt = g.search_batch(np.array([[0.5, 0.5]], dtype=np.float32), 10, 75)
+    assert cnt[0] == 0 and (ids == 0).all() and np.isinf(d).all()
+    X = synth.uniform(5, 2, 3)
+    oix, pid, start = oracle_graph(X, threads=1)
+    g2 = mirror_to_gpu(oix, X, pid, start)
+    _check_search(oix, g2, X)
+
+
+def test_search_self_recall_200():
+    """vamana_test.go:230-252."""
+    from tests.helpers import mirror_to_gpu, oracle_graph
+    X = synth.uniform(200, 2, 5)
+    oix, pid, start = oracle_graph(X, threads=1)
+    g = mirror_to_gpu(oix, X, pid, start)
+    ids, d, cnt = g.search_batch(X, 10, 75)
+    assert (cnt == 10).all() and (ids[:, 0] == pid).all() and (d[:, 0] == 0).all()
+
+
+def test_search_size_lt_k_is_error():
+    """search.go:23-25."""
+    from semadb_b200._capi import ERR_SEARCHSIZE, SdbError
+    from semadb_b200.vamana import IndexVamana, IndexVectorVamanaParameters
+    g = IndexVamana("e", IndexVectorVamanaParameters(2), start_seed=1)
+    with pytest.raises(SdbError) as ei:
+        g.search_batch(np.zeros((1, 2), np.float32), 30, 25)
+    assert ei.value.code == ERR_SEARCHSIZE
+
+
+def test_search_filter():
+    """vamana_test.go:254-276 + oracle parity with a larger filter."""
+    from tests.helpers import mirror_to_gpu, oracle_graph
+    X = synth.uniform(3000, 8, 7)
+    oix, pid, start = oracle_graph(X, threads=1)
+    g = mirror_to_gpu(oix, X, pid, start)
+    filt = [int(pid[10]), int(pid[20]), int(pid[30])]
+    ids, d, cnt = g.search_batch(X[10:11], 10, 75, filter_ids=filt)
+    assert cnt[0] == 3 and ids[0, 0] == pid[10] and sorted(ids[0, :3].tolist()) == sorted(filt)
+    rng = np.random.Generator(np.random.PCG64(3))
+    for nf in (1, 40, 75, 76, 500):
+        f = np.sort(rng.choice(pid, size=nf, replace=False))
+        ref = oix.search(X[:64], k=10, filter_ids=f, threads=4)
+        ids, d, cnt = g.search_batch(X[:64], 10, 75, filter_ids=f)
+        assert (cnt == ref["counts"]).all()
+        assert (ids == ref["ids"].astype(np.uint64)).all()
+        assert d.tobytes() == ref["dists"].tobytes()
+
+
+def test_visited_list_matches_oracle():
+    """greedySearch's second return value (search.go:100), the robustPrune candidate list."""
+    from tests.helpers import mirror_to_gpu, oracle_graph
+    X = synth.sift_shaped(20000, 128, 3)
+    oix, pid, start = oracle_graph(X)
+    g = mirror_to_gpu(oix, X, pid, start)
+    Q = synth.sift_shaped(200, 128, 4, w_seed=3)
+    ref = oix.search(Q, k=1, vis_cap=256, threads=8)
+    vi, vd, vn = g.search_visited(Q, 75, 256)
+    assert (vn == ref["vis_len"]).all()
+    for b in range(len(Q)):
+        n = vn[b]
+        assert (vi[b, :n] == ref["vis_ids"][b, :n]).all()
+        assert vd[b, :n].tobytes() == ref["vis_dists"][b, :n].tobytes()
