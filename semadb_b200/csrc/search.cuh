@@ -80,15 +80,21 @@ struct VisitedTable {
     uint4* p = reinterpret_cast<uint4*>(t);
     for (uint32_t i = lane; i < SLOTS / 4; i += 32) p[i] = e;
   }
-  // true if id was NOT present (and is now) — CheckAndVisit negated (distset.go:105-111)
-  __device__ __forceinline__ bool test_and_set(uint32_t id) {
+  // true if id was NOT present (and is now) — CheckAndVisit negated (distset.go:105-111).
+  // Warp-convergent: every lane calls it (active = this lane has an id to test) and the
+  // probe loop is driven by a vote, so the compiler keeps the warp converged afterwards.
+  __device__ __forceinline__ bool test_and_set(uint32_t id, bool active) {
     uint32_t slot = (id * 0x9E3779B1u) >> (32 - HBITS);
-    for (;;) {
-      uint32_t old = atomicCAS(&t[slot], INVALID_ID, id);
-      if (old == INVALID_ID) return true;
-      if (old == id) return false;
-      slot = (slot + 1) & (SLOTS - 1);
+    bool pending = active, isnew = false;
+    while (__any_sync(SDB_FULL, pending)) {
+      if (pending) {
+        uint32_t old = atomicCAS(&t[slot], INVALID_ID, id);
+        if (old == INVALID_ID) { isnew = true; pending = false; }
+        else if (old == id) pending = false;
+        else slot = (slot + 1) & (SLOTS - 1);
+      }
     }
+    return isnew;
   }
 };
 
@@ -415,8 +421,10 @@ __global__ void __launch_bounds__(128) beam_search_kernel(SearchArgs a, uint32_t
         // test-and-set in order; seeds are unique ascending ids
         bool n0 = false, n1 = false;
         uint32_t i0 = 0, i1 = 0;
-        if (lane < n) { i0 = __ldg(a.filter_seed + b0 + lane); n0 = vt.test_and_set(i0); }
-        if (lane + 32 < n) { i1 = __ldg(a.filter_seed + b0 + lane + 32); n1 = vt.test_and_set(i1); }
+        if (lane < n) i0 = __ldg(a.filter_seed + b0 + lane);
+        n0 = vt.test_and_set(i0, lane < n);
+        if (lane + 32 < n) i1 = __ldg(a.filter_seed + b0 + lane + 32);
+        n1 = vt.test_and_set(i1, lane + 32 < n);
         uint32_t bb0 = __ballot_sync(SDB_FULL, n0), bb1 = __ballot_sync(SDB_FULL, n1);
         int t0 = __popc(bb0);
         int nn = t0 + __popc(bb1);
@@ -440,7 +448,7 @@ __global__ void __launch_bounds__(128) beam_search_kernel(SearchArgs a, uint32_t
     // searchSet.AddWithLimit(startNode) (search.go:57-61)
     {
       bool isnew = false;
-      if (lane == 0) isnew = vt.test_and_set(START_ID);
+      isnew = vt.test_and_set(START_ID, lane == 0);
       isnew = __shfl_sync(SDB_FULL, isnew, 0);
       if (isnew) {
         if (lane == 0) cid[0] = START_ID;
@@ -479,8 +487,8 @@ __global__ void __launch_bounds__(128) beam_search_kernel(SearchArgs a, uint32_t
       const uint32_t* arow = a.adj + size_t(e) * a.R;
       uint32_t n0 = lane < int(a.R) ? __ldg(arow + lane) : INVALID_ID;
       uint32_t n1 = lane + 32 < int(a.R) ? __ldg(arow + lane + 32) : INVALID_ID;
-      bool new0 = (n0 != INVALID_ID) && vt.test_and_set(n0);
-      bool new1 = (n1 != INVALID_ID) && vt.test_and_set(n1);
+      bool new0 = vt.test_and_set(n0, n0 != INVALID_ID);
+      bool new1 = vt.test_and_set(n1, n1 != INVALID_ID);
       uint32_t b0 = __ballot_sync(SDB_FULL, new0), b1 = __ballot_sync(SDB_FULL, new1);
       const int t0 = __popc(b0);
       const int nnew = t0 + __popc(b1);
