@@ -92,6 +92,15 @@ int index_reserve_locked(sdb_index* ix, uint64_t max_node_id) {
   return SDB_OK;
 }
 
+int set_rows_device(sdb_index* ix, uint32_t n, const uint32_t* d_ids, const float* d_vecs, cudaStream_t stream) {
+  if (n == 0) return SDB_OK;
+  scatter_vectors_kernel<<<n, 128, 0, stream>>>(ix->d_vec, ix->vec_pitch, ix->d_exists, d_ids, d_vecs, ix->p.dim, n);
+  ix->launches++;
+  SDB_CUDA(cudaGetLastError());
+  if (ix->quant_active()) return launch_encode_rows(ix, n, d_ids, stream);
+  return SDB_OK;
+}
+
 static int validate(const sdb_params& p) {
   if (p.dim < 1 || p.dim > 4096) return fail(SDB_ERR_INVALID, "vector size must be between 1 and 4096");  // models/index.go:285
   if (p.metric < SDB_METRIC_EUCLIDEAN || p.metric > SDB_METRIC_HAVERSINE) return fail(SDB_ERR_INVALID, "unknown distance metric");

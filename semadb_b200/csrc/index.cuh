@@ -145,5 +145,7 @@ int launch_adc_tables(sdb_index* ix, uint32_t B, const float* d_queries, float* 
 int launch_merge(uint32_t S, uint32_t B, uint32_t k, const uint64_t* in_ids, const float* in_d, const uint32_t* in_c,
                  uint64_t* out_ids, float* out_d, uint32_t* out_c, cudaStream_t stream);
 int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const float* vectors);
+// VectorStore.Set on device-resident ids/vectors: scatter rows, mark exists, encode if fitted
+int set_rows_device(sdb_index* ix, uint32_t n, const uint32_t* d_ids, const float* d_vecs, cudaStream_t stream);
 int fit_locked(sdb_index* ix, uint64_t pq_first_row, int32_t* fitted);
 }  // namespace sdb

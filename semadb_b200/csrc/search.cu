@@ -7,76 +7,58 @@ namespace sdb {
 
 namespace {
 
-struct LaunchPlan {
-  int warps_per_cta = 1;
-  int ctas_per_sm = 1;
-  size_t smem = 0;
-};
-
-template <int KIND, int METRIC, int TRIPS, int UNROLL, int HBITS, bool FILTER, bool RETRY>
+template <int KIND, int METRIC, int TRIPS, int UNROLL, class VT, bool FILTER, bool RETRY, int MINB>
 int launch_variant(sdb_index* ix, const SearchArgs& a, cudaStream_t stream) {
-  auto kern = beam_search_kernel<KIND, METRIC, TRIPS, UNROLL, HBITS, FILTER, RETRY>;
+  auto kern = beam_search_kernel<KIND, METRIC, TRIPS, UNROLL, VT, FILTER, RETRY, MINB>;
   const uint32_t qfloats = (KIND == EVAL_ADC) ? 0 : (a.dim + 3) / 4 * 4;
   const uint32_t qwords = (KIND == EVAL_BITS) ? a.bits_pitch : 0;
-  const size_t per_warp = warp_smem_bytes<HBITS>(qfloats, qwords);
+  const size_t smem = warp_smem_bytes<VT, FILTER>(qfloats, qwords);
   static thread_local int cached_dev = -1;
-  static thread_local LaunchPlan plan;
-  static thread_local size_t plan_per_warp = 0;
-  if (cached_dev != ix->device || plan_per_warp != per_warp) {
-    LaunchPlan best;
-    int best_warps = 0;
-    for (int w : {1, 2, 4}) {
-      size_t smem = per_warp * w;
-      if (smem > ix->smem_optin) continue;
-      SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      int nb = 0;
-      SDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32 * w, smem));
-      if (nb * w > best_warps) {
-        best_warps = nb * w;
-        best.warps_per_cta = w;
-        best.ctas_per_sm = nb;
-        best.smem = smem;
-      }
-    }
-    if (best_warps == 0) return fail(SDB_ERR_INTERNAL, "beam search kernel does not fit in shared memory");
-    SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(best.smem)));
-    plan = best;
-    plan_per_warp = per_warp;
+  static thread_local size_t cached_smem = 0;
+  static thread_local int ctas_per_sm = 0;
+  if (cached_dev != ix->device || cached_smem != smem) {
+    if (smem > ix->smem_optin) return fail(SDB_ERR_INTERNAL, "beam search kernel does not fit in shared memory");
+    SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    int nb = 0;
+    SDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32, smem));
+    if (nb <= 0) return fail(SDB_ERR_INTERNAL, "beam search kernel cannot be resident");
+    ctas_per_sm = nb;
+    cached_smem = smem;
     cached_dev = ix->device;
   }
-  uint32_t resident = uint32_t(ix->sm_count) * plan.ctas_per_sm;
-  uint32_t need = RETRY ? uint32_t(ix->sm_count) : (a.B + plan.warps_per_cta - 1) / plan.warps_per_cta;
+  uint32_t resident = uint32_t(ix->sm_count) * ctas_per_sm;
+  uint32_t need = RETRY ? uint32_t(ix->sm_count) : a.B;
   uint32_t grid = need < resident ? need : resident;
   if (grid == 0) grid = 1;
-  kern<<<grid, 32 * plan.warps_per_cta, plan.smem, stream>>>(a, qfloats, qwords);
+  kern<<<grid, 32, smem, stream>>>(a, qfloats, qwords);
   ix->launches++;
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;
 }
 
-template <int KIND, int METRIC, int TRIPS, int UNROLL, bool FILTER>
+template <int KIND, int METRIC, int TRIPS, int UNROLL, bool FILTER, int MINB>
 int launch_with_retry(sdb_index* ix, SearchArgs a, cudaStream_t stream) {
-  int rc = launch_variant<KIND, METRIC, TRIPS, UNROLL, 13, FILTER, false>(ix, a, stream);
+  int rc = launch_variant<KIND, METRIC, TRIPS, UNROLL, VisitedCompact, FILTER, false, MINB>(ix, a, stream);
   if (rc) return rc;
-  // second pass over queries whose visited table overflowed (normally none): 32768 slots
+  // second pass over queries whose visited set overflowed (normally none): u32 table, 32768 slots
   a.work_counter = a.work_counter + 2;
   constexpr int RK = (KIND == EVAL_FLOAT_FIXED) ? EVAL_FLOAT_GENERIC : KIND;
-  return launch_variant<RK, METRIC, 1, 1, 15, FILTER, true>(ix, a, stream);
+  return launch_variant<RK, METRIC, 1, 1, VisitedTable<15>, FILTER, true, 1>(ix, a, stream);
 }
 
 template <int METRIC>
 int launch_float(sdb_index* ix, const SearchArgs& a, bool filtered, cudaStream_t stream) {
-  if (filtered) return launch_with_retry<EVAL_FLOAT_GENERIC, METRIC, 1, 1, true>(ix, a, stream);
+  if (filtered) return launch_with_retry<EVAL_FLOAT_GENERIC, METRIC, 1, 1, true, 1>(ix, a, stream);
   if (a.dim % 32 == 0) {
     switch (a.dim / 32) {
-      case 4: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 4, 8, false>(ix, a, stream);
-      case 8: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 8, 4, false>(ix, a, stream);
-      case 12: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 12, 3, false>(ix, a, stream);
-      case 24: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 24, 1, false>(ix, a, stream);
+      case 4: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 4, 8, false, 12>(ix, a, stream);
+      case 8: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 8, 4, false, 1>(ix, a, stream);
+      case 12: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 12, 3, false, 1>(ix, a, stream);
+      case 24: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 24, 1, false, 1>(ix, a, stream);
       default: break;
     }
   }
-  return launch_with_retry<EVAL_FLOAT_GENERIC, METRIC, 1, 1, false>(ix, a, stream);
+  return launch_with_retry<EVAL_FLOAT_GENERIC, METRIC, 1, 1, false, 1>(ix, a, stream);
 }
 
 }  // namespace
@@ -129,15 +111,15 @@ int launch_search(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k,
   const bool filtered = d_filter_bits != nullptr;
 
   if (ix->p.quantizer == SDB_QUANT_BINARY && ix->bq_fitted) {
-    return filtered ? launch_with_retry<EVAL_BITS, 0, 1, 1, true>(ix, a, stream)
-                    : launch_with_retry<EVAL_BITS, 0, 1, 1, false>(ix, a, stream);
+    return filtered ? launch_with_retry<EVAL_BITS, 0, 1, 1, true, 1>(ix, a, stream)
+                    : launch_with_retry<EVAL_BITS, 0, 1, 1, false, 1>(ix, a, stream);
   }
   if (ix->p.quantizer == SDB_QUANT_PRODUCT && ix->pq_fitted) {
     if ((rc = ix->d_adc.ensure(size_t(B) * ix->pqM * ix->pqK))) return rc;
     if ((rc = launch_adc_tables(ix, B, d_queries, ix->d_adc.p, stream))) return rc;
     a.adc = ix->d_adc.p;
-    return filtered ? launch_with_retry<EVAL_ADC, 0, 1, 1, true>(ix, a, stream)
-                    : launch_with_retry<EVAL_ADC, 0, 1, 1, false>(ix, a, stream);
+    return filtered ? launch_with_retry<EVAL_ADC, 0, 1, 1, true, 1>(ix, a, stream)
+                    : launch_with_retry<EVAL_ADC, 0, 1, 1, false, 1>(ix, a, stream);
   }
   switch (ix->store_metric) {
     case SDB_METRIC_EUCLIDEAN: return launch_float<METRIC_EUCLIDEAN>(ix, a, filtered, stream);

@@ -74,16 +74,20 @@ template <int HBITS>
 struct VisitedTable {
   static constexpr uint32_t SLOTS = 1u << HBITS;
   static constexpr uint32_t LIMIT = SLOTS - SLOTS / 8;  // refuse beyond 87.5 % load
+  static constexpr size_t BYTES = size_t(SLOTS) * 4;
   uint32_t* t;
+  bool failed;
+  __device__ __forceinline__ void init(unsigned char* base, uint32_t) { t = reinterpret_cast<uint32_t*>(base); }
   __device__ __forceinline__ void clear(int lane) {
     uint4 e = make_uint4(INVALID_ID, INVALID_ID, INVALID_ID, INVALID_ID);
     uint4* p = reinterpret_cast<uint4*>(t);
     for (uint32_t i = lane; i < SLOTS / 4; i += 32) p[i] = e;
+    failed = false;
   }
   // true if id was NOT present (and is now) — CheckAndVisit negated (distset.go:105-111).
   // Warp-convergent: every lane calls it (active = this lane has an id to test) and the
   // probe loop is driven by a vote, so the compiler keeps the warp converged afterwards.
-  __device__ __forceinline__ bool test_and_set(uint32_t id, bool active) {
+  __device__ __forceinline__ bool test_and_set(uint32_t id, bool active, int) {
     uint32_t slot = (id * 0x9E3779B1u) >> (32 - HBITS);
     bool pending = active, isnew = false;
     while (__any_sync(SDB_FULL, pending)) {
@@ -94,6 +98,72 @@ struct VisitedTable {
         else slot = (slot + 1) & (SLOTS - 1);
       }
     }
+    return isnew;
+  }
+};
+
+// ---- exact visited set, compact form: 8192 x 16-bit entries + a 32-entry u32 stash ------
+// Ids are < rows <= 2^b. pi(id) = id*A mod 2^b (A odd) is a bijection on b bits; the top 13
+// bits of pi(id) pick the home slot and the low rb = b-13 bits are the remainder. An entry
+// stores 1 + rem + (disp << rb), disp = linear-probe displacement, so (slot, entry)
+// identifies the id exactly (quotienting) and 0 means empty. A probe that would need
+// disp > dmax = 2^(16-rb) - 2 cannot be encoded: the query is then re-run by the RETRY
+// launch (u32 table). dmax is 254 at 2M rows and 30 at 16M rows, so this is rare. Half the
+// footprint of the u32 table => twice the resident queries per SM.
+struct VisitedCompact {
+  static constexpr int HB = 13;
+  static constexpr uint32_t SLOTS = 1u << HB;
+  static constexpr uint32_t LIMIT = SLOTS - SLOTS / 8;
+  static constexpr size_t BYTES = SLOTS * 2;
+  unsigned short* t;
+  uint32_t mask, rb, rmask, dmax;
+  bool failed;
+  __device__ __forceinline__ void init(unsigned char* base, uint32_t rows) {
+    t = reinterpret_cast<unsigned short*>(base);
+    uint32_t b = rows <= SLOTS ? HB : 32 - __clz(rows - 1);
+    if (b < HB) b = HB;
+    rb = b - HB;
+    mask = b >= 32 ? 0xFFFFFFFFu : ((1u << b) - 1);
+    rmask = (1u << rb) - 1;
+    dmax = rb >= 15 ? 0 : ((1u << (16 - rb)) - 2);
+    if (dmax > 4096) dmax = 4096;
+  }
+  __device__ __forceinline__ void clear(int lane) {
+    uint4 z = make_uint4(0, 0, 0, 0);
+    uint4* p = reinterpret_cast<uint4*>(t);
+    for (uint32_t i = lane; i < SLOTS * 2 / 16; i += 32) p[i] = z;
+    failed = false;
+  }
+  __device__ __forceinline__ bool test_and_set(uint32_t id, bool active, int lane) {
+    const uint32_t v = (id * 0x9E3779B1u) & mask;
+    uint32_t slot = v >> rb;
+    const uint32_t code0 = 1 + (v & rmask);
+    uint32_t disp = 0;
+    bool pending = active, isnew = false, spill = false;
+    // 16-bit compare-and-swap done as a 32-bit CAS on the containing word, inside the same
+    // vote-driven loop (the library's 16-bit atomicCAS hides a divergent retry loop, which
+    // makes the compiler fall back to WARPSYNC.COLLECTIVE shuffles for the rest of the kernel)
+    volatile uint32_t* tw = reinterpret_cast<volatile uint32_t*>(t);
+    while (__any_sync(SDB_FULL, pending)) {
+      if (pending) {
+        const uint32_t code = code0 + (disp << rb);
+        const uint32_t sh = (slot & 1) * 16;
+        const uint32_t w = tw[slot >> 1];
+        const uint32_t half = (w >> sh) & 0xFFFFu;
+        if (half == 0) {
+          const uint32_t old = atomicCAS(const_cast<uint32_t*>(tw) + (slot >> 1), w, w | (code << sh));
+          if (old == w) { isnew = true; pending = false; }
+          // else: the word changed under us; re-read the same slot next round
+        } else if (half == code) {
+          pending = false;
+        } else {
+          slot = (slot + 1) & (SLOTS - 1);
+          if (++disp > dmax) { pending = false; spill = true; }
+        }
+      }
+    }
+    // a probe chain longer than dmax cannot be encoded: hand the query to the RETRY launch
+    if (__any_sync(SDB_FULL, spill)) failed = true;
     return isnew;
   }
 };
@@ -320,37 +390,43 @@ struct AdcEval {
 
 enum EvalKind : int { EVAL_FLOAT_FIXED = 0, EVAL_FLOAT_GENERIC = 1, EVAL_BITS = 2, EVAL_ADC = 3 };
 
-// ---- shared-memory layout per warp --------------------------------------------------
-template <int HBITS>
+// ---- shared-memory layout per query-warp ------------------------------------------------
+template <class VT, bool FILTER>
 __host__ __device__ constexpr size_t warp_smem_bytes(uint32_t qfloats, uint32_t qwords) {
-  return (size_t(1) << HBITS) * 4 + LIST_SLOTS * 8 + LIST_SLOTS * 8 /*filter result list*/ + CAND_SLOTS * 8 +
+  return ((VT::BYTES + 15) / 16) * 16 + LIST_SLOTS * 8 + (FILTER ? LIST_SLOTS * 8 : 0) + CAND_SLOTS * 8 +
          ((size_t(qfloats) * 4 + 15) / 16) * 16 + ((size_t(qwords) * 8 + 15) / 16) * 16;
 }
 
 // ---- the kernel ---------------------------------------------------------------------
-template <int KIND, int METRIC, int TRIPS, int UNROLL, int HBITS, bool FILTER, bool RETRY>
-__global__ void __launch_bounds__(128) beam_search_kernel(SearchArgs a, uint32_t qfloats, uint32_t qwords) {
+// One warp per CTA, one query per warp at a time; MINB = CTAs per SM the register budget
+// must allow (launch bounds).
+template <int KIND, int METRIC, int TRIPS, int UNROLL, class VT, bool FILTER, bool RETRY, int MINB>
+__global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uint32_t qfloats, uint32_t qwords) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  unsigned char* base = smem_raw + size_t(warp) * warp_smem_bytes<HBITS>(qfloats, qwords);
-  VisitedTable<HBITS> vt;
-  vt.t = reinterpret_cast<uint32_t*>(base);
-  base += (size_t(1) << HBITS) * 4;
+  unsigned char* base = smem_raw;
+  VT vt;
+  vt.init(base, a.rows);
+  base += ((VT::BYTES + 15) / 16) * 16;
   CandList list;
   list.id = reinterpret_cast<uint32_t*>(base);
   list.dist = reinterpret_cast<float*>(base + LIST_SLOTS * 4);
   base += LIST_SLOTS * 8;
   CandList res;  // filter mode: k-bounded result set (search.go:33-35)
-  res.id = reinterpret_cast<uint32_t*>(base);
-  res.dist = reinterpret_cast<float*>(base + LIST_SLOTS * 4);
-  base += LIST_SLOTS * 8;
+  res.id = list.id;
+  res.dist = list.dist;
+  if (FILTER) {
+    res.id = reinterpret_cast<uint32_t*>(base);
+    res.dist = reinterpret_cast<float*>(base + LIST_SLOTS * 4);
+    base += LIST_SLOTS * 8;
+  }
   uint32_t* cid = reinterpret_cast<uint32_t*>(base);
   float* cdist = reinterpret_cast<float*>(base + CAND_SLOTS * 4);
   base += CAND_SLOTS * 8;
   float* qs = reinterpret_cast<float*>(base);
   base += ((size_t(qfloats) * 4 + 15) / 16) * 16;
   uint64_t* qbits = reinterpret_cast<uint64_t*>(base);
+  const uint32_t lt = (1u << lane) - 1;
 
   for (;;) {
     uint32_t qi = 0;
@@ -412,32 +488,38 @@ __global__ void __launch_bounds__(128) beam_search_kernel(SearchArgs a, uint32_t
       }
     };
 
+    // stage ids i0/i1 (adjacency order c = lane, lane+32) that pass the visited
+    // test-and-set into cid[]; returns how many
+    auto visit_and_stage = [&](uint32_t i0, bool a0, uint32_t i1, bool a1) -> int {
+      bool new0 = vt.test_and_set(i0, a0, lane);
+      bool new1 = vt.test_and_set(i1, a1, lane);
+      uint32_t b0 = __ballot_sync(SDB_FULL, new0), b1 = __ballot_sync(SDB_FULL, new1);
+      const int t0 = __popc(b0);
+      if (new0) cid[__popc(b0 & lt)] = i0;
+      if (new1) cid[t0 + __popc(b1 & lt)] = i1;
+      __syncwarp();
+      return t0 + __popc(b1);
+    };
+
     if (FILTER) {
       // searchSet.Add(filterPoints...) (plain append, search.go:49) and
       // resultSet.AddWithLimit(filterPoints...) (search.go:50)
-      int nf = int(min(a.n_filter_seed, a.L));
+      const int nf = int(min(a.n_filter_seed, a.L));
       for (int b0 = 0; b0 < nf; b0 += CAND_SLOTS) {
-        int n = min(CAND_SLOTS, nf - b0);
-        // test-and-set in order; seeds are unique ascending ids
-        bool n0 = false, n1 = false;
-        uint32_t i0 = 0, i1 = 0;
-        if (lane < n) i0 = __ldg(a.filter_seed + b0 + lane);
-        n0 = vt.test_and_set(i0, lane < n);
-        if (lane + 32 < n) i1 = __ldg(a.filter_seed + b0 + lane + 32);
-        n1 = vt.test_and_set(i1, lane + 32 < n);
-        uint32_t bb0 = __ballot_sync(SDB_FULL, n0), bb1 = __ballot_sync(SDB_FULL, n1);
-        int t0 = __popc(bb0);
-        int nn = t0 + __popc(bb1);
-        uint32_t lt = (1u << lane) - 1;
-        if (n0) cid[__popc(bb0 & lt)] = i0;
-        if (n1) cid[t0 + __popc(bb1 & lt)] = i1;
-        __syncwarp();
+        const int n = min(CAND_SLOTS, nf - b0);
+        uint32_t i0 = lane < n ? __ldg(a.filter_seed + b0 + lane) : 0;
+        uint32_t i1 = lane + 32 < n ? __ldg(a.filter_seed + b0 + lane + 32) : 0;
+        const int nn = visit_and_stage(i0, lane < n, i1, lane + 32 < n);
         nvisited += nn;
         ndist += nn;
         evaluate(nn);
-        for (int c = lane; c < nn; c += 32) {
-          list.id[list.len + c] = cid[c];
-          list.dist[list.len + c] = cdist[c];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          int c = lane + 32 * j;
+          if (c < nn) {
+            list.id[list.len + c] = cid[c];
+            list.dist[list.len + c] = cdist[c];
+          }
         }
         list.len += nn;
         __syncwarp();
@@ -446,34 +528,34 @@ __global__ void __launch_bounds__(128) beam_search_kernel(SearchArgs a, uint32_t
     }
 
     // searchSet.AddWithLimit(startNode) (search.go:57-61)
-    {
-      bool isnew = false;
-      isnew = vt.test_and_set(START_ID, lane == 0);
-      isnew = __shfl_sync(SDB_FULL, isnew, 0);
-      if (isnew) {
-        if (lane == 0) cid[0] = START_ID;
-        __syncwarp();
-        ++nvisited;
-        ++ndist;
-        evaluate(1);
-        add_with_limit(list, 1);
-      }
+    if (visit_and_stage(START_ID, lane == 0, 0, false) > 0) {
+      ++nvisited;
+      ++ndist;
+      evaluate(1);
+      add_with_limit(list, 1);
     }
 
-    // main loop (search.go:65-98)
+    // main loop (search.go:65-98). pf_*: adjacency row of the runner-up candidate, fetched
+    // one hop early; used if that candidate is indeed expanded next.
+    uint32_t pf_id = INVALID_ID, pf_n0 = INVALID_ID, pf_n1 = INVALID_ID;
     for (;;) {
       const int lim = min(list.len, int(a.L));
-      int pos = -1;
+      int pos = -1, pos2 = -1;
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         int p = lane + 32 * j;
         bool un = (p < lim) && !(list.id[p] & EXPANDED_FLAG);
         uint32_t b = __ballot_sync(SDB_FULL, un);
-        if (b && pos < 0) pos = 32 * j + __ffs(b) - 1;
+        if (b && pos < 0) {
+          pos = 32 * j + __ffs(b) - 1;
+          b &= b - 1;
+        }
+        if (b && pos >= 0 && pos2 < 0) pos2 = 32 * j + __ffs(b) - 1;
       }
       if (pos < 0) break;
       const uint32_t e = list.id[pos];
       const float edist = list.dist[pos];
+      const uint32_t e2 = pos2 >= 0 ? list.id[pos2] : INVALID_ID;
       __syncwarp();
       if (lane == 0) list.id[pos] = e | EXPANDED_FLAG;
       if (a.vis_ids != nullptr && lane == 0) {
@@ -484,37 +566,43 @@ __global__ void __launch_bounds__(128) beam_search_kernel(SearchArgs a, uint32_t
       }
       ++hops;
       // neighbours, adjacency order c = lane, lane+32
-      const uint32_t* arow = a.adj + size_t(e) * a.R;
-      uint32_t n0 = lane < int(a.R) ? __ldg(arow + lane) : INVALID_ID;
-      uint32_t n1 = lane + 32 < int(a.R) ? __ldg(arow + lane + 32) : INVALID_ID;
-      bool new0 = vt.test_and_set(n0, n0 != INVALID_ID);
-      bool new1 = vt.test_and_set(n1, n1 != INVALID_ID);
-      uint32_t b0 = __ballot_sync(SDB_FULL, new0), b1 = __ballot_sync(SDB_FULL, new1);
-      const int t0 = __popc(b0);
-      const int nnew = t0 + __popc(b1);
-      const uint32_t lt = (1u << lane) - 1;
-      if (new0) cid[__popc(b0 & lt)] = n0;
-      if (new1) cid[t0 + __popc(b1 & lt)] = n1;
-      __syncwarp();
+      uint32_t n0, n1;
+      if (e == pf_id) {
+        n0 = pf_n0;
+        n1 = pf_n1;
+      } else {
+        const uint32_t* arow = a.adj + size_t(e) * a.R;
+        n0 = lane < int(a.R) ? __ldg(arow + lane) : INVALID_ID;
+        n1 = lane + 32 < int(a.R) ? __ldg(arow + lane + 32) : INVALID_ID;
+      }
+      pf_id = e2;
+      if (e2 != INVALID_ID) {
+        const uint32_t* prow = a.adj + size_t(e2) * a.R;
+        pf_n0 = lane < int(a.R) ? __ldg(prow + lane) : INVALID_ID;
+        pf_n1 = lane + 32 < int(a.R) ? __ldg(prow + lane + 32) : INVALID_ID;
+      }
+      const int nnew = visit_and_stage(n0, n0 != INVALID_ID, n1, n1 != INVALID_ID);
       nvisited += nnew;
       ndist += nnew;
-      if (nvisited > VisitedTable<HBITS>::LIMIT) { overflow = true; break; }
+      if (nvisited > VT::LIMIT || vt.failed) { overflow = true; break; }
       if (nnew > 0) {
         evaluate(nnew);
         add_with_limit(list, nnew);
       }
       if (FILTER) {
         // resultSet.AddWithLimit(distElem.Point) if the expanded node passes the filter
-        // (search.go:93-95). resultSet dedupes with its own visited set: a node is
-        // expanded at most once and seeds were added up front, so test membership.
+        // (search.go:93-95). resultSet dedupes with its own visited set, which holds the
+        // seeds (search.go:50) and every node added here; a node is expanded at most once.
         bool in_filter = (__ldg(a.filter_bits + (e >> 5)) >> (e & 31)) & 1u;
         if (in_filter) {
-          bool dup = false;
-          for (int p = lane; p < res.len; p += 32) dup |= ((res.id[p] & ID_MASK) == e);
-          // seeds that were rejected/evicted from res are still "visited" in its set
           bool seeded = false;
-          for (uint32_t s = lane; s < min(a.n_filter_seed, a.L); s += 32) seeded |= (__ldg(a.filter_seed + s) == e);
-          if (!__any_sync(SDB_FULL, dup || seeded)) {
+          const uint32_t ns = min(a.n_filter_seed, a.L);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            uint32_t sidx = lane + 32 * j;
+            seeded |= (sidx < ns) && (__ldg(a.filter_seed + sidx) == e);
+          }
+          if (!__any_sync(SDB_FULL, seeded)) {
             if (lane == 0) { cid[0] = e; cdist[0] = edist; }
             __syncwarp();
             add_with_limit(res, 1);
@@ -540,7 +628,7 @@ __global__ void __launch_bounds__(128) beam_search_kernel(SearchArgs a, uint32_t
         uint32_t nid = p < out.len ? (out.id[p] & ID_MASK) : START_ID;
         bool keep = (p < out.len) && (nid != START_ID);
         uint32_t b = __ballot_sync(SDB_FULL, keep);
-        int r = written + __popc(b & ((1u << lane) - 1));
+        int r = written + __popc(b & lt);
         if (keep && r < int(a.k)) {
           a.out_ids[size_t(qi) * a.k + r] = uint64_t(nid);
           a.out_dists[size_t(qi) * a.k + r] = out.dist[p];
