@@ -218,34 +218,18 @@ def main():
         gix.insert_batch(ids, X)
         log(f"[rank {rank}] GPU-built graph (K8): {time.time() - t0:.1f}s")
 
+    from semadb_b200.sharded import SHARD_SHIFT, ShardedSearcher, exchange_topk, pack_global_ids
     B = args.queries
-    d_q = torch.from_numpy(Q).to(dev)
-    d_ids = torch.zeros((B, K), dtype=torch.int64, device=dev)
-    d_d = torch.zeros((B, K), dtype=torch.float32, device=dev)
-    d_c = torch.zeros((B,), dtype=torch.int32, device=dev)
-    if world > 1:
-        g_ids = torch.zeros((world, B, K), dtype=torch.int64, device=dev)
-        g_d = torch.zeros((world, B, K), dtype=torch.float32, device=dev)
-        g_c = torch.zeros((world, B), dtype=torch.int32, device=dev)
-        m_ids = torch.zeros((B, K), dtype=torch.int64, device=dev)
-        m_d = torch.zeros((B, K), dtype=torch.float32, device=dev)
-        m_c = torch.zeros((B,), dtype=torch.int32, device=dev)
+    d_q = torch.from_numpy(Q).to(dev)  # the broadcast query batch, resident on every rank
+    searcher = ShardedSearcher(gix, rank, world)
     stream = torch.cuda.current_stream()
     launches = [0]
+    result = [None]
 
     def step():
         before = gix.launch_count
-        gix.search_batch_device(d_q, K, L, d_ids, d_d, d_c, stream.cuda_stream)
-        launches[0] += gix.launch_count - before
-        if world > 1:
-            d_ids.add_(rank << 40)  # global id = (shard << 40) | node id
-            dist.all_gather_into_tensor(g_ids, d_ids)
-            dist.all_gather_into_tensor(g_d, d_d)
-            dist.all_gather_into_tensor(g_c, d_c)
-            _capi.check(lib.sdb_merge_topk_device(local_rank, world, B, K, g_ids.data_ptr(), g_d.data_ptr(),
-                                                  g_c.data_ptr(), m_ids.data_ptr(), m_d.data_ptr(), m_c.data_ptr(),
-                                                  stream.cuda_stream))
-            launches[0] += 1
+        result[0] = searcher.search_batch_device(d_q, K, L)  # K1 (+ all-gather + K6 at N>1)
+        launches[0] += gix.launch_count - before + (1 if world > 1 else 0)
 
     def barrier():
         if world > 1:
@@ -271,11 +255,14 @@ def main():
 
     # beam-search kernel alone (the dominant kernel), same stream, same inputs
     ks, ke = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k_ids = torch.zeros((B, K), dtype=torch.int64, device=dev)
+    k_d = torch.zeros((B, K), dtype=torch.float32, device=dev)
+    k_c = torch.zeros((B,), dtype=torch.int32, device=dev)
     kern_ms = []
     for _ in range(min(args.steps, 10)):
         torch.cuda.synchronize()
         ks.record(stream)
-        gix.search_batch_device(d_q, K, L, d_ids, d_d, d_c, stream.cuda_stream)
+        gix.search_batch_device(d_q, K, L, k_ids, k_d, k_c, stream.cuda_stream)
         ke.record(stream)
         torch.cuda.synchronize()
         kern_ms.append(ks.elapsed_time(ke))
@@ -289,24 +276,26 @@ def main():
     h_c = torch.zeros((B,), dtype=torch.int32).pin_memory()
     import ctypes as C
 
+    m_ids = torch.zeros((B, K), dtype=torch.int64, device=dev)
+    m_d = torch.zeros((B, K), dtype=torch.float32, device=dev)
+    m_c = torch.zeros((B,), dtype=torch.int32, device=dev)
+
     def e2e_step():
         _capi.check(lib.sdb_search_batch(gix._h, B, C.cast(h_q.data_ptr(), _capi.f32p), K, L, None, 0,
                                          C.cast(h_ids.data_ptr(), _capi.u64p), C.cast(h_d.data_ptr(), _capi.f32p),
                                          C.cast(h_c.data_ptr(), _capi.u32p)))
         if world > 1:
-            # host fan-in of the per-shard lists is the Go cluster layer's job; here the
-            # device path (all-gather + merge) stands in for it
-            d_ids.copy_(h_ids, non_blocking=True)
-            d_d.copy_(h_d, non_blocking=True)
-            d_c.copy_(h_c, non_blocking=True)
-            d_ids.add_(rank << 40)
-            dist.all_gather_into_tensor(g_ids, d_ids)
-            dist.all_gather_into_tensor(g_d, d_d)
-            dist.all_gather_into_tensor(g_c, d_c)
+            # The host fan-in of per-shard lists is the Go cluster layer's job
+            # (cluster/actions.go:357-376); here the lists go back to the device and through
+            # the same all-gather + merge (K6), and the merged list returns to the host.
+            g_ids, g_d, g_c = exchange_topk(pack_global_ids(h_ids.to(dev, non_blocking=True), rank),
+                                            h_d.to(dev, non_blocking=True), h_c.to(dev, non_blocking=True))
             _capi.check(lib.sdb_merge_topk_device(local_rank, world, B, K, g_ids.data_ptr(), g_d.data_ptr(),
                                                   g_c.data_ptr(), m_ids.data_ptr(), m_d.data_ptr(), m_c.data_ptr(),
                                                   stream.cuda_stream))
             h_ids.copy_(m_ids)
+            h_d.copy_(m_d)
+            h_c.copy_(m_c)
 
     for _ in range(2):
         e2e_step()
@@ -330,7 +319,7 @@ def main():
     if rank == 0:
         nq = min(args.recall_queries, B)
         fi, fd, fc = gix.flat_search_batch(Q[:nq], K)  # exact ground truth on the GPU (K5)
-        got = d_ids.cpu().numpy()[:nq] & ((1 << 40) - 1)
+        got = k_ids.cpu().numpy()[:nq]  # this rank's shard-local result
         recall = float(np.mean([len(set(got[b].tolist()) & set(fi[b].tolist())) / K for b in range(nq)]))
         if not args.no_cpu_baseline and world == 1:
             from oracle import oraclelib as O
@@ -351,9 +340,9 @@ def main():
                    "sample": f"all {B} queries x {reps} passes, {threads} threads, one query per thread",
                    "single_thread_qps": qps1}
             if args.graph == "oracle":
-                same = (d_ids.cpu().numpy() == ref["ids"].astype(np.int64)).all(axis=1).mean()
+                same = (k_ids.cpu().numpy() == ref["ids"].astype(np.int64)).all(axis=1).mean()
                 parity = {"id_rows_identical_to_oracle": float(same),
-                          "dists_bit_identical": bool(d_d.cpu().numpy().tobytes() == ref["dists"].tobytes())}
+                          "dists_bit_identical": bool(k_d.cpu().numpy().tobytes() == ref["dists"].tobytes())}
 
     if rank == 0:
         ms_step = ms_total / args.steps

@@ -1,0 +1,113 @@
+"""Shard-per-GPU search: the collection is split into independent shards (one graph, one
+start node, one id space per GPU), queries are broadcast, every GPU searches its own
+shard (K1), the per-GPU top-k lists are exchanged with one NCCL all-gather over NVLink and
+merged by the K6 kernel on every rank.
+
+Mirrors ClusterNode.SearchPoints (cluster/actions.go:275-379): per-shard request limit
+(actions.go:291-299), scatter to every shard (actions.go:316-351), concatenate + sort by
+HybridScore descending + truncate (actions.go:357-376).
+
+Point placement: the reference fills shards sequentially from the UUID-sorted batch
+(cluster/placement.go:23-50; UUIDs are random, so the effect is a uniform random partition
+into near-equal chunks). Here: a seeded shuffle, then `position mod n_shards` — also a
+uniform random partition into near-equal shards.
+
+One process per GPU (torch.distributed, backend nccl); torch is plumbing only (device
+tensors, the collective). The merge runs through the C ABI.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+from . import _capi
+
+SHARD_SHIFT = 40  # global id = (shard << 40) | node id
+
+
+def partition_points(n_points: int, n_shards: int, seed: int = 0) -> np.ndarray:
+    """shard index of each of n_points (seeded shuffle then position mod n_shards)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    perm = rng.permutation(n_points)
+    out = np.empty(n_points, dtype=np.int32)
+    out[perm] = np.arange(n_points, dtype=np.int64) % n_shards
+    return out
+
+
+def shard_limit(limit: int, n_shards: int, max_search_limit: int = 75) -> int:
+    """targetLimit of cluster/actions.go:291-299 (f32 arithmetic like the reference)."""
+    return int(_capi.lib().sdb_shard_limit(int(limit), int(n_shards), int(max_search_limit)))
+
+
+def pack_global_ids(local_ids, shard: int):
+    """works on numpy arrays and torch tensors (int64/uint64)."""
+    return local_ids + (int(shard) << SHARD_SHIFT)
+
+
+def unpack_global_ids(global_ids):
+    return global_ids >> SHARD_SHIFT, global_ids & ((1 << SHARD_SHIFT) - 1)
+
+
+def exchange_topk(ids, dists, counts, group=None):
+    """All-gather of per-rank [B,k] results into shard-major [S,B,k] / [S,B] tensors.
+    12*k+4 bytes per query per rank — latency-bound, one collective per tensor."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+
+    def gather(t):
+        t = t.contiguous()
+        # concatenated-along-dim-0 output is accepted by both nccl and gloo
+        out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t, group=group)
+        return out.view((world,) + tuple(t.shape))
+
+    g_ids, g_d, g_c = gather(ids), gather(dists), gather(counts)
+    return g_ids, g_d, g_c
+
+
+class ShardedSearcher:
+    """One rank's view of a sharded collection."""
+
+    def __init__(self, index, rank: Optional[int] = None, world: Optional[int] = None, group=None):
+        import torch.distributed as dist
+        self.index = index
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self._bufs = None
+
+    def _ensure(self, B, k, device):
+        import torch
+        if self._bufs is not None and self._bufs[0].shape == (B, k):
+            return
+        self._bufs = (torch.zeros((B, k), dtype=torch.int64, device=device),
+                      torch.zeros((B, k), dtype=torch.float32, device=device),
+                      torch.zeros((B,), dtype=torch.int32, device=device),
+                      torch.zeros((B, k), dtype=torch.int64, device=device),
+                      torch.zeros((B, k), dtype=torch.float32, device=device),
+                      torch.zeros((B,), dtype=torch.int32, device=device))
+
+    def search_batch_device(self, d_queries, k: int, search_size: int, max_search_limit: int = 75):
+        """d_queries: [B, dim] f32 CUDA tensor, identical on every rank (broadcast by the
+        caller). Returns merged (global ids [B,k] int64, dists [B,k], counts [B]) on every rank."""
+        import torch
+        B = int(d_queries.shape[0])
+        dev = d_queries.device
+        self._ensure(B, k, dev)
+        l_ids, l_d, l_c, m_ids, m_d, m_c = self._bufs
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        # the reference asks each shard for min(k, floor(k/S*1.42+10)) results; the local
+        # search still fills k slots and the merge reads only the first `per_shard`
+        per_shard = shard_limit(k, self.world, max_search_limit)
+        self.index.search_batch_device(d_queries, k, search_size, l_ids, l_d, l_c, stream)
+        if per_shard < k:
+            l_c.clamp_(max=per_shard)
+        if self.world == 1:
+            return l_ids, l_d, l_c
+        g_ids, g_d, g_c = exchange_topk(pack_global_ids(l_ids, self.rank), l_d, l_c, self.group)
+        _capi.check(_capi.lib().sdb_merge_topk_device(dev.index or 0, self.world, B, k, g_ids.data_ptr(),
+                                                      g_d.data_ptr(), g_c.data_ptr(), m_ids.data_ptr(),
+                                                      m_d.data_ptr(), m_c.data_ptr(), stream))
+        return m_ids, m_d, m_c
