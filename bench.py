@@ -47,6 +47,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    of this same command (profiles/k1_traffic.json); None if absent."""
+    p = ROOT / "profiles" / "k1_traffic.json"
+    try:
+        t = json.loads(p.read_text())
+        return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -359,7 +370,9 @@ def main():
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                         "frac": achieved / peak,
+                         "traffic": measured_traffic() if (args.n == 1_000_000 and B == 10_000) else None,
+                         "algorithmic_bytes_per_launch": bytes_q * B, "peak_kind": peak_kind,
                          "kernel": "beam_search_kernel", "kernel_ms": kern_ms},
             "cpu_baseline": cpu,
             "e2e": {"value": world * B / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": B * DIM * 4,

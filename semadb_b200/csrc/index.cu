@@ -208,6 +208,7 @@ int sdb_index_create(const sdb_params* params, sdb_index** out) {
   }
   ix->sm_count = prop.multiProcessorCount;
   ix->smem_optin = prop.sharedMemPerBlockOptin;
+  ix->smem_per_sm = prop.sharedMemPerMultiprocessor;
   if ((e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     delete ix;
     return cuda_fail(e, "cudaStreamCreate");

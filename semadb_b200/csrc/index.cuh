@@ -82,6 +82,7 @@ struct sdb_index {
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   size_t smem_optin = 0;
+  size_t smem_per_sm = 233472;
   mutable std::mutex mu;
 
   uint32_t rows = 0;  // allocated rows

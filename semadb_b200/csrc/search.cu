@@ -3,14 +3,19 @@
 
 #include "index.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace sdb {
 
 namespace {
 
-template <int KIND, int METRIC, int TRIPS, int UNROLL, class VT, bool FILTER, bool RETRY, int MINB>
+template <int KIND, int METRIC, int TRIPS, int SETS, bool LEGACY, int MERGE_MIN, class VT, bool FILTER, bool RETRY, int MINB>
 int launch_variant(sdb_index* ix, const SearchArgs& a, cudaStream_t stream) {
-  auto kern = beam_search_kernel<KIND, METRIC, TRIPS, UNROLL, VT, FILTER, RETRY, MINB>;
-  const uint32_t qfloats = (KIND == EVAL_ADC) ? 0 : (a.dim + 3) / 4 * 4;
+  auto kern = beam_search_kernel<KIND, METRIC, TRIPS, SETS, LEGACY, MERGE_MIN, VT, FILTER, RETRY, MINB>;
+  // FloatEvalGrouped keeps short queries (<= 4 float4 per lane) in registers: no shared copy
+  constexpr bool QREG = (KIND == EVAL_FLOAT_FIXED) && !LEGACY && TRIPS <= 4;
+  const uint32_t qfloats = (KIND == EVAL_ADC || QREG) ? 0 : (a.dim + 3) / 4 * 4;
   const uint32_t qwords = (KIND == EVAL_BITS) ? a.bits_pitch : 0;
   const size_t smem = warp_smem_bytes<VT, FILTER>(qfloats, qwords);
   static thread_local int cached_dev = -1;
@@ -22,7 +27,18 @@ int launch_variant(sdb_index* ix, const SearchArgs& a, cudaStream_t stream) {
     int nb = 0;
     SDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 32, smem));
     if (nb <= 0) return fail(SDB_ERR_INTERNAL, "beam search kernel cannot be resident");
+    if (MINB > 1 && nb > MINB) nb = MINB;
     ctas_per_sm = nb;
+    // The unified L1/shared array is also where in-flight global loads land: ask for no more
+    // shared memory than the resident CTAs need so the rest stays L1 (more rows in flight).
+    const size_t need_smem = size_t(nb) * (smem + 1024);
+    int pct = int((need_smem * 100 + ix->smem_per_sm - 1) / ix->smem_per_sm);
+    if (const char* e = getenv("SDB_K1_CARVEOUT")) pct = atoi(e);
+    if (pct > 100) pct = 100;
+    SDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    if (getenv("SDB_DEBUG_OCC"))
+      fprintf(stderr, "[sdb] beam_search variant: smem %zu B/CTA, %d CTAs/SM, carveout %d%% (%zu KB needed)\n", smem, nb, pct,
+              need_smem >> 10);
     cached_smem = smem;
     cached_dev = ix->device;
   }
@@ -30,35 +46,54 @@ int launch_variant(sdb_index* ix, const SearchArgs& a, cudaStream_t stream) {
   uint32_t need = RETRY ? uint32_t(ix->sm_count) : a.B;
   uint32_t grid = need < resident ? need : resident;
   if (grid == 0) grid = 1;
+  if (!RETRY && (a.flags & 2u) && a.B > grid) {
+    // equal number of queries per resident warp: no half-empty last wave
+    const uint32_t waves = (a.B + grid - 1) / grid;
+    grid = (a.B + waves - 1) / waves;
+  }
   kern<<<grid, 32, smem, stream>>>(a, qfloats, qwords);
   ix->launches++;
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;
 }
 
-template <int KIND, int METRIC, int TRIPS, int UNROLL, bool FILTER, int MINB>
+template <int KIND, int METRIC, int TRIPS, int SETS, bool LEGACY, int MERGE_MIN, bool FILTER, int MINB, class VT = VisitedCompactN<5888>>
 int launch_with_retry(sdb_index* ix, SearchArgs a, cudaStream_t stream) {
-  int rc = launch_variant<KIND, METRIC, TRIPS, UNROLL, VisitedCompact, FILTER, false, MINB>(ix, a, stream);
+  int rc = launch_variant<KIND, METRIC, TRIPS, SETS, LEGACY, MERGE_MIN, VT, FILTER, false, MINB>(ix, a, stream);
   if (rc) return rc;
   // second pass over queries whose visited set overflowed (normally none): u32 table, 32768 slots
   a.work_counter = a.work_counter + 2;
   constexpr int RK = (KIND == EVAL_FLOAT_FIXED) ? EVAL_FLOAT_GENERIC : KIND;
-  return launch_variant<RK, METRIC, 1, 1, VisitedTable<15>, FILTER, true, 1>(ix, a, stream);
+  return launch_variant<RK, METRIC, 1, 1, false, 0, VisitedTable<15>, FILTER, true, 1>(ix, a, stream);
+}
+
+// Tuning knob for A/B runs on the GPU (not part of the ABI): SDB_K1_VARIANT picks the
+// evaluator layout / list-update form of the dim-128 kernel.
+int k1_variant() {
+  const char* e = getenv("SDB_K1_VARIANT");
+  return e ? atoi(e) : -1;
 }
 
 template <int METRIC>
 int launch_float(sdb_index* ix, const SearchArgs& a, bool filtered, cudaStream_t stream) {
-  if (filtered) return launch_with_retry<EVAL_FLOAT_GENERIC, METRIC, 1, 1, true, 1>(ix, a, stream);
+  if (filtered) return launch_with_retry<EVAL_FLOAT_GENERIC, METRIC, 1, 1, false, 0, true, 1>(ix, a, stream);
   if (a.dim % 32 == 0) {
     switch (a.dim / 32) {
-      case 4: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 4, 8, false, 12>(ix, a, stream);
-      case 8: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 8, 4, false, 1>(ix, a, stream);
-      case 12: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 12, 3, false, 1>(ix, a, stream);
-      case 24: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 24, 1, false, 1>(ix, a, stream);
+      case 4:
+        switch (k1_variant()) {
+          // round-1 baseline (unpipelined evaluator, sequential list update, 8192-slot table)
+          case 0: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 4, 8, true, 0, false, 12, VisitedCompact>(ix, a, stream);
+          case 1: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 4, 6, false, 0, false, 12>(ix, a, stream);
+          case 2: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 4, 5, false, 2, false, 12, VisitedCompactN<6144>>(ix, a, stream);
+          default: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 4, 6, false, 2, false, 12>(ix, a, stream);
+        }
+      case 8: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 8, 3, false, 2, false, 12>(ix, a, stream);
+      case 12: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 12, 2, false, 2, false, 12>(ix, a, stream);
+      case 24: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 24, 1, false, 2, false, 12>(ix, a, stream);
       default: break;
     }
   }
-  return launch_with_retry<EVAL_FLOAT_GENERIC, METRIC, 1, 1, false, 1>(ix, a, stream);
+  return launch_with_retry<EVAL_FLOAT_GENERIC, METRIC, 1, 1, false, 2, false, 12>(ix, a, stream);
 }
 
 }  // namespace
@@ -104,6 +139,10 @@ int launch_search(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k,
   a.filter_seed = d_filter_seed;
   a.n_filter_seed = n_filter_seed;
   a.filter_bits = d_filter_bits;
+  {
+    const char* e = getenv("SDB_K1_FLAGS");
+    a.flags = e ? uint32_t(atoi(e)) : 0u;
+  }
   a.work_counter = ix->d_work.p;
   a.retry_count = ix->d_work.p + 1;
   a.retry_list = ix->d_work.p + 4;
@@ -111,15 +150,15 @@ int launch_search(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k,
   const bool filtered = d_filter_bits != nullptr;
 
   if (ix->p.quantizer == SDB_QUANT_BINARY && ix->bq_fitted) {
-    return filtered ? launch_with_retry<EVAL_BITS, 0, 1, 1, true, 1>(ix, a, stream)
-                    : launch_with_retry<EVAL_BITS, 0, 1, 1, false, 1>(ix, a, stream);
+    return filtered ? launch_with_retry<EVAL_BITS, 0, 1, 1, false, 0, true, 1>(ix, a, stream)
+                    : launch_with_retry<EVAL_BITS, 0, 1, 1, false, 0, false, 12>(ix, a, stream);
   }
   if (ix->p.quantizer == SDB_QUANT_PRODUCT && ix->pq_fitted) {
     if ((rc = ix->d_adc.ensure(size_t(B) * ix->pqM * ix->pqK))) return rc;
     if ((rc = launch_adc_tables(ix, B, d_queries, ix->d_adc.p, stream))) return rc;
     a.adc = ix->d_adc.p;
-    return filtered ? launch_with_retry<EVAL_ADC, 0, 1, 1, true, 1>(ix, a, stream)
-                    : launch_with_retry<EVAL_ADC, 0, 1, 1, false, 1>(ix, a, stream);
+    return filtered ? launch_with_retry<EVAL_ADC, 0, 1, 1, false, 0, true, 1>(ix, a, stream)
+                    : launch_with_retry<EVAL_ADC, 0, 1, 1, false, 0, false, 12>(ix, a, stream);
   }
   switch (ix->store_metric) {
     case SDB_METRIC_EUCLIDEAN: return launch_float<METRIC_EUCLIDEAN>(ix, a, filtered, stream);

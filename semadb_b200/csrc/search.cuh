@@ -17,9 +17,11 @@
 #pragma once
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace sdb {
 
-constexpr int LIST_SLOTS = 96;   // >= max searchSize (75), 3 per lane
+constexpr int LIST_SLOTS = 80;   // > max searchSize (75); lanes cover positions lane + 32j, j < 3
 constexpr int CAND_SLOTS = 64;   // >= max degreeBound (64), 2 per lane
 constexpr uint32_t EXPANDED_FLAG = 0x80000000u;
 constexpr uint32_t ID_MASK = 0x7FFFFFFFu;
@@ -64,6 +66,7 @@ struct SearchArgs {
   const uint32_t* filter_bits;  // bitmask over rows
   // work distribution: work_counter hands out batch slots; a query whose visited table
   // overflows is appended to retry_list and re-run by the RETRY launch (bigger table).
+  uint32_t flags;  // tuning (A/B): bit 0 = probe the two ids of a lane one after the other
   uint32_t* work_counter;
   uint32_t* retry_list;
   uint32_t* retry_count;
@@ -77,6 +80,7 @@ struct VisitedTable {
   static constexpr size_t BYTES = size_t(SLOTS) * 4;
   uint32_t* t;
   bool failed;
+  __device__ __forceinline__ uint32_t limit() const { return LIMIT; }
   __device__ __forceinline__ void init(unsigned char* base, uint32_t) { t = reinterpret_cast<uint32_t*>(base); }
   __device__ __forceinline__ void clear(int lane) {
     uint4 e = make_uint4(INVALID_ID, INVALID_ID, INVALID_ID, INVALID_ID);
@@ -100,6 +104,10 @@ struct VisitedTable {
     }
     return isnew;
   }
+  __device__ __forceinline__ void test_and_set2(uint32_t i0, bool a0, uint32_t i1, bool a1, bool& n0, bool& n1, int lane) {
+    n0 = test_and_set(i0, a0, lane);
+    n1 = test_and_set(i1, a1, lane);
+  }
 };
 
 // ---- exact visited set, compact form: 8192 x 16-bit entries + a 32-entry u32 stash ------
@@ -118,6 +126,7 @@ struct VisitedCompact {
   unsigned short* t;
   uint32_t mask, rb, rmask, dmax;
   bool failed;
+  __device__ __forceinline__ uint32_t limit() const { return LIMIT; }
   __device__ __forceinline__ void init(unsigned char* base, uint32_t rows) {
     t = reinterpret_cast<unsigned short*>(base);
     uint32_t b = rows <= SLOTS ? HB : 32 - __clz(rows - 1);
@@ -166,6 +175,144 @@ struct VisitedCompact {
     if (__any_sync(SDB_FULL, spill)) failed = true;
     return isnew;
   }
+  // Two ids per lane (adjacency slots lane and lane+32) probed in one vote-driven loop: the
+  // two probe chains overlap instead of running back to back. Slot-0 ids are tried first
+  // inside an iteration, so a lane's own pair keeps adjacency order.
+  __device__ __forceinline__ void test_and_set2(uint32_t i0, bool a0, uint32_t i1, bool a1, bool& n0, bool& n1, int) {
+    const uint32_t v0 = (i0 * 0x9E3779B1u) & mask, v1 = (i1 * 0x9E3779B1u) & mask;
+    uint32_t slot0 = v0 >> rb, slot1 = v1 >> rb;
+    const uint32_t c0 = 1 + (v0 & rmask), c1 = 1 + (v1 & rmask);
+    uint32_t disp0 = 0, disp1 = 0;
+    bool p0 = a0, p1 = a1, spill = false;
+    n0 = false;
+    n1 = false;
+    volatile uint32_t* tw = reinterpret_cast<volatile uint32_t*>(t);
+    while (__any_sync(SDB_FULL, p0 || p1)) {
+      if (p0) {
+        const uint32_t code = c0 + (disp0 << rb);
+        const uint32_t sh = (slot0 & 1) * 16;
+        const uint32_t w = tw[slot0 >> 1];
+        const uint32_t half = (w >> sh) & 0xFFFFu;
+        if (half == 0) {
+          const uint32_t old = atomicCAS(const_cast<uint32_t*>(tw) + (slot0 >> 1), w, w | (code << sh));
+          if (old == w) { n0 = true; p0 = false; }
+        } else if (half == code) {
+          p0 = false;
+        } else {
+          slot0 = (slot0 + 1) & (SLOTS - 1);
+          if (++disp0 > dmax) { p0 = false; spill = true; }
+        }
+      }
+      if (p1) {
+        const uint32_t code = c1 + (disp1 << rb);
+        const uint32_t sh = (slot1 & 1) * 16;
+        const uint32_t w = tw[slot1 >> 1];
+        const uint32_t half = (w >> sh) & 0xFFFFu;
+        if (half == 0) {
+          const uint32_t old = atomicCAS(const_cast<uint32_t*>(tw) + (slot1 >> 1), w, w | (code << sh));
+          if (old == w) { n1 = true; p1 = false; }
+        } else if (half == code) {
+          p1 = false;
+        } else {
+          slot1 = (slot1 + 1) & (SLOTS - 1);
+          if (++disp1 > dmax) { p1 = false; spill = true; }
+        }
+      }
+    }
+    if (__any_sync(SDB_FULL, spill)) failed = true;
+  }
+};
+
+// ---- exact visited set, compact form with a non-power-of-two slot count ------------------
+// Same quotienting idea as VisitedCompact with NSLOTS = 6144 (12 KB): together with the trimmed
+// list/staging areas a query-warp then needs 13.4 KB of shared memory, so 16 instead of 12
+// query-warps are resident per SM. pi(id) = id*A mod 2^b as before; span = ceil(2^b / NSLOTS),
+// home slot = pi / span, remainder = pi % span, entry = 1 + remainder + disp*span (16 bits).
+// disp <= dmax = (65535 - span) / span: 382 at 1M rows, 46 at 8M rows; beyond that (or above
+// 87.5 % load) the query goes to the RETRY launch.
+template <uint32_t NSLOTS>
+struct VisitedCompactN {
+  static constexpr uint32_t SLOTS = NSLOTS;
+  static constexpr size_t BYTES = size_t(NSLOTS) * 2;
+  unsigned short* t;
+  uint32_t mask, span, magic, used, dmax, lim;
+  bool failed;
+  __device__ __forceinline__ uint32_t limit() const { return lim; }
+  __device__ __forceinline__ void init(unsigned char* base, uint32_t rows) {
+    t = reinterpret_cast<unsigned short*>(base);
+    uint32_t b = rows <= 2 ? 1 : 32 - __clz(rows - 1);
+    if (b < 16) b = 16;
+    mask = b >= 32 ? 0xFFFFFFFFu : ((1u << b) - 1);
+    const uint64_t space = uint64_t(1) << b;
+    span = uint32_t((space + NSLOTS - 1) / NSLOTS);
+    magic = uint32_t((uint64_t(1) << 32) / span);
+    used = uint32_t((space + span - 1) / span);
+    dmax = span >= 32768 ? 0 : (65535u - span) / span;
+    if (dmax > 4096) dmax = 4096;
+    lim = used - used / 8;
+  }
+  __device__ __forceinline__ void clear(int lane) {
+    uint4 z = make_uint4(0, 0, 0, 0);
+    uint4* p = reinterpret_cast<uint4*>(t);
+    for (uint32_t i = lane; i < NSLOTS * 2 / 16; i += 32) p[i] = z;
+    failed = false;
+  }
+  __device__ __forceinline__ void home(uint32_t id, uint32_t& slot, uint32_t& code) const {
+    const uint32_t v = (id * 0x9E3779B1u) & mask;
+    uint32_t q = __umulhi(v, magic);
+    uint32_t r = v - q * span;
+    if (r >= span) { ++q; r -= span; }  // the estimate is short by at most one
+    slot = q;
+    code = 1 + r;
+  }
+  __device__ __forceinline__ void test_and_set2(uint32_t i0, bool a0, uint32_t i1, bool a1, bool& n0, bool& n1, int) {
+    uint32_t slot0, slot1, c0, c1;
+    home(i0, slot0, c0);
+    home(i1, slot1, c1);
+    uint32_t disp0 = 0, disp1 = 0;
+    bool p0 = a0, p1 = a1, spill = false;
+    n0 = false;
+    n1 = false;
+    volatile uint32_t* tw = reinterpret_cast<volatile uint32_t*>(t);
+    while (__any_sync(SDB_FULL, p0 || p1)) {
+      if (p0) {
+        const uint32_t sh = (slot0 & 1) * 16;
+        const uint32_t w = tw[slot0 >> 1];
+        const uint32_t half = (w >> sh) & 0xFFFFu;
+        if (half == 0) {
+          const uint32_t old = atomicCAS(const_cast<uint32_t*>(tw) + (slot0 >> 1), w, w | (c0 << sh));
+          if (old == w) { n0 = true; p0 = false; }
+        } else if (half == c0) {
+          p0 = false;
+        } else {
+          slot0 = slot0 + 1 == used ? 0 : slot0 + 1;
+          c0 += span;
+          if (++disp0 > dmax) { p0 = false; spill = true; }
+        }
+      }
+      if (p1) {
+        const uint32_t sh = (slot1 & 1) * 16;
+        const uint32_t w = tw[slot1 >> 1];
+        const uint32_t half = (w >> sh) & 0xFFFFu;
+        if (half == 0) {
+          const uint32_t old = atomicCAS(const_cast<uint32_t*>(tw) + (slot1 >> 1), w, w | (c1 << sh));
+          if (old == w) { n1 = true; p1 = false; }
+        } else if (half == c1) {
+          p1 = false;
+        } else {
+          slot1 = slot1 + 1 == used ? 0 : slot1 + 1;
+          c1 += span;
+          if (++disp1 > dmax) { p1 = false; spill = true; }
+        }
+      }
+    }
+    if (__any_sync(SDB_FULL, spill)) failed = true;
+  }
+  __device__ __forceinline__ bool test_and_set(uint32_t id, bool active, int lane) {
+    bool n0, n1;
+    test_and_set2(id, active, 0, false, n0, n1, lane);
+    return n0;
+  }
 };
 
 // ---- bounded candidate list (distset.go:133-200) in shared memory ------------------
@@ -174,6 +321,7 @@ struct CandList {
   float* dist;
   int len;
   int cap;
+  bool nan_seen;  // a NaN distance reached this list: only the sequential form is exact from then on
   // Insert one element with AddWithLimit semantics; caller has already applied the
   // "full && d > worst" rejection. Warp-synchronous; all lanes call with the same args.
   __device__ __forceinline__ void insert(uint32_t nid, float d, int lane) {
@@ -206,19 +354,121 @@ struct CandList {
     if (!full) ++len;
     __syncwarp();
   }
+
+  // Batch form of AddWithLimit (distset.go:166-200) for n staged candidates, arrival order =
+  // index. Let U = list ∪ candidates ordered by (distance, list-before-candidates, arrival).
+  // If the elements of U at ranks cap-1 and cap have different distances (or |U| <= cap),
+  // applying insert() one candidate at a time yields exactly the first cap elements of U in
+  // that order: an element with d <= theta (the rank cap-1 distance) is never rejected
+  // (worst >= theta whenever the list is full) and never evicted (that would need cap+1
+  // elements with d <= theta); equal distances keep arrival order (strict '<' bubble).
+  // Otherwise (a tie straddles the cut — the reference then lets the newest equal win,
+  // distset.go:184-194) or if a candidate distance is NaN, nothing is modified and false is
+  // returned: the caller applies the sequential form. min_m: below this many surviving
+  // candidates the sequential form is cheaper — also returns false, untouched.
+  __device__ __forceinline__ bool merge(const uint32_t* cid, const float* cdist, int n, int lane, uint32_t lt, int min_m) {
+    const int len0 = len;
+    const bool full = (len0 == cap);
+    const float worst = full ? dist[cap - 1] : 0.0f;
+    const float d0 = lane < n ? cdist[lane] : 0.0f;
+    const float d1 = lane + 32 < n ? cdist[lane + 32] : 0.0f;
+    const bool s0 = lane < n && !(full && d0 > worst);
+    const bool s1 = lane + 32 < n && !(full && d1 > worst);
+    const uint32_t b0 = __ballot_sync(SDB_FULL, s0), b1 = __ballot_sync(SDB_FULL, s1);
+    const int m = __popc(b0) + __popc(b1);
+    if (m == 0) return true;
+    if (__any_sync(SDB_FULL, (s0 && d0 != d0) || (s1 && d1 != d1))) nan_seen = true;
+    if (nan_seen || m < min_m) return false;
+    // position among the old items: number of items with dist <= d (newcomers go after equals)
+    int lo0 = 0, hi0 = len0, lo1 = 0, hi1 = len0;
+#pragma unroll
+    for (int it = 0; it < 7; ++it) {  // len0 <= 96 < 128
+      const int m0 = (lo0 + hi0) >> 1, m1 = (lo1 + hi1) >> 1;
+      const float x0 = dist[min(m0, LIST_SLOTS - 1)], x1 = dist[min(m1, LIST_SLOTS - 1)];
+      if (lo0 < hi0) { if (x0 <= d0) lo0 = m0 + 1; else hi0 = m0; }
+      if (lo1 < hi1) { if (x1 <= d1) lo1 = m1 + 1; else hi1 = m1; }
+    }
+    // rank among the surviving candidates by (distance, arrival)
+    int r0 = 0, r1 = 0;
+    if (m > 1) {
+      for (uint32_t bb = b0; bb; bb &= bb - 1) {
+        const int c = __ffs(bb) - 1;
+        const float dc = __shfl_sync(SDB_FULL, d0, c);
+        r0 += (dc < d0) || (dc == d0 && c < lane);
+        r1 += (dc <= d1);
+      }
+      for (uint32_t bb = b1; bb; bb &= bb - 1) {
+        const int c = __ffs(bb) - 1;
+        const float dc = __shfl_sync(SDB_FULL, d1, c);
+        r0 += (dc < d0);
+        r1 += (dc < d1) || (dc == d1 && c < lane);
+      }
+    }
+    const int f0 = s0 ? lo0 + r0 : 0x7FFF, f1 = s1 ? lo1 + r1 : 0x7FFF;
+    // which final positions are taken by candidates (positions < 96 are all that matter)
+    uint32_t x[3];
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+      x[w] = ((f0 >> 5) == w ? (1u << (f0 & 31)) : 0u) | ((f1 >> 5) == w ? (1u << (f1 & 31)) : 0u);
+      x[w] = __reduce_or_sync(SDB_FULL, x[w]);
+    }
+    // old item landing at final position P = lane + 32j is item P - (candidates below P)
+    uint32_t oid[3];
+    float od[3];
+    bool take[3];
+    int below = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int P = lane + 32 * j;
+      const bool occ = (x[j] >> lane) & 1u;
+      const int i = P - below - __popc(x[j] & lt);
+      take[j] = !occ && P <= cap && i < len0;
+      oid[j] = 0;
+      od[j] = 0.0f;
+      if (take[j]) { oid[j] = id[i]; od[j] = dist[i]; }
+      below += __popc(x[j]);
+    }
+    if (len0 + m > cap) {
+      // distances at ranks cap-1 (last kept) and cap (first dropped)
+      float dcut[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int P = cap - 1 + e, j = P >> 5, l = P & 31;
+        const float mine = j == 0 ? od[0] : (j == 1 ? od[1] : od[2]);
+        float v = __shfl_sync(SDB_FULL, mine, l);
+        const uint32_t h0 = __ballot_sync(SDB_FULL, f0 == P), h1 = __ballot_sync(SDB_FULL, f1 == P);
+        if (h0) v = __shfl_sync(SDB_FULL, d0, __ffs(h0) - 1);
+        if (h1) v = __shfl_sync(SDB_FULL, d1, __ffs(h1) - 1);
+        dcut[e] = v;
+      }
+      if (dcut[0] == dcut[1]) return false;
+    }
+    __syncwarp();
+    const int newlen = min(cap, len0 + m);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int P = lane + 32 * j;
+      if (take[j] && P < newlen) { id[P] = oid[j]; dist[P] = od[j]; }
+    }
+    if (f0 < newlen) { id[f0] = cid[lane]; dist[f0] = d0; }
+    if (f1 < newlen) { id[f1] = cid[lane + 32]; dist[f1] = d1; }
+    len = newlen;
+    __syncwarp();
+    return true;
+  }
 };
 
 // ---- distance evaluators -----------------------------------------------------------
 // Each evaluates cdist[c] = dist(query, row cid[c]) for c in [0, n), warp-cooperatively.
 
-// f32 rows, dim = 32*TRIPS exactly, query slice in registers (TRIPS <= 4) or shared.
+// (A/B baseline) f32 rows, dim = 32*TRIPS: batches of 4*UNROLL rows, no pipelining across batches.
 template <int METRIC, int TRIPS, int UNROLL>
-struct FloatEvalFixed {
+struct FloatEvalBatch {
   static constexpr bool L2 = (METRIC == METRIC_EUCLIDEAN);
   static constexpr bool QREG = (TRIPS <= 4);
   float4 q[QREG ? TRIPS : 1];
   const float* qs;
-  __device__ __forceinline__ void load_query(const float* qsmem, int lane) {
+  __device__ __forceinline__ void load_query(const float* qsmem, const float*, int lane) {
     qs = qsmem;
     if (QREG) {
 #pragma unroll
@@ -253,6 +503,70 @@ struct FloatEvalFixed {
         float r = group_reduce(acc, 0.0f);
         int ci = base + 4 * u + grp;
         if (g == 0 && ci < n) cdist[ci] = metric_epilogue<METRIC>(r);
+      }
+    }
+    __syncwarp();
+  }
+};
+
+// f32 rows, dim = 32*TRIPS exactly. An 8-lane group owns a row: lane g loads the float4 at
+// element 32t + 4g of every trip (one full 128-byte line per group per load instruction) and
+// so holds partial sums 4g..4g+3 of the asm's 32. Row sets (4 rows per warp-wide load) are
+// software-pipelined: SETS sets stay in flight and set s+SETS is issued as soon as set s has
+// been consumed. Queries of <= 4 trips live in registers (read straight from global).
+// Measured on B200 (profiles/r01_ab_k1.txt): narrower groups (4 or 2 lanes per row => fewer
+// shuffles, 32- or 64-byte pieces of 8 or 16 rows per load) run 1.4x / 2.7x slower — the L1
+// processes one 128-byte line per wavefront, so lines per instruction is what counts; parking
+// the partial sums in shared memory and folding them in one lane also lost to the shuffles.
+template <int METRIC, int TRIPS, int SETS>
+struct FloatEvalFixed {
+  static constexpr bool L2 = (METRIC == METRIC_EUCLIDEAN);
+  static constexpr bool QREG = (TRIPS <= 4);
+  float4 q[QREG ? TRIPS : 1];
+  const float* qs;
+  const float* qglobal;
+  __device__ __forceinline__ void load_query(const float* qsmem, const float* qg, int lane) {
+    qs = qsmem;
+    qglobal = qg;
+    if (QREG) {
+#pragma unroll
+      for (int t = 0; t < TRIPS; ++t) q[t] = ldg_f4(qg + 32 * t + 4 * (lane & 7));
+    }
+  }
+  __device__ __forceinline__ void issue(const SearchArgs& a, const uint32_t* cid, int n, int s, int g, int grp,
+                                        float4 (&v)[TRIPS]) {
+    // groups past the end read the query's own row in global memory instead (cache-hot, no
+    // branch, result discarded) so every load is unconditional
+    const int ci = s * 4 + grp;
+    const float* row = (ci < n ? a.vec + size_t(cid[ci]) * a.vec_pitch : qglobal) + 4 * g;
+#pragma unroll
+    for (int t = 0; t < TRIPS; ++t) v[t] = ldg_f4_stream(row + 32 * t);
+  }
+  __device__ __forceinline__ void consume(float* cdist, int n, int s, int g, int grp, const float4 (&v)[TRIPS]) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < TRIPS; ++t) {
+      const float4 x = QREG ? q[t] : *reinterpret_cast<const float4*>(qs + 32 * t + 4 * g);
+      trip_accum<L2>(x, v[t], acc);
+    }
+    const float r = group_reduce(acc, 0.0f);
+    const int ci = s * 4 + grp;
+    if (g == 0 && ci < n) cdist[ci] = metric_epilogue<METRIC>(r);
+  }
+  __device__ __forceinline__ void eval(const SearchArgs& a, const uint32_t* cid, float* cdist, int n, int lane) {
+    const int g = lane & 7, grp = lane >> 3;
+    const int nsets = (n + 3) >> 2;
+    float4 v[SETS][TRIPS];
+#pragma unroll
+    for (int u = 0; u < SETS; ++u)
+      if (u < nsets) issue(a, cid, n, u, g, grp, v[u]);
+    for (int base = 0; base < nsets; base += SETS) {
+#pragma unroll
+      for (int u = 0; u < SETS; ++u) {
+        const int s = base + u;
+        if (s >= nsets) break;  // warp-uniform
+        consume(cdist, n, s, g, grp, v[u]);
+        if (s + SETS < nsets) issue(a, cid, n, s + SETS, g, grp, v[u]);
       }
     }
     __syncwarp();
@@ -400,7 +714,10 @@ __host__ __device__ constexpr size_t warp_smem_bytes(uint32_t qfloats, uint32_t 
 // ---- the kernel ---------------------------------------------------------------------
 // One warp per CTA, one query per warp at a time; MINB = CTAs per SM the register budget
 // must allow (launch bounds).
-template <int KIND, int METRIC, int TRIPS, int UNROLL, class VT, bool FILTER, bool RETRY, int MINB>
+// SETS: FloatEvalFixed pipeline depth (LEGACY: the unpipelined FloatEvalBatch, kept as the
+// A/B baseline); MERGE_MIN > 0: use the batch form of AddWithLimit (CandList::merge) when at
+// least that many candidates survive.
+template <int KIND, int METRIC, int TRIPS, int SETS, bool LEGACY, int MERGE_MIN, class VT, bool FILTER, bool RETRY, int MINB>
 __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uint32_t qfloats, uint32_t qwords) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -444,11 +761,13 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
       for (uint32_t i = lane; i < qfloats; i += 32) qs[i] = i < a.dim ? __ldg(qg + i) : 0.0f;
     }
     __syncwarp();
-    FloatEvalFixed<METRIC, (KIND == EVAL_FLOAT_FIXED ? TRIPS : 1), (KIND == EVAL_FLOAT_FIXED ? UNROLL : 1)> ev_fixed;
+    constexpr bool FIXED = (KIND == EVAL_FLOAT_FIXED);
+    typename std::conditional<LEGACY, FloatEvalBatch<METRIC, (FIXED ? TRIPS : 1), (FIXED ? SETS : 1)>,
+                              FloatEvalFixed<METRIC, (FIXED ? TRIPS : 1), (FIXED ? SETS : 1)>>::type ev_fixed;
     FloatEvalGeneric<METRIC> ev_gen;
     BitEval ev_bits;
     AdcEval ev_adc;
-    if (KIND == EVAL_FLOAT_FIXED) ev_fixed.load_query(qs, lane);
+    if (KIND == EVAL_FLOAT_FIXED) ev_fixed.load_query(qs, a.queries + size_t(qi) * a.dim, lane);
     if (KIND == EVAL_FLOAT_GENERIC) ev_gen.load_query(qs, lane);
     if (KIND == EVAL_BITS) ev_bits.encode_query(a, qs, qbits, lane);
     if (KIND == EVAL_ADC) ev_adc.table = a.adc + size_t(qi) * a.pqM * a.pqK;
@@ -461,8 +780,10 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
 
     list.len = 0;
     list.cap = int(a.L);
+    list.nan_seen = false;
     res.len = 0;
     res.cap = int(a.k);
+    res.nan_seen = false;
     uint32_t hops = 0, ndist = 0, nvisited = 0;
     bool overflow = false;
 
@@ -491,8 +812,13 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
     // stage ids i0/i1 (adjacency order c = lane, lane+32) that pass the visited
     // test-and-set into cid[]; returns how many
     auto visit_and_stage = [&](uint32_t i0, bool a0, uint32_t i1, bool a1) -> int {
-      bool new0 = vt.test_and_set(i0, a0, lane);
-      bool new1 = vt.test_and_set(i1, a1, lane);
+      bool new0, new1;
+      if (a.flags & 1u) {
+        new0 = vt.test_and_set(i0, a0, lane);
+        new1 = vt.test_and_set(i1, a1, lane);
+      } else {
+        vt.test_and_set2(i0, a0, i1, a1, new0, new1, lane);
+      }
       uint32_t b0 = __ballot_sync(SDB_FULL, new0), b1 = __ballot_sync(SDB_FULL, new1);
       const int t0 = __popc(b0);
       if (new0) cid[__popc(b0 & lt)] = i0;
@@ -584,10 +910,10 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
       const int nnew = visit_and_stage(n0, n0 != INVALID_ID, n1, n1 != INVALID_ID);
       nvisited += nnew;
       ndist += nnew;
-      if (nvisited > VT::LIMIT || vt.failed) { overflow = true; break; }
+      if (nvisited > vt.limit() || vt.failed) { overflow = true; break; }
       if (nnew > 0) {
         evaluate(nnew);
-        add_with_limit(list, nnew);
+        if (MERGE_MIN == 0 || !list.merge(cid, cdist, nnew, lane, lt, MERGE_MIN)) add_with_limit(list, nnew);
       }
       if (FILTER) {
         // resultSet.AddWithLimit(distElem.Point) if the expanded node passes the filter

@@ -44,6 +44,23 @@ def test_search_c1_shape_small():
     _check_search(oix, g, Q)
 
 
+@pytest.mark.parametrize("dim", [128, 96])
+def test_search_boundary_ties(dim):
+    """0/1-valued coordinates: squared-L2 distances are small integers, so ties at the cut of
+    the candidate list are everywhere — the newest-equal-wins rule (distset.go:184-194) must
+    hold in the batch form of the list update too."""
+    from tests.helpers import mirror_to_gpu, oracle_graph
+    rng = np.random.Generator(np.random.PCG64(11))
+    X = (rng.random((6000, dim)) < 0.3).astype(np.float32)
+    X[1000:1200] = X[:200]  # exact duplicates
+    Q = (rng.random((400, dim)) < 0.3).astype(np.float32)
+    oix, ids, start = oracle_graph(X)
+    g = mirror_to_gpu(oix, X, ids, start)
+    _check_search(oix, g, Q)
+    _check_search(oix, g, X[:300], k=75, L=75)
+    _check_search(oix, g, Q[:100], k=5, L=25)
+
+
 def test_search_sift_shaped_100k():
     from tests.helpers import mirror_to_gpu, oracle_graph, recall_at_k
     X = synth.sift_shaped(100_000, 128, 3)
