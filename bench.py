@@ -41,6 +41,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 DIM, L, R, ALPHA, K = 128, 75, 64, 1.2, 10
+_OUT = sys.stdout
 
 
 def log(*a):
@@ -163,7 +164,7 @@ def run_reference(args):
                          "sample": f"{nq} of {args.queries} queries per step, {threads} threads, one query per thread"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_OUT, flush=True)
 
 
 def workload_config(args, world):
@@ -176,7 +177,18 @@ def workload_config(args, world):
             else "single shard"}
 
 
+def _quarantine_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) write to fd 1; the driver expects
+    exactly one JSON line there. Route fd 1 to stderr and keep a private handle for the line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    global _OUT
+    _OUT = _quarantine_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -380,7 +392,7 @@ def main():
             "gpu_launches": n_launch,
             "clocks": clocks,
         }
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

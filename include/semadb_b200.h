@@ -150,6 +150,25 @@ int sdb_flat_search_batch(sdb_index* ix, uint32_t B, const float* queries, uint3
 /* ---- insert: replaces IndexVamana.InsertUpdateDelete's insert branch (vamana.go:136-201,
  * insert.go:16-68): greedySearch + robustPrune + back-edges for n new points, batched. */
 int sdb_insert_batch(sdb_index* ix, uint64_t n, const uint64_t* ids, const float* vectors);
+/* The whole of IndexVamana.InsertUpdateDelete (vamana.go:136-263) except the trailing Fit and
+ * flush: has_vector[i] == 0 stands for a nil vector (IndexVectorChange.Vector == nil,
+ * vamana.go:122-125; NULL = all have vectors). Each change is classified against the store
+ * (vamana.go:158-185): absent+vector = insert, present+vector = update, present+nil = delete,
+ * absent+nil = skipped. Inserts run first (batched); then removeInboundEdges over the
+ * updated and deleted ids (EdgeScan node.go:142-199, pruneDeleteNeighbour prune.go:12-84,
+ * orphans re-attached to the start node prune.go:137-151); then the deleted rows are dropped
+ * and the updated points re-inserted one by one in input order (vamana.go:249-253; batched if
+ * the index is `relaxed`). Ids 0 and 1 are errors (vamana.go:150-157). */
+int sdb_insert_update_delete(sdb_index* ix, uint64_t n, const uint64_t* ids, const float* vectors,
+                             const uint8_t* has_vector);
+/* EdgeScan alone (node.go:142-199; vamana_test.go:142-175): ids flagged toPrune / toSave for a
+ * delete set, ascending. Buffers need room for sdb_index_max_node_id()+1 ids. */
+int sdb_edge_scan(sdb_index* ix, uint64_t n_delete, const uint64_t* delete_ids, uint64_t* to_prune,
+                  uint64_t* n_prune, uint64_t* to_save, uint64_t* n_save);
+/* Edges of the start node beyond degreeBound (AddNeighbourIfNotExists is unbounded,
+ * node.go:73-80): hydrate / flush the tail of n1e. get: *n = count, copies min(*n, cap). */
+int sdb_index_get_start_overflow(sdb_index* ix, uint64_t cap, uint64_t* out, uint64_t* n);
+int sdb_index_set_start_overflow(sdb_index* ix, uint64_t n, const uint64_t* ids);
 /* Mini-batch schedule of the batched insert: batch b has min(max_batch, max(min_batch,
  * inserted_so_far / growth_div)) points. 0 keeps a field's default. */
 int sdb_insert_config(sdb_index* ix, uint32_t min_batch, uint32_t max_batch, uint32_t growth_div);

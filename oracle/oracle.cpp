@@ -319,6 +319,9 @@ struct Index {
   std::vector<uint8_t> exists;
   std::vector<uint32_t> adj;
   std::vector<uint16_t> deg;
+  // edges of the start node beyond R: removeInboundEdges re-attaches orphans with
+  // AddNeighbourIfNotExists, which has no degree bound (prune.go:137-151, node.go:73-80)
+  std::vector<uint32_t> start_extra;
   uint32_t maxNodeId = 0;
   size_t count = 0;
   std::unique_ptr<Spin[]> locks;
@@ -555,7 +558,7 @@ int greedy_search(Index* ix, const float* query, int k, int L, const uint32_t* f
   uint32_t start = 1;
   if (ix->cap <= 1 || !ix->exists[1]) return 3;
   searchSet.add_with_limit(&start, 1);
-  sc.nb.resize(ix->R);
+  sc.nb.resize(size_t(ix->R) + ix->start_extra.size());
   for (size_t i = 0; i < std::min(searchSet.items.size(), size_t(L));) {
     Elem e = searchSet.items[i];
     if (e.visited) { ++i; continue; }
@@ -572,6 +575,10 @@ int greedy_search(Index* ix, const float* query, int k, int L, const uint32_t* f
     } else {
       dg = ix->deg[id];
       std::memcpy(sc.nb.data(), ix->A(id), sizeof(uint32_t) * dg);
+    }
+    if (id == 1 && !ix->start_extra.empty()) {
+      std::memcpy(sc.nb.data() + dg, ix->start_extra.data(), sizeof(uint32_t) * ix->start_extra.size());
+      dg += int(ix->start_extra.size());
     }
     searchSet.add_with_limit(sc.nb.data(), dg);
     if (filter && std::binary_search(filter, filter + nfilter, id)) resultSet->add_with_limit(&id, 1);
@@ -646,6 +653,107 @@ int insert_single(Index* ix, uint32_t id, const float* v, SearchScratch& sc, Sea
     }
     if (locked) ix->locks[b].unlock();
   }
+  return 0;
+}
+
+// Edge list of a node including the start node's overflow edges.
+void node_edges(const Index* ix, uint32_t id, std::vector<uint32_t>& out) {
+  out.assign(ix->A(id), ix->A(id) + ix->deg[id]);
+  if (id == 1) out.insert(out.end(), ix->start_extra.begin(), ix->start_extra.end());
+}
+
+void set_node_edges(Index* ix, uint32_t id, const uint32_t* e, int n) {
+  std::memcpy(ix->A(id), e, sizeof(uint32_t) * n);
+  ix->deg[id] = uint16_t(n);
+  if (id == 1) ix->start_extra.clear();
+}
+
+// EdgeScan (shard/index/vamana/node.go:142-199). del: per-row flags. Iteration order of the
+// reference is Go map order; here ascending node id. toPrune = valid nodes
+// with an edge into the delete set; toSave = valid nodes (except the start node) that no
+// valid node points at — counted before any pruning, edges into the delete set included.
+void edge_scan(const Index* ix, const std::vector<uint8_t>& del, std::vector<uint32_t>& toPrune,
+               std::vector<uint32_t>& toSave) {
+  toPrune.clear();
+  toSave.clear();
+  std::vector<uint8_t> hasInbound(ix->cap, 0);
+  std::vector<uint32_t> e;
+  for (uint32_t id = 0; id < ix->cap; ++id) {
+    if (!ix->exists[id] || del[id]) continue;
+    node_edges(ix, id, e);
+    bool added = false;
+    for (uint32_t t : e) {
+      hasInbound[t] = 1;
+      if (!added && del[t]) { toPrune.push_back(id); added = true; }
+    }
+  }
+  for (uint32_t id = 0; id < ix->cap; ++id)
+    if (ix->exists[id] && !del[id] && !hasInbound[id] && id != 1) toSave.push_back(id);
+}
+
+// pruneDeleteNeighbour (shard/index/vamana/prune.go:12-84)
+int prune_delete_neighbour(Index* ix, uint32_t a, const std::vector<uint8_t>& del) {
+  std::vector<uint32_t> ea, eb, validIds, toExpand;
+  node_edges(ix, a, ea);
+  for (uint32_t b : ea) (del[b] ? toExpand : validIds).push_back(b);
+  if (toExpand.empty()) return 20;  // prune.go:37-40
+  for (uint32_t b : toExpand) {
+    node_edges(ix, b, eb);
+    for (uint32_t c : eb)
+      if (!del[c]) validIds.push_back(c);
+  }
+  // candidateSet.Add(vecs...) dedupes with a VisitedMap, then Sort() (prune.go:59-66)
+  PointDist fn(ix, a);
+  std::vector<Elem> cand;
+  {
+    std::vector<uint32_t> seen(validIds);
+    std::sort(seen.begin(), seen.end());
+    std::vector<uint8_t> used(seen.size(), 0);
+    for (uint32_t p : validIds) {
+      size_t k = std::lower_bound(seen.begin(), seen.end(), p) - seen.begin();
+      if (used[k]) continue;
+      used[k] = 1;
+      cand.push_back(Elem{p, fn(p), false, false});
+    }
+  }
+  for (size_t i = 0; i < cand.size(); ++i)
+    for (size_t j = i; j > 0 && cand[j].dist < cand[j - 1].dist; --j) std::swap(cand[j], cand[j - 1]);
+  std::vector<uint32_t> out(std::max<size_t>(cand.size(), size_t(ix->R)));
+  int n = 0;
+  if (int(cand.size()) > ix->R) {
+    n = robust_prune(ix, a, cand, out.data(), nullptr);  // prune.go:68-70
+  } else {
+    for (const Elem& c : cand)
+      if (c.id != a) out[n++] = c.id;  // prune.go:72-81
+  }
+  set_node_edges(ix, a, out.data(), n);
+  return 0;
+}
+
+// removeInboundEdges (shard/index/vamana/prune.go:88-154)
+int remove_inbound_edges(Index* ix, const std::vector<uint8_t>& del, std::vector<uint32_t>* toPruneOut,
+                         std::vector<uint32_t>* toSaveOut) {
+  std::vector<uint32_t> toPrune, toSave;
+  edge_scan(ix, del, toPrune, toSave);
+  for (uint32_t a : toPrune) {
+    int rc = prune_delete_neighbour(ix, a, del);
+    if (rc) return rc;
+  }
+  if (!toSave.empty()) {
+    if (ix->cap <= 1 || !ix->exists[1]) return 3;
+    for (uint32_t p : toSave) {
+      if (p == 1) continue;
+      // startNode.AddNeighbourIfNotExists(point) (node.go:73-80): no degree bound
+      bool present = false;
+      for (int t = 0; t < ix->deg[1] && !present; ++t) present = ix->A(1)[t] == p;
+      for (uint32_t x : ix->start_extra) present = present || x == p;
+      if (present) continue;
+      if (ix->deg[1] < ix->R) { ix->A(1)[ix->deg[1]] = p; ix->deg[1]++; }
+      else ix->start_extra.push_back(p);
+    }
+  }
+  if (toPruneOut) *toPruneOut = toPrune;
+  if (toSaveOut) *toSaveOut = toSave;
   return 0;
 }
 
@@ -807,6 +915,79 @@ int orc_index_insert(void* h, const uint32_t* ids, const float* vecs, size_t n, 
     if (rc) err.store(rc);
   });
   return err.load();
+}
+
+// insertUpdateDelete (vamana.go:136-263) without the trailing Fit/flush: classify each
+// change against the store (has_vec[i] == 0 means a nil vector), run the inserts
+// (threads as in orc_index_insert), removeInboundEdges over updated ∪ deleted ids, drop the
+// deleted rows, re-insert the updated points one by one in input order (vamana.go:249-253).
+int orc_index_update_delete(void* h, const uint32_t* ids, const float* vecs, const uint8_t* has_vec, size_t n,
+                            int threads) {
+  auto* ix = static_cast<Index*>(h);
+  std::vector<uint32_t> ins_ids, upd, dele;
+  std::vector<float> ins_vecs;
+  std::vector<size_t> upd_src;
+  for (size_t i = 0; i < n; ++i) {
+    if (ids[i] == 1 || ids[i] == 0) return 10;  // vamana.go:150-157
+    bool exists = ids[i] < ix->cap && ix->exists[ids[i]];
+    if (!exists && !has_vec[i]) continue;
+    if (!exists) {
+      ins_ids.push_back(ids[i]);
+      ins_vecs.insert(ins_vecs.end(), vecs + i * ix->dim, vecs + (i + 1) * ix->dim);
+    } else if (has_vec[i]) {
+      upd.push_back(ids[i]);
+      upd_src.push_back(i);
+    } else {
+      dele.push_back(ids[i]);
+    }
+  }
+  if (!ins_ids.empty()) {
+    int rc = orc_index_insert(h, ins_ids.data(), ins_vecs.data(), ins_ids.size(), threads);
+    if (rc) return rc;
+  }
+  if (!upd.empty() || !dele.empty()) {
+    std::vector<uint8_t> del(ix->cap, 0);
+    for (uint32_t id : upd) del[id] = 1;
+    for (uint32_t id : dele) del[id] = 1;
+    int rc = remove_inbound_edges(ix, del, nullptr, nullptr);
+    if (rc) return rc;
+  }
+  for (uint32_t id : dele) {  // vecStore.Delete + nodeStore.Delete (vamana.go:231-236)
+    if (!ix->exists[id]) continue;
+    ix->exists[id] = 0;
+    ix->count--;
+    ix->deg[id] = 0;
+  }
+  SearchScratch sc;
+  SearchOut so;
+  for (size_t u = 0; u < upd.size(); ++u) {
+    const float* v = vecs + upd_src[u] * ix->dim;
+    ix->set(upd[u], v);
+    int rc = insert_single(ix, upd[u], v, sc, so, false);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// EdgeScan alone (vamana_test.go:142-175). Returns counts through n_prune / n_save.
+void orc_edge_scan(void* h, const uint32_t* del_ids, size_t ndel, uint32_t* prune_out, size_t* n_prune,
+                   uint32_t* save_out, size_t* n_save) {
+  auto* ix = static_cast<Index*>(h);
+  std::vector<uint8_t> del(ix->cap, 0);
+  for (size_t i = 0; i < ndel; ++i)
+    if (del_ids[i] < ix->cap) del[del_ids[i]] = 1;
+  std::vector<uint32_t> tp, ts;
+  edge_scan(ix, del, tp, ts);
+  std::copy(tp.begin(), tp.end(), prune_out);
+  std::copy(ts.begin(), ts.end(), save_out);
+  *n_prune = tp.size();
+  *n_save = ts.size();
+}
+
+size_t orc_index_start_extra(void* h, uint32_t* out, size_t cap) {
+  auto* ix = static_cast<Index*>(h);
+  for (size_t i = 0; i < ix->start_extra.size() && i < cap; ++i) out[i] = ix->start_extra[i];
+  return ix->start_extra.size();
 }
 
 // vecStore.Fit() (vamana.go:258): BQ mean threshold (binary.go:145-185) or PQ k-means

@@ -75,6 +75,13 @@ def lib():
     L.orc_index_insert.argtypes = [C.c_void_p, u32p, f32p, C.c_size_t, C.c_int]
     L.orc_index_fit.restype = C.c_int
     L.orc_index_fit.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+    L.orc_index_update_delete.argtypes = [C.c_void_p, u32p, f32p, u8p, C.c_size_t, C.c_int]
+    L.orc_index_update_delete.restype = C.c_int
+    L.orc_edge_scan.argtypes = [C.c_void_p, u32p, C.c_size_t, u32p, C.POINTER(C.c_size_t), u32p,
+                                C.POINTER(C.c_size_t)]
+    L.orc_edge_scan.restype = None
+    L.orc_index_start_extra.argtypes = [C.c_void_p, u32p, C.c_size_t]
+    L.orc_index_start_extra.restype = C.c_size_t
     L.orc_index_set_pq.restype = C.c_int
     L.orc_index_set_pq.argtypes = [C.c_void_p, f32p, f32p, C.c_int]
     L.orc_index_get_pq.restype = C.c_int
@@ -235,6 +242,30 @@ class OracleIndex:
         rc = lib().orc_index_insert(self._h, _p(ids, u32p), _p(vecs, f32p), len(ids), threads)
         if rc:
             raise RuntimeError(f"oracle insert failed rc={rc}")
+
+    def update_delete(self, ids, vecs, has_vec, threads=1):
+        """insertUpdateDelete (vamana.go:136-263) minus Fit: has_vec[i] == 0 is a nil vector."""
+        ids, vecs = _u32(ids), _f32(vecs)
+        hv = np.ascontiguousarray(has_vec, dtype=np.uint8)
+        assert vecs.shape == (len(ids), self.dim) and hv.shape == (len(ids),)
+        rc = lib().orc_index_update_delete(self._h, _p(ids, u32p), _p(vecs, f32p), _p(hv, u8p), len(ids), threads)
+        if rc:
+            raise RuntimeError(f"oracle update_delete failed rc={rc}")
+
+    def edge_scan(self, delete_ids):
+        """EdgeScan (node.go:142-199): (toPrune, toSave) in ascending id order."""
+        d = _u32(delete_ids)
+        cap = self.capacity
+        tp, ts = np.zeros(cap, dtype=np.uint32), np.zeros(cap, dtype=np.uint32)
+        n1, n2 = C.c_size_t(0), C.c_size_t(0)
+        lib().orc_edge_scan(self._h, _p(d, u32p), len(d), _p(tp, u32p), C.byref(n1), _p(ts, u32p), C.byref(n2))
+        return tp[:n1.value].copy(), ts[:n2.value].copy()
+
+    def start_extra(self):
+        n = int(lib().orc_index_start_extra(self._h, None, 0))
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        lib().orc_index_start_extra(self._h, _p(out, u32p), n)
+        return out[:n]
 
     def fit(self, pq_first=0, pq_alias=False, threads=1):
         return lib().orc_index_fit(self._h, pq_first, int(pq_alias), threads)

@@ -68,6 +68,10 @@ _SIGS = {
     "sdb_flat_search_batch": (C.c_int, [H, C.c_uint32, f32p, C.c_uint32, u64p, C.c_uint64, u64p, f32p, u32p]),
     "sdb_insert_batch": (C.c_int, [H, C.c_uint64, u64p, f32p]),
     "sdb_insert_config": (C.c_int, [H, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "sdb_insert_update_delete": (C.c_int, [H, C.c_uint64, u64p, f32p, u8p]),
+    "sdb_edge_scan": (C.c_int, [H, C.c_uint64, u64p, u64p, u64p, u64p, u64p]),
+    "sdb_index_get_start_overflow": (C.c_int, [H, C.c_uint64, u64p, u64p]),
+    "sdb_index_set_start_overflow": (C.c_int, [H, C.c_uint64, u64p]),
     "sdb_index_fit": (C.c_int, [H, C.c_uint64, i32p]),
     "sdb_index_get_pq": (C.c_int, [H, f32p, f32p]),
     "sdb_index_set_pq": (C.c_int, [H, f32p, f32p]),

@@ -255,6 +255,7 @@ void sdb_index_destroy(sdb_index* ix) {
   cudaFree(ix->d_adj);
   cudaFree(ix->d_deg);
   cudaFree(ix->d_exists);
+  ix->d_start_extra.release();
   cudaFree(ix->d_bq_thr);
   cudaFree(ix->d_pq_centroids);
   cudaFree(ix->d_pq_cdist);
@@ -622,6 +623,43 @@ int sdb_insert_batch(sdb_index* ix, uint64_t n, const uint64_t* ids, const float
   std::lock_guard<std::mutex> g(ix->mu);
   SDB_CUDA(cudaSetDevice(ix->device));
   return insert_batch_locked(ix, n, ids, vectors);
+}
+
+int sdb_insert_update_delete(sdb_index* ix, uint64_t n, const uint64_t* ids, const float* vectors,
+                             const uint8_t* has_vector) {
+  if (!ix) return fail(SDB_ERR_INVALID, "null index");
+  if (n == 0) return SDB_OK;
+  if (!ids || !vectors) return fail(SDB_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(ix->mu);
+  SDB_CUDA(cudaSetDevice(ix->device));
+  return insert_update_delete_locked(ix, n, ids, vectors, has_vector);
+}
+
+int sdb_edge_scan(sdb_index* ix, uint64_t n_delete, const uint64_t* delete_ids, uint64_t* to_prune, uint64_t* n_prune,
+                  uint64_t* to_save, uint64_t* n_save) {
+  if (!ix || (n_delete && !delete_ids) || !to_prune || !n_prune || !to_save || !n_save)
+    return fail(SDB_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(ix->mu);
+  SDB_CUDA(cudaSetDevice(ix->device));
+  return edge_scan_locked(ix, n_delete, delete_ids, to_prune, n_prune, to_save, n_save);
+}
+
+int sdb_index_get_start_overflow(sdb_index* ix, uint64_t cap, uint64_t* out, uint64_t* n) {
+  if (!ix || !n || (cap && !out)) return fail(SDB_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(ix->mu);
+  *n = ix->h_start_extra.size();
+  for (uint64_t i = 0; i < *n && i < cap; ++i) out[i] = ix->h_start_extra[i];
+  return SDB_OK;
+}
+
+int sdb_index_set_start_overflow(sdb_index* ix, uint64_t n, const uint64_t* ids) {
+  if (!ix || (n && !ids)) return fail(SDB_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(ix->mu);
+  SDB_CUDA(cudaSetDevice(ix->device));
+  for (uint64_t i = 0; i < n; ++i)
+    if (ids[i] >= ix->rows || !ix->h_exists[ids[i]]) return fail(SDB_ERR_NOTFOUND, "node id does not exist: " + std::to_string(ids[i]));
+  ix->h_start_extra.assign(ids, ids + n);
+  return upload_start_extra(ix);
 }
 
 int sdb_insert_config(sdb_index* ix, uint32_t min_batch, uint32_t max_batch, uint32_t growth_div) {

@@ -94,6 +94,10 @@ struct sdb_index {
   uint32_t* d_deg = nullptr;
   uint8_t* d_exists = nullptr;
   std::vector<uint8_t> h_exists;
+  // edges of the start node beyond degree_bound: removeInboundEdges re-attaches orphaned nodes
+  // with AddNeighbourIfNotExists, which is unbounded (prune.go:137-151, node.go:73-80)
+  std::vector<uint32_t> h_start_extra;
+  sdb::DevBuf<uint32_t> d_start_extra;
   uint64_t count = 0;
   uint32_t max_node_id = 0;
 
@@ -145,8 +149,15 @@ int launch_encode_rows(sdb_index* ix, uint32_t n, const uint32_t* d_ids, cudaStr
 int launch_adc_tables(sdb_index* ix, uint32_t B, const float* d_queries, float* d_out, cudaStream_t stream);
 int launch_merge(uint32_t S, uint32_t B, uint32_t k, const uint64_t* in_ids, const float* in_d, const uint32_t* in_c,
                  uint64_t* out_ids, float* out_d, uint32_t* out_c, cudaStream_t stream);
-int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const float* vectors);
+// reinsert: ids already exist (update path, vamana.go:249-253): rows are overwritten, one point per mini-batch
+int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const float* vectors, bool reinsert = false);
 // VectorStore.Set on device-resident ids/vectors: scatter rows, mark exists, encode if fitted
 int set_rows_device(sdb_index* ix, uint32_t n, const uint32_t* d_ids, const float* d_vecs, cudaStream_t stream);
 int fit_locked(sdb_index* ix, uint64_t pq_first_row, int32_t* fitted);
+// insertUpdateDelete (vamana.go:136-263) minus Fit/flush; has_vector[i] == 0 = nil vector
+int insert_update_delete_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const float* vectors,
+                                const uint8_t* has_vector);
+int upload_start_extra(sdb_index* ix);
+int edge_scan_locked(sdb_index* ix, uint64_t n_delete, const uint64_t* delete_ids, uint64_t* to_prune,
+                     uint64_t* n_prune, uint64_t* to_save, uint64_t* n_save);
 }  // namespace sdb

@@ -15,162 +15,18 @@
 // and reproduces the oracle's graph edge for edge; larger batches search a slightly stale
 // snapshot, like the reference's concurrent insert workers (vamana.go:190-195).
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
 #include <cstdlib>
 #include <string>
 
-#include "common.cuh"
-#include "index.cuh"
+#include "prune.cuh"
 
 namespace sdb {
 
 namespace {
-
-constexpr int PRUNE_THREADS = 128;
-constexpr int PRUNE_GROUPS = PRUNE_THREADS / 8;
-constexpr int MAX_CAND = 256;  // visited-list capacity handed to robustPrune
-
-struct StoreView {
-  int mode;  // 0 float rows, 1 bit rows, 2 PQ codes (SDC)
-  int metric;
-  const float* vec; uint32_t vec_pitch; uint32_t dim;
-  const uint64_t* bits; uint32_t bits_pitch; uint32_t words;
-  const uint8_t* codes; uint32_t codes_pitch; uint32_t pqM, pqK;
-  const float* cdist;
-  uint32_t row_bytes;  // bytes staged per candidate row
-};
-
-struct PruneShared {
-  uint32_t id[MAX_CAND + 1];
-  float dist[MAX_CAND + 1];
-  uint32_t sid[MAX_CAND + 1];   // sorted
-  float sdist[MAX_CAND + 1];
-  uint8_t removed[MAX_CAND + 1];
-  uint32_t edges[64];
-  int n;
-  int cnt;
-};
-
-// distance between two staged rows by an 8-lane group; result valid in the group's lane 0.
-// All 32 lanes of the warp must call it together.
-template <int METRIC>
-__device__ __forceinline__ float group_float_dist(const float* x, const float* y, uint32_t dim, int g) {
-  constexpr bool L2 = (METRIC == METRIC_EUCLIDEAN);
-  const int trips = dim >> 5;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int t = 0; t < trips; ++t) {
-    float4 a = *reinterpret_cast<const float4*>(x + 32 * t + 4 * g);
-    float4 b = *reinterpret_cast<const float4*>(y + 32 * t + 4 * g);
-    trip_accum<L2>(a, b, acc);
-  }
-  float tail = 0.0f;
-  if (g == 0)
-    for (uint32_t i = trips << 5; i < dim; ++i) tail = tail_accum<L2>(x[i], y[i], tail);
-  return metric_epilogue<METRIC>(group_reduce(acc, tail));
-}
-
-__device__ __forceinline__ float row_dist(const StoreView& s, const unsigned char* x, const unsigned char* y, int g) {
-  if (s.mode == 0) {
-    const float* a = reinterpret_cast<const float*>(x);
-    const float* b = reinterpret_cast<const float*>(y);
-    switch (s.metric) {
-      case METRIC_EUCLIDEAN: return group_float_dist<METRIC_EUCLIDEAN>(a, b, s.dim, g);
-      case METRIC_DOT: return group_float_dist<METRIC_DOT>(a, b, s.dim, g);
-      case METRIC_COSINE: return group_float_dist<METRIC_COSINE>(a, b, s.dim, g);
-      default: {
-        // haversine: float64 math in lane 0; keep the warp's shuffle count consistent
-        float r = (g == 0) ? haversine_thread(a, b) : 0.0f;
-        return r;
-      }
-    }
-  }
-  float r = 0.0f;
-  if (g == 0) {
-    if (s.mode == 1) {
-      const uint64_t* a = reinterpret_cast<const uint64_t*>(x);
-      const uint64_t* b = reinterpret_cast<const uint64_t*>(y);
-      int c = 0, u = 0;
-      for (uint32_t w = 0; w < s.words; ++w) {
-        if (s.metric == METRIC_JACCARD) { c += __popcll(a[w] & b[w]); u += __popcll(a[w] | b[w]); }
-        else c += __popcll(a[w] ^ b[w]);
-      }
-      r = bits_finish(s.metric, c, u);
-    } else {
-      // SDC: sum_i centroidDists[i][cx[i]][cy[i]] sequential f32 (product.go:299-303)
-      for (uint32_t m = 0; m < s.pqM; ++m) r = __fadd_rn(r, __ldg(s.cdist + (size_t(m) * s.pqK + x[m]) * s.pqK + y[m]));
-    }
-  }
-  return r;
-}
-
-__device__ __forceinline__ const unsigned char* global_row(const StoreView& s, uint32_t id) {
-  if (s.mode == 0) return reinterpret_cast<const unsigned char*>(s.vec + size_t(id) * s.vec_pitch);
-  if (s.mode == 1) return reinterpret_cast<const unsigned char*>(s.bits + size_t(id) * s.bits_pitch);
-  return s.codes + size_t(id) * s.codes_pitch;
-}
-
-// Stable sort of (id, dist)[0..n) by distance into (sid, sdist): equals the reference's
-// insertion sort (distset.go:223-238, strict '<' swaps => stable).
-__device__ void stable_sort_by_dist(PruneShared& sh) {
-  const int n = sh.n;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float di = sh.dist[i];
-    int rank = 0;
-    for (int j = 0; j < n; ++j) {
-      float dj = sh.dist[j];
-      rank += (dj < di) || (dj == di && j < i);
-    }
-    sh.sid[rank] = sh.id[i];
-    sh.sdist[rank] = di;
-  }
-  __syncthreads();
-}
-
-// Stage rows of the sorted candidates into shared memory (as many as fit).
-__device__ void stage_rows(const StoreView& s, PruneShared& sh, unsigned char* rows, int staged) {
-  const uint32_t vec16 = s.row_bytes / 16;
-  const uint32_t total = uint32_t(staged) * vec16;
-  for (uint32_t t = threadIdx.x; t < total; t += blockDim.x) {
-    const uint32_t c = t / vec16, i = t % vec16;
-    const uint4* src = reinterpret_cast<const uint4*>(global_row(s, sh.sid[c]));
-    reinterpret_cast<uint4*>(rows + size_t(c) * s.row_bytes)[i] = __ldg(src + i);
-  }
-  __syncthreads();
-}
-
-// robustPrune (search.go:106-138) over the sorted candidates in sh.sid/sdist; node = id of
-// the node being pruned (skipped if it appears, search.go:116). Fills sh.edges/sh.cnt.
-__device__ void robust_prune_cta(const StoreView& s, PruneShared& sh, const unsigned char* rows, int staged,
-                                 uint32_t node, int R, float alpha) {
-  const int n = sh.n;
-  const int lane = threadIdx.x & 31;
-  const int g = lane & 7;
-  const int grp = threadIdx.x >> 3;  // 0..PRUNE_GROUPS-1
-  for (int i = threadIdx.x; i < n; i += blockDim.x) sh.removed[i] = 0;
-  if (threadIdx.x == 0) sh.cnt = 0;
-  __syncthreads();
-  for (int i = 0; i < n; ++i) {
-    if (sh.removed[i] || sh.sid[i] == node) continue;  // block-uniform
-    __syncthreads();
-    if (threadIdx.x == 0) sh.edges[sh.cnt++] = sh.sid[i];
-    __syncthreads();
-    if (sh.cnt >= R) break;
-    const unsigned char* xi = i < staged ? rows + size_t(i) * s.row_bytes : global_row(s, sh.sid[i]);
-    for (int j0 = i + 1; j0 < n; j0 += PRUNE_GROUPS) {
-      int j = j0 + grp;
-      bool act = (j < n) && !sh.removed[j];
-      // warp-uniform skip when none of this warp's 4 groups has work
-      if (!__any_sync(SDB_FULL, act)) continue;
-      int jj = act ? j : i;
-      const unsigned char* yj = jj < staged ? rows + size_t(jj) * s.row_bytes : global_row(s, sh.sid[jj]);
-      float d = row_dist(s, xi, yj, g);
-      if (act && g == 0 && __fmul_rn(alpha, d) < sh.sdist[j]) sh.removed[j] = 1;  // search.go:132
-    }
-    __syncthreads();
-  }
-  __syncthreads();
-}
 
 struct InsertArgs {
   StoreView s;
@@ -188,8 +44,9 @@ struct InsertArgs {
 };
 
 __global__ void __launch_bounds__(PRUNE_THREADS) prune_new_kernel(InsertArgs a) {
-  extern __shared__ __align__(16) unsigned char dyn[];
-  __shared__ PruneShared sh;
+  extern __shared__ __align__(16) unsigned char dyn_raw[];
+  PruneShared sh;
+  unsigned char* dyn = sh.carve(dyn_raw, MAX_CAND + 1);
   const uint32_t b = blockIdx.x;
   const uint32_t A = a.new_ids[b];
   uint32_t n = a.vis_len[b];
@@ -197,7 +54,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS) prune_new_kernel(InsertArgs a) 
     if (threadIdx.x == 0) atomicExch(a.error_flag, 1u);
     n = min(min(n, a.vis_cap), uint32_t(MAX_CAND));
   }
-  if (threadIdx.x == 0) sh.n = int(n);
+  sh.n = int(n);
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
     sh.id[i] = a.vis_ids[size_t(b) * a.vis_cap + i];
     sh.dist[i] = a.vis_dists[size_t(b) * a.vis_cap + i];
@@ -207,7 +64,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS) prune_new_kernel(InsertArgs a) 
   int staged = min(int(n), a.staged_max);
   stage_rows(a.s, sh, dyn, staged);
   robust_prune_cta(a.s, sh, dyn, staged, A, int(a.R), a.alpha);
-  const int cnt = sh.cnt;
+  const int cnt = *sh.cnt;
   for (uint32_t t = threadIdx.x; t < a.R; t += blockDim.x) {
     uint32_t e = t < uint32_t(cnt) ? sh.edges[t] : INVALID_ID;
     a.adj[size_t(A) * a.R + t] = e;
@@ -247,8 +104,9 @@ struct BackArgs {
 };
 
 __global__ void __launch_bounds__(PRUNE_THREADS) backedge_kernel(BackArgs a) {
-  extern __shared__ __align__(16) unsigned char dyn[];
-  __shared__ PruneShared sh;
+  extern __shared__ __align__(16) unsigned char dyn_raw[];
+  PruneShared sh;
+  unsigned char* dyn = sh.carve(dyn_raw, MAX_CAND + 1);
   __shared__ uint32_t cur[64 + 1];
   const int lane = threadIdx.x & 31;
   const int g = lane & 7;
@@ -269,7 +127,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS) backedge_kernel(BackArgs a) {
       if (cur_n + 1 > int(a.R)) {
         // candidateSet.Add(nodeB.neighbours...), Add(vecA): distances from B (insert.go:48-57)
         const int n = cur_n + 1;
-        if (threadIdx.x == 0) sh.n = n;
+        sh.n = n;
         for (int i = threadIdx.x; i < n; i += blockDim.x) sh.id[i] = i < cur_n ? cur[i] : A;
         __syncthreads();
         for (int j0 = 0; j0 < n; j0 += PRUNE_GROUPS) {
@@ -285,7 +143,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS) backedge_kernel(BackArgs a) {
         int staged = min(n, a.staged_max);
         stage_rows(a.s, sh, dyn, staged);
         robust_prune_cta(a.s, sh, dyn, staged, B, int(a.R), a.alpha);
-        cur_n = sh.cnt;
+        cur_n = *sh.cnt;
         for (int t = threadIdx.x; t < cur_n; t += blockDim.x) cur[t] = sh.edges[t];
       } else {
         if (threadIdx.x == 0) cur[cur_n] = A;  // nodeB.AddNeighbour(vecA) (insert.go:62)
@@ -297,6 +155,34 @@ __global__ void __launch_bounds__(PRUNE_THREADS) backedge_kernel(BackArgs a) {
       a.adj[size_t(B) * a.R + t] = t < uint32_t(cur_n) ? cur[t] : INVALID_ID;
     if (threadIdx.x == 0) a.deg[B] = uint32_t(cur_n);
   }
+}
+
+// A new point none of whose out-neighbours kept the back-edge has no inbound edge at all: a
+// mini-batch searches a snapshot, so mutually close new points cannot link to each other and
+// robustPrune(B) may drop all of them from the few old nodes they share. One CTA per new point
+// A: unlinked[b] = 1 iff no row adj[B], B in N(A), contains A.
+__global__ void unlinked_flag_kernel(const uint32_t* new_ids, uint32_t m, uint32_t R, const uint32_t* adj,
+                                     const uint32_t* deg, uint8_t* unlinked) {
+  const uint32_t b = blockIdx.x;
+  if (b >= m) return;
+  const uint32_t A = new_ids[b];
+  const uint32_t dA = deg[A];
+  int found = 0;
+  for (uint32_t j = 0; j < dA; ++j) {
+    const uint32_t B = adj[size_t(A) * R + j];
+    for (uint32_t t = threadIdx.x; t < R; t += blockDim.x) found |= adj[size_t(B) * R + t] == A;
+  }
+  found = __syncthreads_or(found);
+  if (threadIdx.x == 0) unlinked[b] = (found || dA == 0) ? 0 : 1;
+}
+
+__global__ void gather_retry_kernel(const uint32_t* sel, uint32_t n, const uint32_t* src_ids, const float* src_vecs,
+                                    uint32_t dim, uint32_t* dst_ids, float* dst_vecs) {
+  const uint32_t i = blockIdx.x;
+  if (i >= n) return;
+  const uint32_t s = sel[i];
+  if (threadIdx.x == 0) dst_ids[i] = src_ids[s];
+  for (uint32_t t = threadIdx.x; t < dim; t += blockDim.x) dst_vecs[size_t(i) * dim + t] = src_vecs[size_t(s) * dim + t];
 }
 
 // debug aid (SDB_DEBUG_INSERT=1): adjacency rows must hold deg valid ids then padding
@@ -314,25 +200,9 @@ __global__ void check_rows_kernel(const uint32_t* adj, const uint32_t* deg, cons
   if (bad && atomicAdd(report, 1u) == 0) { report[1] = id; report[2] = d; }
 }
 
-StoreView make_view(const sdb_index* ix) {
-  StoreView s{};
-  s.vec = ix->d_vec; s.vec_pitch = ix->vec_pitch; s.dim = ix->p.dim;
-  s.bits = ix->d_bits; s.bits_pitch = ix->bits_pitch; s.words = ix->words;
-  s.codes = ix->d_codes; s.codes_pitch = ix->codes_pitch; s.pqM = ix->pqM; s.pqK = ix->pqK;
-  s.cdist = ix->d_pq_cdist;
-  if (ix->p.quantizer == SDB_QUANT_BINARY && ix->bq_fitted) {
-    s.mode = 1; s.metric = ix->bq_metric; s.row_bytes = ix->bits_pitch * 8;
-  } else if (ix->p.quantizer == SDB_QUANT_PRODUCT && ix->pq_fitted) {
-    s.mode = 2; s.metric = ix->store_metric; s.row_bytes = ix->codes_pitch;
-  } else {
-    s.mode = 0; s.metric = ix->store_metric; s.row_bytes = ix->vec_pitch * 4;
-  }
-  return s;
-}
-
 }  // namespace
 
-int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const float* vectors) {
+int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const float* vectors, bool reinsert) {
   // classify like insertUpdateDelete (vamana.go:149-185): only fresh inserts are handled here
   std::vector<uint32_t> h32(n);
   uint64_t mx = 0;
@@ -340,7 +210,7 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
     if (ids[i] == START_ID) return fail(SDB_ERR_RESERVED_ID, "cannot modify point with start id: 1");
     if (ids[i] == 0) return fail(SDB_ERR_RESERVED_ID, "invalid point id: 0");
     if (ids[i] >= (uint64_t(1) << 31) - 1) return fail(SDB_ERR_INVALID, "node id too large for a device index");
-    if (ids[i] < ix->rows && ix->h_exists[ids[i]]) return fail(SDB_ERR_STATE, "point already exists (update is not supported by the GPU index yet): " + std::to_string(ids[i]));
+    if (!reinsert && ids[i] < ix->rows && ix->h_exists[ids[i]]) return fail(SDB_ERR_STATE, "point already exists (updates go through sdb_insert_update_delete): " + std::to_string(ids[i]));
     mx = std::max(mx, ids[i]);
     h32[i] = uint32_t(ids[i]);
   }
@@ -350,7 +220,9 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
   cudaStream_t st = ix->stream;
   const uint32_t R = ix->p.degree_bound, L = ix->p.search_size, dim = ix->p.dim;
   const uint32_t vis_cap = MAX_CAND;
-  const uint32_t max_batch = std::max<uint32_t>(1, ix->ins_max_batch);
+  // updated points are re-inserted one by one (vamana.go:249-253) unless the index is relaxed
+  const bool one_by_one = reinsert && !ix->p.relaxed;
+  const uint32_t max_batch = one_by_one ? 1u : std::max<uint32_t>(1, ix->ins_max_batch);
 
   // device copies of ids and vectors for the whole call (chunked to bound staging)
   const uint64_t chunk_pts = std::max<uint64_t>(max_batch, (uint64_t(512) << 20) / (dim * sizeof(float)));
@@ -358,9 +230,13 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
   sdb::DevBuf<float> d_vecs;
   sdb::DevBuf<uint32_t> d_pair_key, d_pair_val, d_pair_key2, d_pair_val2, d_seg, d_misc;
   sdb::DevBuf<unsigned char> d_cubtmp;
+  sdb::DevBuf<uint8_t> d_unflag;
+  sdb::DevBuf<uint32_t> d_sel, d_retry_ids[2];
+  sdb::DevBuf<float> d_retry_vecs[2];
   auto release_all = [&]() {
     d_ids.release(); d_vecs.release(); d_pair_key.release(); d_pair_val.release(); d_pair_key2.release();
-    d_pair_val2.release(); d_seg.release(); d_misc.release(); d_cubtmp.release();
+    d_pair_val2.release(); d_seg.release(); d_misc.release(); d_cubtmp.release(); d_unflag.release(); d_sel.release();
+    for (int i = 0; i < 2; ++i) { d_retry_ids[i].release(); d_retry_vecs[i].release(); }
   };
 #define INS_CHECK(expr)            \
   do {                             \
@@ -386,15 +262,27 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
   INS_CHECK(ix->d_oid.ensure(max_batch));
   INS_CHECK(ix->d_od.ensure(max_batch));
   INS_CHECK(ix->d_oc.ensure(max_batch));
-  size_t cub_bytes = 0;
+  size_t cub_bytes = 0, sel_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, d_pair_key.p, d_pair_key2.p, d_pair_val.p, d_pair_val2.p, int(max_pairs), 0, 32, st);
-  INS_CHECK(d_cubtmp.ensure(cub_bytes + 16));
+  // repair pass for new points left without an inbound edge (batched schedule only)
+  const bool repair = max_batch > 1;
+  if (repair) {
+    INS_CHECK(d_unflag.ensure(max_batch));
+    INS_CHECK(d_sel.ensure(max_batch));
+    for (int i = 0; i < 2; ++i) {
+      INS_CHECK(d_retry_ids[i].ensure(max_batch));
+      INS_CHECK(d_retry_vecs[i].ensure(size_t(max_batch) * dim));
+    }
+    cub::DeviceSelect::Flagged(nullptr, sel_bytes, thrust::counting_iterator<uint32_t>(0), d_unflag.p, d_sel.p, d_misc.p,
+                               int(max_batch), st);
+  }
+  INS_CHECK(d_cubtmp.ensure(std::max(cub_bytes, sel_bytes) + 16));
   INS_CUDA(cudaMemsetAsync(d_misc.p, 0, 8 * sizeof(uint32_t), st));
   uint32_t* d_err = d_misc.p + 1;
   uint32_t* d_segcount = d_misc.p;
 
   // shared memory budget for staged candidate rows
-  size_t static_smem = sizeof(PruneShared) + 512;
+  size_t static_smem = PruneShared::bytes(MAX_CAND + 1) + 512;
   cudaFuncAttributes fa;
   INS_CUDA(cudaFuncGetAttributes(&fa, prune_new_kernel));
   static_smem = std::max(static_smem, fa.sharedSizeBytes);
@@ -416,18 +304,12 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
     size_t budget = std::min<size_t>(ix->smem_optin, size_t(100) << 10);
     size_t dyn_budget = budget > static_smem ? budget - static_smem : 0;
     int staged_max = int(std::min<size_t>(MAX_CAND, dyn_budget / view.row_bytes));
-    size_t dyn_smem = size_t(staged_max) * view.row_bytes;
+    size_t dyn_smem = PruneShared::bytes(MAX_CAND + 1) + size_t(staged_max) * view.row_bytes;
     INS_CUDA(cudaFuncSetAttribute(prune_new_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn_smem)));
     INS_CUDA(cudaFuncSetAttribute(backedge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn_smem)));
 
-    uint64_t done = 0;
-    while (done < cn) {
-      uint64_t total_in = inserted_before + c0 + done;
-      uint64_t want = std::max<uint64_t>(ix->ins_min_batch, total_in / std::max<uint32_t>(1, ix->ins_growth_div));
-      uint32_t m = uint32_t(std::min<uint64_t>(std::min<uint64_t>(want, max_batch), cn - done));
-      if (m == 0) m = 1;
-      const uint32_t* b_ids = d_ids.p + done;
-      const float* b_vecs = d_vecs.p + done * dim;
+    // one mini-batch: search, prune, group back-edge pairs, apply them
+    auto run_batch = [&](const uint32_t* b_ids, const float* b_vecs, uint32_t m, uint64_t at) -> int {
       // 1. greedySearch(vec, 1, L) with the visited list
       INS_CHECK(launch_search(ix, m, b_vecs, 1, L, ix->d_oid.p, ix->d_od.p, ix->d_oc.p, ix->d_vis_ids.p, ix->d_vis_d.p,
                               ix->d_vis_len.p, vis_cap, nullptr, 0, nullptr, st));
@@ -479,7 +361,55 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
         INS_CUDA(cudaStreamSynchronize(st));
         if (rep[0]) {
           release_all();
-          return fail(SDB_ERR_INTERNAL, "insert debug: " + std::to_string(rep[0]) + " inconsistent rows after a batch of " + std::to_string(m) + " at offset " + std::to_string(c0 + done) + ", first node " + std::to_string(rep[1]) + " deg " + std::to_string(rep[2]));
+          return fail(SDB_ERR_INTERNAL, "insert debug: " + std::to_string(rep[0]) + " inconsistent rows after a batch of " + std::to_string(m) + " at offset " + std::to_string(at) + ", first node " + std::to_string(rep[1]) + " deg " + std::to_string(rep[2]));
+        }
+      }
+      return SDB_OK;
+    };
+    // how many of a mini-batch's points ended up without any inbound edge (ascending list in d_sel)
+    auto count_unlinked = [&](const uint32_t* b_ids, uint32_t m, uint32_t* out) -> int {
+      unlinked_flag_kernel<<<m, 64, 0, st>>>(b_ids, m, R, ix->d_adj, ix->d_deg, d_unflag.p);
+      ix->launches++;
+      INS_CUDA(cudaGetLastError());
+      size_t tb = sel_bytes;
+      INS_CUDA(cub::DeviceSelect::Flagged(d_cubtmp.p, tb, thrust::counting_iterator<uint32_t>(0), d_unflag.p, d_sel.p,
+                                          d_misc.p + 3, int(m), st));
+      ix->launches++;
+      INS_CUDA(cudaMemcpyAsync(out, d_misc.p + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      INS_CUDA(cudaStreamSynchronize(st));
+      return SDB_OK;
+    };
+
+    uint64_t done = 0;
+    while (done < cn) {
+      uint64_t total_in = inserted_before + c0 + done;
+      uint64_t want = std::max<uint64_t>(ix->ins_min_batch, total_in / std::max<uint32_t>(1, ix->ins_growth_div));
+      uint32_t m = uint32_t(std::min<uint64_t>(std::min<uint64_t>(want, max_batch), cn - done));
+      if (m == 0) m = 1;
+      const uint32_t* b_ids = d_ids.p + done;
+      const float* b_vecs = d_vecs.p + done * dim;
+      INS_CHECK(run_batch(b_ids, b_vecs, m, c0 + done));
+      if (repair && m > 1) {
+        // Re-insert the points nobody points at, in quarter-size mini-batches, until every point
+        // has an inbound edge or the batches are down to one point (= the sequential schedule,
+        // after which an orphan is what the reference would have produced too).
+        const uint32_t* cur_ids = b_ids;
+        const float* cur_vecs = b_vecs;
+        uint32_t cur_m = m;
+        for (int round = 0; cur_m > 1 && round < 16; ++round) {
+          uint32_t un = 0;
+          INS_CHECK(count_unlinked(cur_ids, cur_m, &un));
+          if (un == 0) break;
+          const int w = round & 1;
+          gather_retry_kernel<<<un, 128, 0, st>>>(d_sel.p, un, cur_ids, cur_vecs, dim, d_retry_ids[w].p, d_retry_vecs[w].p);
+          ix->launches++;
+          INS_CUDA(cudaGetLastError());
+          const uint32_t sub = std::max<uint32_t>(1, std::min<uint32_t>(un, cur_m) / 4);
+          for (uint32_t off = 0; off < un; off += sub)
+            INS_CHECK(run_batch(d_retry_ids[w].p + off, d_retry_vecs[w].p + size_t(off) * dim, std::min(sub, un - off), c0 + done));
+          cur_ids = d_retry_ids[w].p;
+          cur_vecs = d_retry_vecs[w].p;
+          cur_m = sub > 1 ? un : 1;
         }
       }
       done += m;

@@ -1,0 +1,190 @@
+// prune.cuh — shared pieces of the graph-mutation kernels (insert.cu, delete.cu): the store
+// view for DistanceFromPoint (plain.go:87-97, binary.go:213-234, product.go:279-305), the
+// stable candidate sort (distset.go:223-238) and robustPrune (search.go:106-138) run by one
+// CTA over a candidate list held in shared memory.
+#pragma once
+#include "common.cuh"
+#include "index.cuh"
+
+namespace sdb {
+
+constexpr int PRUNE_THREADS = 128;
+constexpr int PRUNE_GROUPS = PRUNE_THREADS / 8;
+constexpr int MAX_CAND = 256;  // visited-list capacity handed to robustPrune
+
+struct StoreView {
+  int mode;  // 0 float rows, 1 bit rows, 2 PQ codes (SDC)
+  int metric;
+  const float* vec; uint32_t vec_pitch; uint32_t dim;
+  const uint64_t* bits; uint32_t bits_pitch; uint32_t words;
+  const uint8_t* codes; uint32_t codes_pitch; uint32_t pqM, pqK;
+  const float* cdist;
+  uint32_t row_bytes;  // bytes staged per candidate row
+};
+
+// Candidate list of one CTA, carved out of dynamic shared memory (capacity chosen per launch).
+struct PruneShared {
+  uint32_t* id;      // [cap] arrival order
+  float* dist;       // [cap]
+  uint32_t* sid;     // [cap] sorted by distance (stable)
+  float* sdist;      // [cap]
+  uint8_t* removed;  // [cap]
+  uint32_t* edges;   // [64] result
+  int n;             // candidates (same value in every thread)
+  int* cnt;          // shared: edges written so far
+  static __host__ __device__ size_t bytes(int cap) {
+    return ((size_t(cap) * 17 + 15) / 16) * 16 + 64 * 4 + 16;
+  }
+  // returns the first byte after the carved area (16-byte aligned)
+  __device__ __forceinline__ unsigned char* carve(unsigned char* base, int cap) {
+    id = reinterpret_cast<uint32_t*>(base);
+    dist = reinterpret_cast<float*>(base + size_t(cap) * 4);
+    sid = reinterpret_cast<uint32_t*>(base + size_t(cap) * 8);
+    sdist = reinterpret_cast<float*>(base + size_t(cap) * 12);
+    removed = base + size_t(cap) * 16;
+    unsigned char* p = base + ((size_t(cap) * 17 + 15) / 16) * 16;
+    edges = reinterpret_cast<uint32_t*>(p);
+    cnt = reinterpret_cast<int*>(p + 64 * 4);
+    n = 0;
+    return p + 64 * 4 + 16;
+  }
+};
+
+// distance between two staged rows by an 8-lane group; result valid in the group's lane 0.
+// All 32 lanes of the warp must call it together.
+template <int METRIC>
+__device__ __forceinline__ float group_float_dist(const float* x, const float* y, uint32_t dim, int g) {
+  constexpr bool L2 = (METRIC == METRIC_EUCLIDEAN);
+  const int trips = dim >> 5;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < trips; ++t) {
+    float4 a = *reinterpret_cast<const float4*>(x + 32 * t + 4 * g);
+    float4 b = *reinterpret_cast<const float4*>(y + 32 * t + 4 * g);
+    trip_accum<L2>(a, b, acc);
+  }
+  float tail = 0.0f;
+  if (g == 0)
+    for (uint32_t i = trips << 5; i < dim; ++i) tail = tail_accum<L2>(x[i], y[i], tail);
+  return metric_epilogue<METRIC>(group_reduce(acc, tail));
+}
+
+__device__ __forceinline__ float row_dist(const StoreView& s, const unsigned char* x, const unsigned char* y, int g) {
+  if (s.mode == 0) {
+    const float* a = reinterpret_cast<const float*>(x);
+    const float* b = reinterpret_cast<const float*>(y);
+    switch (s.metric) {
+      case METRIC_EUCLIDEAN: return group_float_dist<METRIC_EUCLIDEAN>(a, b, s.dim, g);
+      case METRIC_DOT: return group_float_dist<METRIC_DOT>(a, b, s.dim, g);
+      case METRIC_COSINE: return group_float_dist<METRIC_COSINE>(a, b, s.dim, g);
+      default: {
+        // haversine: float64 math in lane 0; keep the warp's shuffle count consistent
+        float r = (g == 0) ? haversine_thread(a, b) : 0.0f;
+        return r;
+      }
+    }
+  }
+  float r = 0.0f;
+  if (g == 0) {
+    if (s.mode == 1) {
+      const uint64_t* a = reinterpret_cast<const uint64_t*>(x);
+      const uint64_t* b = reinterpret_cast<const uint64_t*>(y);
+      int c = 0, u = 0;
+      for (uint32_t w = 0; w < s.words; ++w) {
+        if (s.metric == METRIC_JACCARD) { c += __popcll(a[w] & b[w]); u += __popcll(a[w] | b[w]); }
+        else c += __popcll(a[w] ^ b[w]);
+      }
+      r = bits_finish(s.metric, c, u);
+    } else {
+      // SDC: sum_i centroidDists[i][cx[i]][cy[i]] sequential f32 (product.go:299-303)
+      for (uint32_t m = 0; m < s.pqM; ++m) r = __fadd_rn(r, __ldg(s.cdist + (size_t(m) * s.pqK + x[m]) * s.pqK + y[m]));
+    }
+  }
+  return r;
+}
+
+__device__ __forceinline__ const unsigned char* global_row(const StoreView& s, uint32_t id) {
+  if (s.mode == 0) return reinterpret_cast<const unsigned char*>(s.vec + size_t(id) * s.vec_pitch);
+  if (s.mode == 1) return reinterpret_cast<const unsigned char*>(s.bits + size_t(id) * s.bits_pitch);
+  return s.codes + size_t(id) * s.codes_pitch;
+}
+
+// Stable sort of (id, dist)[0..n) by distance into (sid, sdist): equals the reference's
+// insertion sort (distset.go:223-238, strict '<' swaps => stable).
+__device__ inline void stable_sort_by_dist(PruneShared& sh) {
+  const int n = sh.n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float di = sh.dist[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      float dj = sh.dist[j];
+      rank += (dj < di) || (dj == di && j < i);
+    }
+    sh.sid[rank] = sh.id[i];
+    sh.sdist[rank] = di;
+  }
+  __syncthreads();
+}
+
+// Stage rows of the sorted candidates into shared memory (as many as fit).
+__device__ inline void stage_rows(const StoreView& s, PruneShared& sh, unsigned char* rows, int staged) {
+  const uint32_t vec16 = s.row_bytes / 16;
+  const uint32_t total = uint32_t(staged) * vec16;
+  for (uint32_t t = threadIdx.x; t < total; t += blockDim.x) {
+    const uint32_t c = t / vec16, i = t % vec16;
+    const uint4* src = reinterpret_cast<const uint4*>(global_row(s, sh.sid[c]));
+    reinterpret_cast<uint4*>(rows + size_t(c) * s.row_bytes)[i] = __ldg(src + i);
+  }
+  __syncthreads();
+}
+
+// robustPrune (search.go:106-138) over the sorted candidates in sh.sid/sdist; node = id of
+// the node being pruned (skipped if it appears, search.go:116). Fills sh.edges/sh.cnt.
+__device__ inline void robust_prune_cta(const StoreView& s, PruneShared& sh, const unsigned char* rows, int staged,
+                                 uint32_t node, int R, float alpha) {
+  const int n = sh.n;
+  const int lane = threadIdx.x & 31;
+  const int g = lane & 7;
+  const int grp = threadIdx.x >> 3;  // 0..PRUNE_GROUPS-1
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sh.removed[i] = 0;
+  if (threadIdx.x == 0) *sh.cnt = 0;
+  __syncthreads();
+  for (int i = 0; i < n; ++i) {
+    if (sh.removed[i] || sh.sid[i] == node) continue;  // block-uniform
+    __syncthreads();
+    if (threadIdx.x == 0) sh.edges[(*sh.cnt)++] = sh.sid[i];
+    __syncthreads();
+    if (*sh.cnt >= R) break;
+    const unsigned char* xi = i < staged ? rows + size_t(i) * s.row_bytes : global_row(s, sh.sid[i]);
+    for (int j0 = i + 1; j0 < n; j0 += PRUNE_GROUPS) {
+      int j = j0 + grp;
+      bool act = (j < n) && !sh.removed[j];
+      // warp-uniform skip when none of this warp's 4 groups has work
+      if (!__any_sync(SDB_FULL, act)) continue;
+      int jj = act ? j : i;
+      const unsigned char* yj = jj < staged ? rows + size_t(jj) * s.row_bytes : global_row(s, sh.sid[jj]);
+      float d = row_dist(s, xi, yj, g);
+      if (act && g == 0 && __fmul_rn(alpha, d) < sh.sdist[j]) sh.removed[j] = 1;  // search.go:132
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+}
+
+inline StoreView make_view(const sdb_index* ix) {
+  StoreView s{};
+  s.vec = ix->d_vec; s.vec_pitch = ix->vec_pitch; s.dim = ix->p.dim;
+  s.bits = ix->d_bits; s.bits_pitch = ix->bits_pitch; s.words = ix->words;
+  s.codes = ix->d_codes; s.codes_pitch = ix->codes_pitch; s.pqM = ix->pqM; s.pqK = ix->pqK;
+  s.cdist = ix->d_pq_cdist;
+  if (ix->p.quantizer == SDB_QUANT_BINARY && ix->bq_fitted) {
+    s.mode = 1; s.metric = ix->bq_metric; s.row_bytes = ix->bits_pitch * 8;
+  } else if (ix->p.quantizer == SDB_QUANT_PRODUCT && ix->pq_fitted) {
+    s.mode = 2; s.metric = ix->store_metric; s.row_bytes = ix->codes_pitch;
+  } else {
+    s.mode = 0; s.metric = ix->store_metric; s.row_bytes = ix->vec_pitch * 4;
+  }
+  return s;
+}
+
+
+}  // namespace sdb

@@ -10,9 +10,10 @@ namespace sdb {
 
 namespace {
 
-template <int KIND, int METRIC, int TRIPS, int SETS, bool LEGACY, int MERGE_MIN, class VT, bool FILTER, bool RETRY, int MINB>
-int launch_variant(sdb_index* ix, const SearchArgs& a, cudaStream_t stream) {
-  auto kern = beam_search_kernel<KIND, METRIC, TRIPS, SETS, LEGACY, MERGE_MIN, VT, FILTER, RETRY, MINB>;
+template <int KIND, int METRIC, int TRIPS, int SETS, bool LEGACY, int MERGE_MIN, class VT, bool FILTER, bool RETRY, int MINB,
+          bool XTRA>
+int launch_variant_x(sdb_index* ix, const SearchArgs& a, cudaStream_t stream) {
+  auto kern = beam_search_kernel<KIND, METRIC, TRIPS, SETS, LEGACY, MERGE_MIN, VT, FILTER, RETRY, MINB, XTRA>;
   // FloatEvalGrouped keeps short queries (<= 4 float4 per lane) in registers: no shared copy
   constexpr bool QREG = (KIND == EVAL_FLOAT_FIXED) && !LEGACY && TRIPS <= 4;
   const uint32_t qfloats = (KIND == EVAL_ADC || QREG) ? 0 : (a.dim + 3) / 4 * 4;
@@ -55,6 +56,15 @@ int launch_variant(sdb_index* ix, const SearchArgs& a, cudaStream_t stream) {
   ix->launches++;
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;
+}
+
+// the start node's overflow edges (after deletes; normally none) get their own instantiation so
+// the common case pays nothing for them (the extra loop cost 5 % on C2)
+template <int KIND, int METRIC, int TRIPS, int SETS, bool LEGACY, int MERGE_MIN, class VT, bool FILTER, bool RETRY, int MINB>
+int launch_variant(sdb_index* ix, const SearchArgs& a, cudaStream_t stream) {
+  if (a.n_start_extra != 0)
+    return launch_variant_x<KIND, METRIC, TRIPS, SETS, LEGACY, MERGE_MIN, VT, FILTER, RETRY, MINB, true>(ix, a, stream);
+  return launch_variant_x<KIND, METRIC, TRIPS, SETS, LEGACY, MERGE_MIN, VT, FILTER, RETRY, MINB, false>(ix, a, stream);
 }
 
 template <int KIND, int METRIC, int TRIPS, int SETS, bool LEGACY, int MERGE_MIN, bool FILTER, int MINB, class VT = VisitedCompactN<5888>>
@@ -121,6 +131,8 @@ int launch_search(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k,
   a.bit_metric = ix->bq_metric;
   a.adj = ix->d_adj;
   a.R = ix->p.degree_bound;
+  a.start_extra = ix->d_start_extra.p;
+  a.n_start_extra = uint32_t(ix->h_start_extra.size());
   a.rows = ix->rows;
   a.queries = d_queries;
   a.dim = ix->p.dim;

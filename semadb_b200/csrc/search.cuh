@@ -43,6 +43,8 @@ struct SearchArgs {
   // graph
   const uint32_t* adj;     // [rows][R], INVALID_ID padded
   uint32_t R;
+  const uint32_t* start_extra;  // edges of node 1 beyond R (normally none)
+  uint32_t n_start_extra;
   uint32_t rows;
   // batch
   const float* queries;    // [B][dim]
@@ -717,7 +719,9 @@ __host__ __device__ constexpr size_t warp_smem_bytes(uint32_t qfloats, uint32_t 
 // SETS: FloatEvalFixed pipeline depth (LEGACY: the unpipelined FloatEvalBatch, kept as the
 // A/B baseline); MERGE_MIN > 0: use the batch form of AddWithLimit (CandList::merge) when at
 // least that many candidates survive.
-template <int KIND, int METRIC, int TRIPS, int SETS, bool LEGACY, int MERGE_MIN, class VT, bool FILTER, bool RETRY, int MINB>
+// XTRA: the start node has edges beyond R (a.start_extra) — compiled in only when it does.
+template <int KIND, int METRIC, int TRIPS, int SETS, bool LEGACY, int MERGE_MIN, class VT, bool FILTER, bool RETRY, int MINB,
+          bool XTRA>
 __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uint32_t qfloats, uint32_t qwords) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -907,14 +911,24 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
         pf_n0 = lane < int(a.R) ? __ldg(prow + lane) : INVALID_ID;
         pf_n1 = lane + 32 < int(a.R) ? __ldg(prow + lane + 32) : INVALID_ID;
       }
-      const int nnew = visit_and_stage(n0, n0 != INVALID_ID, n1, n1 != INVALID_ID);
-      nvisited += nnew;
-      ndist += nnew;
-      if (nvisited > vt.limit() || vt.failed) { overflow = true; break; }
-      if (nnew > 0) {
-        evaluate(nnew);
-        if (MERGE_MIN == 0 || !list.merge(cid, cdist, nnew, lane, lt, MERGE_MIN)) add_with_limit(list, nnew);
+      // searchSet.AddWithLimit(neighbours...) (search.go:90), 64 adjacency slots at a time: the
+      // row itself, then — for the start node only — its edges beyond R (orphans re-attached
+      // after deletes, prune.go:137-151; normally none). One copy of the hop body.
+      for (uint32_t x0 = 0;; x0 += CAND_SLOTS) {
+        const int nnew = visit_and_stage(n0, n0 != INVALID_ID, n1, n1 != INVALID_ID);
+        nvisited += nnew;
+        ndist += nnew;
+        if (nvisited > vt.limit() || vt.failed) { overflow = true; break; }
+        if (nnew > 0) {
+          evaluate(nnew);
+          if (MERGE_MIN == 0 || !list.merge(cid, cdist, nnew, lane, lt, MERGE_MIN)) add_with_limit(list, nnew);
+        }
+        if (!XTRA || e != START_ID || x0 >= a.n_start_extra) break;
+        const uint32_t j0 = x0 + lane, j1 = x0 + 32 + lane;
+        n0 = j0 < a.n_start_extra ? __ldg(a.start_extra + j0) : INVALID_ID;
+        n1 = j1 < a.n_start_extra ? __ldg(a.start_extra + j1) : INVALID_ID;
       }
+      if (overflow) break;
       if (FILTER) {
         // resultSet.AddWithLimit(distElem.Point) if the expanded node passes the filter
         // (search.go:93-95). resultSet dedupes with its own visited set, which holds the

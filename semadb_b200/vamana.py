@@ -345,6 +345,36 @@ class _DeviceIndex:
             raise SdbError(_capi.ERR_INVALID, "vectors must be [n, dim]")
         check(self._lib.sdb_insert_batch(self._h, len(ids), _ptr(ids, u64p), _ptr(v, f32p)))
 
+    def insert_update_delete_batch(self, ids, vectors, has_vector=None):
+        """sdb_insert_update_delete: the whole classify / insert / removeInboundEdges / drop /
+        re-insert sequence of vamana.go:136-253 for n changes (has_vector[i] == 0 = nil vector)."""
+        ids, v = _u64(ids), _f32(vectors)
+        if v.shape != (len(ids), self.dim):
+            raise SdbError(_capi.ERR_INVALID, "vectors must be [n, dim]")
+        hv = None if has_vector is None else np.ascontiguousarray(has_vector, dtype=np.uint8)
+        check(self._lib.sdb_insert_update_delete(self._h, len(ids), _ptr(ids, u64p), _ptr(v, f32p), _ptr(hv, u8p)))
+
+    def edge_scan(self, delete_ids):
+        """EdgeScan (node.go:142-199): (toPrune, toSave), ascending ids."""
+        d = _u64(delete_ids)
+        cap = self.max_node_id + 2
+        tp, ts = np.zeros(cap, dtype=np.uint64), np.zeros(cap, dtype=np.uint64)
+        n1, n2 = C.c_uint64(0), C.c_uint64(0)
+        check(self._lib.sdb_edge_scan(self._h, len(d), _ptr(d, u64p), _ptr(tp, u64p), C.byref(n1), _ptr(ts, u64p),
+                                      C.byref(n2)))
+        return tp[:n1.value].copy(), ts[:n2.value].copy()
+
+    def get_start_overflow(self) -> np.ndarray:
+        n = C.c_uint64(0)
+        check(self._lib.sdb_index_get_start_overflow(self._h, 0, None, C.byref(n)))
+        out = np.zeros(max(1, n.value), dtype=np.uint64)
+        check(self._lib.sdb_index_get_start_overflow(self._h, n.value, _ptr(out, u64p), C.byref(n)))
+        return out[:n.value]
+
+    def set_start_overflow(self, ids):
+        ids = _u64(ids)
+        check(self._lib.sdb_index_set_start_overflow(self._h, len(ids), _ptr(ids, u64p)))
+
     def insert_config(self, min_batch=0, max_batch=0, growth_div=0):
         check(self._lib.sdb_insert_config(self._h, min_batch, max_batch, growth_div))
 
@@ -366,20 +396,17 @@ class IndexVamana(_DeviceIndex):
         self.set_start(start_vector)
 
     def insert_update_delete(self, changes: Iterable[IndexVectorChange], pq_first_row: int = 0) -> None:
-        """InsertUpdateDelete (vamana.go:127-263): classify, insert, then Fit.
-        Updates/deletes need the EdgeScan path: not built yet."""
-        ins_ids, ins_vecs = [], []
+        """InsertUpdateDelete (vamana.go:127-263): classify against the store, insert, remove
+        the inbound edges of updated/deleted points, drop deleted rows, re-insert updated
+        points, then Fit (vamana.go:258)."""
+        ids, vecs, has = [], [], []
+        zero = np.zeros(self.dim, dtype=np.float32)
         for ch in changes:
-            if ch.id == STARTID:
-                raise SdbError(_capi.ERR_RESERVED_ID, f"cannot modify point with start id: {STARTID}")
-            if ch.id == 0:
-                raise SdbError(_capi.ERR_RESERVED_ID, "invalid point id: 0")
-            if ch.vector is None:
-                raise SdbError(_capi.ERR_STATE, "delete is not supported by the GPU index yet")
-            ins_ids.append(ch.id)
-            ins_vecs.append(ch.vector)
-        if ins_ids:
-            self.insert_batch(np.asarray(ins_ids, dtype=np.uint64), np.asarray(ins_vecs, dtype=np.float32))
+            ids.append(ch.id)
+            has.append(0 if ch.vector is None else 1)
+            vecs.append(zero if ch.vector is None else np.asarray(ch.vector, dtype=np.float32))
+        if ids:
+            self.insert_update_delete_batch(np.asarray(ids, dtype=np.uint64), np.stack(vecs), np.asarray(has, np.uint8))
         self.fit(pq_first_row)  # vamana.go:258
 
     def search(self, options: SearchVectorVamanaOptions, filter_ids=None):

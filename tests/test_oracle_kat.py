@@ -367,3 +367,99 @@ def test_merge_topk():
     oi, od, oc = O.merge_topk(ids, d, c, 3)
     assert oi[0].tolist() == [1, 4, 2] and oc[0] == 3
     assert od[0].tolist() == [np.float32(0.1), np.float32(0.2), np.float32(0.4)]
+
+
+# ---- update / delete path (vamana.go:223-253, prune.go, node.go:142-199) ----------------
+
+def _graph_invariants(ix, alive_ids):
+    """shard_vector_test.go:198-225 (no dangling or self edges) + vamana_test.go:63-75 (every
+    point reachable from the start node)."""
+    adj, deg = ix.get_graph()
+    alive = set(int(i) for i in alive_ids) | {1}
+    extra = [int(x) for x in ix.start_extra()]
+    seen, todo = {1}, [1]
+    while todo:
+        v = todo.pop()
+        nb = [int(x) for x in adj[v, :deg[v]]] + (extra if v == 1 else [])
+        for u in nb:
+            assert u in alive, f"edge {v}->{u} points at a deleted node"
+            assert u != v, f"self edge at {v}"
+            if u not in seen:
+                seen.add(u)
+                todo.append(u)
+    assert seen == alive, f"{len(alive - seen)} points unreachable from the start node"
+
+
+def test_edge_scan_kat():
+    """vamana_test.go:142-175: graph 2->{3,6} 3->{2,4} 4->{3,5} 5->{4} 6->{2}; deleting {3,4}
+    gives toPrune [2,5] and toSave [5]."""
+    ix = O.OracleIndex(2, "euclidean", 75, 64, 1.2)
+    ix.set_start(np.array([1, 0], np.float32))
+    ix.set_vectors(np.arange(2, 7, dtype=np.uint32), np.zeros((5, 2), np.float32))
+    adj = np.full((7, 64), 0xFFFFFFFF, dtype=np.uint32)
+    deg = np.zeros(7, np.uint16)
+    for nid, e in {2: [3, 6], 3: [2, 4], 4: [3, 5], 5: [4], 6: [2]}.items():
+        adj[nid, :len(e)] = e
+        deg[nid] = len(e)
+    ix.set_graph(adj, deg)
+    tp, ts = ix.edge_scan([3, 4])
+    assert tp.tolist() == [2, 5] and ts.tolist() == [5]
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_update_delete_invariants(threads):
+    """Test_ConcurrentCUD (vamana_test.go:92-140) + shard_vector_test.go:198-225,408-420."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    n = 1500
+    X = rng.random((n, 8), dtype=np.float32)
+    ix = O.OracleIndex(8, "euclidean", 75, 64, 1.2)
+    ix.set_start(O.random_unit_vector(8, 3))
+    ids = np.arange(2, n + 2, dtype=np.uint32)
+    ix.insert(ids, X, threads=threads)
+    # one call: 200 new points, 150 updates, 250 deletes, 5 deletes of absent ids (skipped)
+    new_ids = np.arange(n + 2, n + 202, dtype=np.uint32)
+    upd_ids = ids[100:250]
+    del_ids = ids[300:550]
+    ghost = np.arange(5000, 5005, dtype=np.uint32)
+    ch_ids = np.concatenate([new_ids, upd_ids, del_ids, ghost])
+    vec = rng.random((len(ch_ids), 8), dtype=np.float32)
+    has = np.concatenate([np.ones(350, np.uint8), np.zeros(255, np.uint8)])
+    ix.update_delete(ch_ids, vec, has, threads=threads)
+    alive = np.concatenate([np.setdiff1d(ids, del_ids), new_ids])
+    assert ix.count == len(alive) + 1
+    _graph_invariants(ix, alive)
+    # updated points are found at their new position, deleted ones never come back
+    got = ix.search(vec[200:350], k=10)
+    assert (got["ids"][:, 0] == upd_ids).all() and (got["dists"][:, 0] == 0).all()
+    assert not np.isin(got["ids"], del_ids).any()
+    assert (ix.get_vectors(upd_ids) == vec[200:350]).all()
+
+
+def test_delete_orphan_goes_to_start_overflow():
+    """removeInboundEdges re-attaches nodes that lost every inbound edge to the start node with
+    AddNeighbourIfNotExists (prune.go:137-151), which ignores the degree bound: with the start
+    node already at R edges the orphan lands in the overflow list and stays searchable; a
+    later pruneDeleteNeighbour of the start node folds the overflow back under R."""
+    R = 4
+    ix = O.OracleIndex(2, "euclidean", 25, R, 1.2)
+    ix.set_start(np.array([1, 0], np.float32))
+    pts = np.array([[i, 0.5 * i] for i in range(2, 11)], np.float32)
+    ix.set_vectors(np.arange(2, 11, dtype=np.uint32), pts)
+    adj = np.full((11, R), 0xFFFFFFFF, dtype=np.uint32)
+    deg = np.zeros(11, np.uint16)
+    g = {1: [2, 3, 4, 5], 2: [6, 3], 3: [2, 4], 4: [3, 5], 5: [4, 8], 6: [7], 7: [6], 8: [9, 10], 9: [8], 10: [8]}
+    for nid, e in g.items():
+        adj[nid, :len(e)] = e
+        deg[nid] = len(e)
+    ix.set_graph(adj, deg)
+    tp, ts = ix.edge_scan([6])
+    assert tp.tolist() == [2, 7] and ts.tolist() == [7]
+    ix.update_delete(np.array([6], np.uint32), np.zeros((1, 2), np.float32), np.zeros(1, np.uint8))
+    assert ix.start_extra().tolist() == [7]
+    _graph_invariants(ix, [2, 3, 4, 5, 7, 8, 9, 10])
+    got = ix.search(pts[5:6], k=3, search_size=25)  # node 7's own vector
+    assert got["ids"][0, 0] == 7 and got["dists"][0, 0] == 0
+    # deleting node 2 prunes the start node: candidates = {3,4,5,7} + N(2)\{deleted} -> <= R edges
+    ix.update_delete(np.array([2], np.uint32), np.zeros((1, 2), np.float32), np.zeros(1, np.uint8))
+    assert ix.start_extra().tolist() == []
+    _graph_invariants(ix, [3, 4, 5, 7, 8, 9, 10])
