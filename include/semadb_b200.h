@@ -169,6 +169,11 @@ int sdb_edge_scan(sdb_index* ix, uint64_t n_delete, const uint64_t* delete_ids, 
  * node.go:73-80): hydrate / flush the tail of n1e. get: *n = count, copies min(*n, cap). */
 int sdb_index_get_start_overflow(sdb_index* ix, uint64_t cap, uint64_t* out, uint64_t* n);
 int sdb_index_set_start_overflow(sdb_index* ix, uint64_t n, const uint64_t* ids);
+/* Ascending ids of the nodes whose edge list changed since the last clearing call (the
+ * graphNode.isDirty / CheckAndClearDirty protocol of ItemCache.Flush, node.go:17,104-110,
+ * itemcache.go:236): what nodeStore.Flush must rewrite under n<id>e. *n = how many are dirty;
+ * copies min(*n, cap); flags are cleared only if clear != 0 and everything fitted. */
+int sdb_index_dirty_edges(sdb_index* ix, uint64_t cap, uint64_t* ids_out, uint64_t* n_out, int32_t clear);
 /* Mini-batch schedule of the batched insert: batch b has min(max_batch, max(min_batch,
  * inserted_so_far / growth_div)) points. 0 keeps a field's default. */
 int sdb_insert_config(sdb_index* ix, uint32_t min_batch, uint32_t max_batch, uint32_t growth_div);
@@ -186,6 +191,10 @@ int sdb_index_get_bq_threshold(sdb_index* ix, float* threshold);
 int sdb_index_set_bq_threshold(sdb_index* ix, const float* threshold);
 /* Stored codes of n points: PQ -> M bytes each; BQ -> ceil(dim/64) u64 each (LE bytes). */
 int sdb_index_get_codes(sdb_index* ix, uint64_t n, const uint64_t* ids, uint8_t* out);
+/* Hydrate quantized points from their n<id>q payload alone (binary.go:275-296, product.go:
+ * 349-371: once a point has codes its raw vector is no longer loaded). Same layout as
+ * sdb_index_get_codes; the quantizer must be fitted (sdb_index_set_pq / set_bq_threshold). */
+int sdb_index_set_codes(sdb_index* ix, uint64_t n, const uint64_t* ids, const uint8_t* codes);
 
 /* ---- distance family (distance/distance.go:11-12 FloatDistFunc / BitDistFunc), batched:
  * out[i] = dist(x[i], y[i]) for n pairs of dim floats / `words` u64 words. */

@@ -78,6 +78,8 @@ _SIGS = {
     "sdb_index_get_bq_threshold": (C.c_int, [H, f32p]),
     "sdb_index_set_bq_threshold": (C.c_int, [H, f32p]),
     "sdb_index_get_codes": (C.c_int, [H, C.c_uint64, u64p, u8p]),
+    "sdb_index_set_codes": (C.c_int, [H, C.c_uint64, u64p, u8p]),
+    "sdb_index_dirty_edges": (C.c_int, [H, C.c_uint64, u64p, u64p, C.c_int32]),
     "sdb_distance_float": (C.c_int, [C.c_int32, C.c_int32, C.c_uint64, C.c_uint32, f32p, f32p, f32p]),
     "sdb_distance_bits": (C.c_int, [C.c_int32, C.c_int32, C.c_uint64, C.c_uint32, u64p, u64p, f32p]),
     "sdb_index_query_dists": (C.c_int, [H, f32p, C.c_uint64, u64p, f32p]),

@@ -52,7 +52,7 @@ __global__ void save_mark_kernel(const uint8_t* __restrict__ exists, const uint3
 
 struct PruneDelArgs {
   StoreView s;
-  uint32_t* adj; uint32_t* deg; uint32_t R; float alpha;
+  uint32_t* adj; uint32_t* deg; uint8_t* dirty; uint32_t R; float alpha;
   const uint32_t* delbits;
   const uint32_t* prune_ids; uint32_t n_prune;
   const uint32_t* start_extra; uint32_t n_start_extra;
@@ -151,7 +151,10 @@ __global__ void __launch_bounds__(PRUNE_THREADS) prune_delete_kernel(PruneDelArg
     }
     for (uint32_t t = threadIdx.x; t < a.R; t += blockDim.x)
       a.adj[size_t(A) * a.R + t] = t < uint32_t(cnt) ? sh.edges[t] : INVALID_ID;
-    if (threadIdx.x == 0) a.deg[A] = uint32_t(cnt);
+    if (threadIdx.x == 0) {
+      a.deg[A] = uint32_t(cnt);
+      a.dirty[A] = 1;
+    }
   }
 }
 
@@ -255,7 +258,7 @@ int remove_inbound_edges(sdb_index* ix, const std::vector<uint8_t>& h_del) {
   if (sb.n_prune) {
     PruneDelArgs pa{};
     pa.s = make_view(ix);
-    pa.adj = ix->d_adj; pa.deg = ix->d_deg; pa.R = R; pa.alpha = ix->p.alpha;
+    pa.adj = ix->d_adj; pa.deg = ix->d_deg; pa.dirty = ix->d_dirty; pa.R = R; pa.alpha = ix->p.alpha;
     pa.delbits = sb.d_del.p; pa.prune_ids = sb.d_prune.p; pa.n_prune = sb.n_prune;
     pa.start_extra = ix->d_start_extra.p; pa.n_start_extra = n_extra;
     const size_t cap = (size_t(R) + n_extra) * (R + 1) + 1;
@@ -296,6 +299,7 @@ int remove_inbound_edges(sdb_index* ix, const std::vector<uint8_t>& h_del) {
     }
     SDB_CUDA(cudaMemcpyAsync(ix->d_adj + size_t(START_ID) * R, row.data(), R * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     SDB_CUDA(cudaMemcpyAsync(ix->d_deg + START_ID, &dS, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    SDB_CUDA(cudaMemsetAsync(ix->d_dirty + START_ID, 1, 1, st));
     SDB_CUDA(cudaStreamSynchronize(st));
     if ((rc = upload_start_extra(ix))) return rc;
   }
@@ -303,6 +307,38 @@ int remove_inbound_edges(sdb_index* ix, const std::vector<uint8_t>& h_del) {
 }
 
 }  // namespace
+
+// Ascending ids of the nodes whose edge list changed since the last clearing call
+// (graphNode.isDirty / CheckAndClearDirty, node.go:17,104-110): what a flush must rewrite.
+int dirty_edges_locked(sdb_index* ix, uint64_t cap, uint64_t* ids_out, uint64_t* n_out, int clear) {
+  cudaStream_t st = ix->stream;
+  const uint32_t rows = ix->rows;
+  DevBuf<uint32_t> d_ids, d_cnt;
+  DevBuf<unsigned char> d_tmp;
+  struct Rel {
+    DevBuf<uint32_t>&a, &b; DevBuf<unsigned char>& c;
+    ~Rel() { a.release(); b.release(); c.release(); }
+  } rel{d_ids, d_cnt, d_tmp};
+  int rc;
+  if ((rc = d_ids.ensure(rows)) || (rc = d_cnt.ensure(1))) return rc;
+  thrust::counting_iterator<uint32_t> iota(0);
+  size_t tb = 0;
+  cub::DeviceSelect::Flagged(nullptr, tb, iota, ix->d_dirty, d_ids.p, d_cnt.p, int(rows), st);
+  if ((rc = d_tmp.ensure(tb + 16))) return rc;
+  SDB_CUDA(cub::DeviceSelect::Flagged(d_tmp.p, tb, iota, ix->d_dirty, d_ids.p, d_cnt.p, int(rows), st));
+  ix->launches++;
+  uint32_t n = 0;
+  SDB_CUDA(cudaMemcpyAsync(&n, d_cnt.p, sizeof(n), cudaMemcpyDeviceToHost, st));
+  SDB_CUDA(cudaStreamSynchronize(st));
+  *n_out = n;
+  const uint32_t take = uint32_t(std::min<uint64_t>(n, cap));
+  std::vector<uint32_t> h(take);
+  if (take) SDB_CUDA(cudaMemcpy(h.data(), d_ids.p, take * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  for (uint32_t i = 0; i < take; ++i) ids_out[i] = h[i];
+  if (clear && take == n) SDB_CUDA(cudaMemsetAsync(ix->d_dirty, 0, rows, st));
+  SDB_CUDA(cudaStreamSynchronize(st));
+  return SDB_OK;
+}
 
 int edge_scan_locked(sdb_index* ix, uint64_t n_delete, const uint64_t* delete_ids, uint64_t* to_prune,
                      uint64_t* n_prune, uint64_t* to_save, uint64_t* n_save) {

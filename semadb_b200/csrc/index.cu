@@ -87,6 +87,7 @@ int index_reserve_locked(sdb_index* ix, uint64_t max_node_id) {
   if ((rc = grow(&ix->d_adj, o * ix->p.degree_bound, n * ix->p.degree_bound, ix->stream, true))) return rc;
   if ((rc = grow(&ix->d_deg, o, n, ix->stream))) return rc;
   if ((rc = grow(&ix->d_exists, o, n, ix->stream))) return rc;
+  if ((rc = grow(&ix->d_dirty, o, n, ix->stream))) return rc;
   ix->h_exists.resize(n, 0);
   ix->rows = uint32_t(n);
   return SDB_OK;
@@ -255,6 +256,7 @@ void sdb_index_destroy(sdb_index* ix) {
   cudaFree(ix->d_adj);
   cudaFree(ix->d_deg);
   cudaFree(ix->d_exists);
+  cudaFree(ix->d_dirty);
   ix->d_start_extra.release();
   cudaFree(ix->d_bq_thr);
   cudaFree(ix->d_pq_centroids);
@@ -761,6 +763,45 @@ int sdb_index_get_codes(sdb_index* ix, uint64_t n, const uint64_t* ids, uint8_t*
   }
   SDB_CUDA(cudaStreamSynchronize(ix->stream));
   return SDB_OK;
+}
+
+int sdb_index_set_codes(sdb_index* ix, uint64_t n, const uint64_t* ids, const uint8_t* codes) {
+  if (!ix || (n && (!ids || !codes))) return fail(SDB_ERR_INVALID, "null argument");
+  if (n == 0) return SDB_OK;
+  std::lock_guard<std::mutex> g(ix->mu);
+  SDB_CUDA(cudaSetDevice(ix->device));
+  if (!ix->quant_active()) return fail(SDB_ERR_STATE, "quantizer is not fitted");
+  uint64_t mx = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    if (ids[i] == 0) return fail(SDB_ERR_RESERVED_ID, "invalid point id: 0");
+    mx = std::max(mx, ids[i]);
+  }
+  int rc = index_reserve_locked(ix, mx);
+  if (rc) return rc;
+  size_t width = ix->p.quantizer == SDB_QUANT_PRODUCT ? ix->pqM : size_t(ix->words) * 8;
+  size_t pitch = ix->p.quantizer == SDB_QUANT_PRODUCT ? ix->codes_pitch : size_t(ix->bits_pitch) * 8;
+  uint8_t* base = ix->p.quantizer == SDB_QUANT_PRODUCT ? ix->d_codes : reinterpret_cast<uint8_t*>(ix->d_bits);
+  const uint8_t one = 1;
+  for (uint64_t i = 0; i < n; ++i) {
+    SDB_CUDA(cudaMemcpyAsync(base + size_t(ids[i]) * pitch, codes + i * width, width, cudaMemcpyHostToDevice, ix->stream));
+    SDB_CUDA(cudaMemcpyAsync(ix->d_exists + ids[i], &one, 1, cudaMemcpyHostToDevice, ix->stream));
+  }
+  SDB_CUDA(cudaStreamSynchronize(ix->stream));
+  for (uint64_t i = 0; i < n; ++i) {
+    if (!ix->h_exists[ids[i]]) {
+      ix->h_exists[ids[i]] = 1;
+      ix->count++;
+    }
+    if (ids[i] > ix->max_node_id) ix->max_node_id = uint32_t(ids[i]);
+  }
+  return SDB_OK;
+}
+
+int sdb_index_dirty_edges(sdb_index* ix, uint64_t cap, uint64_t* ids_out, uint64_t* n_out, int32_t clear) {
+  if (!ix || !n_out || (cap && !ids_out)) return fail(SDB_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(ix->mu);
+  SDB_CUDA(cudaSetDevice(ix->device));
+  return dirty_edges_locked(ix, cap, ids_out, n_out, clear);
 }
 
 int sdb_pq_adc_tables(sdb_index* ix, uint32_t B, const float* queries, float* out) {

@@ -93,6 +93,7 @@ struct sdb_index {
   uint32_t* d_adj = nullptr;
   uint32_t* d_deg = nullptr;
   uint8_t* d_exists = nullptr;
+  uint8_t* d_dirty = nullptr;  // [rows] edge list changed since the last sdb_index_dirty_edges(clear)
   std::vector<uint8_t> h_exists;
   // edges of the start node beyond degree_bound: removeInboundEdges re-attaches orphaned nodes
   // with AddNeighbourIfNotExists, which is unbounded (prune.go:137-151, node.go:73-80)
@@ -158,6 +159,7 @@ int fit_locked(sdb_index* ix, uint64_t pq_first_row, int32_t* fitted);
 int insert_update_delete_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const float* vectors,
                                 const uint8_t* has_vector);
 int upload_start_extra(sdb_index* ix);
+int dirty_edges_locked(sdb_index* ix, uint64_t cap, uint64_t* ids_out, uint64_t* n_out, int clear);
 int edge_scan_locked(sdb_index* ix, uint64_t n_delete, const uint64_t* delete_ids, uint64_t* to_prune,
                      uint64_t* n_prune, uint64_t* to_save, uint64_t* n_save);
 }  // namespace sdb

@@ -30,7 +30,7 @@ namespace {
 
 struct InsertArgs {
   StoreView s;
-  uint32_t* adj; uint32_t* deg; uint32_t R; float alpha;
+  uint32_t* adj; uint32_t* deg; uint8_t* dirty; uint32_t R; float alpha;
   const uint32_t* new_ids;   // [m]
   const uint32_t* vis_ids;   // [m][vis_cap] expansion order
   const float* vis_dists;
@@ -71,7 +71,10 @@ __global__ void __launch_bounds__(PRUNE_THREADS) prune_new_kernel(InsertArgs a) 
     a.pair_key[size_t(b) * a.R + t] = e;
     a.pair_val[size_t(b) * a.R + t] = b * a.R + t;
   }
-  if (threadIdx.x == 0) a.deg[A] = uint32_t(cnt);
+  if (threadIdx.x == 0) {
+    a.deg[A] = uint32_t(cnt);
+    a.dirty[A] = 1;
+  }
 }
 
 __global__ void segment_heads_kernel(const uint32_t* keys, uint32_t n, uint32_t* seg_start, uint32_t* seg_count) {
@@ -93,7 +96,7 @@ __global__ void iota_segments_kernel(const uint32_t* keys, uint32_t n, uint32_t*
 
 struct BackArgs {
   StoreView s;
-  uint32_t* adj; uint32_t* deg; uint32_t R; float alpha;
+  uint32_t* adj; uint32_t* deg; uint8_t* dirty; uint32_t R; float alpha;
   const uint32_t* new_ids;     // [m]
   const uint32_t* keys;        // sorted targets
   const uint32_t* vals;        // sorted pair indices (A index = val / R)
@@ -153,7 +156,10 @@ __global__ void __launch_bounds__(PRUNE_THREADS) backedge_kernel(BackArgs a) {
     }
     for (uint32_t t = threadIdx.x; t < a.R; t += blockDim.x)
       a.adj[size_t(B) * a.R + t] = t < uint32_t(cur_n) ? cur[t] : INVALID_ID;
-    if (threadIdx.x == 0) a.deg[B] = uint32_t(cur_n);
+    if (threadIdx.x == 0) {
+      a.deg[B] = uint32_t(cur_n);
+      a.dirty[B] = 1;
+    }
   }
 }
 
@@ -315,7 +321,7 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
                               ix->d_vis_len.p, vis_cap, nullptr, 0, nullptr, st));
       // 2. robustPrune(A) + emit back-edge pairs
       InsertArgs ia{};
-      ia.s = view; ia.adj = ix->d_adj; ia.deg = ix->d_deg; ia.R = R; ia.alpha = ix->p.alpha;
+      ia.s = view; ia.adj = ix->d_adj; ia.deg = ix->d_deg; ia.dirty = ix->d_dirty; ia.R = R; ia.alpha = ix->p.alpha;
       ia.new_ids = b_ids; ia.vis_ids = ix->d_vis_ids.p; ia.vis_dists = ix->d_vis_d.p; ia.vis_len = ix->d_vis_len.p;
       ia.vis_cap = vis_cap; ia.m = m; ia.pair_key = d_pair_key.p; ia.pair_val = d_pair_val.p;
       ia.staged_max = staged_max; ia.error_flag = d_err;
@@ -341,7 +347,7 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
       }
       // 4. back-edges
       BackArgs ba{};
-      ba.s = view; ba.adj = ix->d_adj; ba.deg = ix->d_deg; ba.R = R; ba.alpha = ix->p.alpha;
+      ba.s = view; ba.adj = ix->d_adj; ba.deg = ix->d_deg; ba.dirty = ix->d_dirty; ba.R = R; ba.alpha = ix->p.alpha;
       ba.new_ids = b_ids; ba.keys = skeys; ba.vals = svals; ba.n_pairs = np; ba.seg_start = d_seg.p;
       ba.seg_count = d_segcount; ba.staged_max = staged_max;
       if (m == 1) {

@@ -1,0 +1,30 @@
+"""The C++ host mirror (semadb_b200/host/*.hpp: IndexVamana, bucket codec, query coalescer)
+driven by tests/cpp/host_test.cpp — the reference's own Go tests of the same surface
+(vamana_test.go, conversion_test.go, keys_test.go) restated in the host language stand-in."""
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+BIN = ROOT / "tests" / "cpp" / "host_test"
+
+
+def _build():
+    subprocess.run(["make", "-C", str(ROOT / "tests" / "cpp")], check=True, capture_output=True)
+    assert BIN.exists()
+
+
+def test_host_codec_and_models():
+    _build()
+    r = subprocess.run([str(BIN), "codec"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "host_test codec: ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_host_index_on_gpu():
+    _build()
+    r = subprocess.run([str(BIN), "gpu"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert "host_test gpu: ok" in r.stdout
