@@ -128,6 +128,9 @@ struct sdb_index {
   sdb::DevBuf<uint8_t> d_tmp8;
   sdb::PinBuf<uint8_t> h_stage;
   uint32_t last_B = 0;
+  int vt_level = 0;                  // visited-table size step (search.cu)
+  bool retry_check_pending = false;  // d_work holds the retry count of the last search
+  cudaStream_t last_search_stream = nullptr;
   uint64_t launches = 0;
 
   // insert schedule

@@ -19,6 +19,8 @@
 #include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <string>
 
@@ -125,33 +127,44 @@ __global__ void __launch_bounds__(PRUNE_THREADS) backedge_kernel(BackArgs a) {
     for (uint32_t t = threadIdx.x; t < a.R; t += blockDim.x) cur[t] = a.adj[size_t(B) * a.R + t];
     __syncthreads();
     const unsigned char* xb = global_row(a.s, B);
-    for (uint32_t p = p0; p < a.n_pairs && a.keys[p] == B; ++p) {
-      const uint32_t A = a.new_ids[a.vals[p] / a.R];
-      if (cur_n + 1 > int(a.R)) {
-        // candidateSet.Add(nodeB.neighbours...), Add(vecA): distances from B (insert.go:48-57)
-        const int n = cur_n + 1;
-        sh.n = n;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) sh.id[i] = i < cur_n ? cur[i] : A;
-        __syncthreads();
-        for (int j0 = 0; j0 < n; j0 += PRUNE_GROUPS) {
-          int j = j0 + grp;
-          bool act = j < n;
-          if (!__any_sync(SDB_FULL, act)) continue;
-          const unsigned char* yj = global_row(a.s, sh.id[act ? j : 0]);
-          float d = row_dist(a.s, xb, yj, g);
-          if (act && g == 0) sh.dist[j] = d;
-        }
-        __syncthreads();
-        stable_sort_by_dist(sh);  // candidateSet.Sort() (insert.go:58)
-        int staged = min(n, a.staged_max);
-        stage_rows(a.s, sh, dyn, staged);
-        robust_prune_cta(a.s, sh, dyn, staged, B, int(a.R), a.alpha);
-        cur_n = *sh.cnt;
-        for (int t = threadIdx.x; t < cur_n; t += blockDim.x) cur[t] = sh.edges[t];
-      } else {
-        if (threadIdx.x == 0) cur[cur_n] = A;  // nodeB.AddNeighbour(vecA) (insert.go:62)
+    uint32_t p_end = p0;
+    while (p_end < a.n_pairs && a.keys[p_end] == B) ++p_end;
+    uint32_t p = p0;
+    while (p < p_end) {
+      if (cur_n + 1 <= int(a.R)) {
+        if (threadIdx.x == 0) cur[cur_n] = a.new_ids[a.vals[p] / a.R];  // nodeB.AddNeighbour(vecA) (insert.go:62)
         ++cur_n;
+        ++p;
+        __syncthreads();
+        continue;
       }
+      // deg(B)+1 > R: candidateSet.Add(nodeB.neighbours...), Add(vecA), distances from B, Sort,
+      // robustPrune(B) (insert.go:44-59). A target that receives several new in-edges from one
+      // mini-batch takes them in one prune (with one new point per mini-batch — the reference's
+      // sequential schedule — this is exactly insert.go): hubs would otherwise serialise
+      // hundreds of prunes in one CTA.
+      const int c = int(min(p_end - p, uint32_t(MAX_CAND - cur_n)));
+      const int n = cur_n + c;
+      sh.n = n;
+      for (int i = threadIdx.x; i < n; i += blockDim.x)
+        sh.id[i] = i < cur_n ? cur[i] : a.new_ids[a.vals[p + (i - cur_n)] / a.R];
+      __syncthreads();
+      for (int j0 = 0; j0 < n; j0 += PRUNE_GROUPS) {
+        int j = j0 + grp;
+        bool act = j < n;
+        if (!__any_sync(SDB_FULL, act)) continue;
+        const unsigned char* yj = global_row(a.s, sh.id[act ? j : 0]);
+        float d = row_dist(a.s, xb, yj, g);
+        if (act && g == 0) sh.dist[j] = d;
+      }
+      __syncthreads();
+      stable_sort_by_dist(sh);  // candidateSet.Sort() (insert.go:58)
+      int staged = min(n, a.staged_max);
+      stage_rows(a.s, sh, dyn, staged);
+      robust_prune_cta(a.s, sh, dyn, staged, B, int(a.R), a.alpha);
+      cur_n = *sh.cnt;
+      for (int t = threadIdx.x; t < cur_n; t += blockDim.x) cur[t] = sh.edges[t];
+      p += uint32_t(c);
       __syncthreads();
     }
     for (uint32_t t = threadIdx.x; t < a.R; t += blockDim.x)
@@ -314,11 +327,24 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
     INS_CUDA(cudaFuncSetAttribute(prune_new_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn_smem)));
     INS_CUDA(cudaFuncSetAttribute(backedge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn_smem)));
 
+    // SDB_DEBUG_INSERT_STATS: per-phase wall time (synchronises after every phase)
+    const bool timing = getenv("SDB_DEBUG_INSERT_STATS") != nullptr;
+    double t_phase[4] = {0, 0, 0, 0};
+    auto tick = [&](int phase, std::chrono::steady_clock::time_point& t0) {
+      if (!timing) return;
+      cudaStreamSynchronize(st);
+      auto t1 = std::chrono::steady_clock::now();
+      t_phase[phase] += std::chrono::duration<double>(t1 - t0).count();
+      t0 = t1;
+    };
     // one mini-batch: search, prune, group back-edge pairs, apply them
     auto run_batch = [&](const uint32_t* b_ids, const float* b_vecs, uint32_t m, uint64_t at) -> int {
+      auto t0 = std::chrono::steady_clock::now();
+      if (timing) cudaStreamSynchronize(st);
       // 1. greedySearch(vec, 1, L) with the visited list
       INS_CHECK(launch_search(ix, m, b_vecs, 1, L, ix->d_oid.p, ix->d_od.p, ix->d_oc.p, ix->d_vis_ids.p, ix->d_vis_d.p,
                               ix->d_vis_len.p, vis_cap, nullptr, 0, nullptr, st));
+      tick(0, t0);
       // 2. robustPrune(A) + emit back-edge pairs
       InsertArgs ia{};
       ia.s = view; ia.adj = ix->d_adj; ia.deg = ix->d_deg; ia.dirty = ix->d_dirty; ia.R = R; ia.alpha = ix->p.alpha;
@@ -328,6 +354,7 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
       prune_new_kernel<<<m, PRUNE_THREADS, dyn_smem, st>>>(ia);
       ix->launches++;
       INS_CUDA(cudaGetLastError());
+      tick(1, t0);
       // 3. group pairs by target (stable => batch order within a target)
       const uint32_t np = m * R;
       const uint32_t* skeys = d_pair_key.p;
@@ -345,6 +372,7 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
         ix->launches++;
         INS_CUDA(cudaGetLastError());
       }
+      tick(2, t0);
       // 4. back-edges
       BackArgs ba{};
       ba.s = view; ba.adj = ix->d_adj; ba.deg = ix->d_deg; ba.dirty = ix->d_dirty; ba.R = R; ba.alpha = ix->p.alpha;
@@ -359,6 +387,7 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
       backedge_kernel<<<grid, PRUNE_THREADS, dyn_smem, st>>>(ba);
       ix->launches++;
       INS_CUDA(cudaGetLastError());
+      tick(3, t0);
       if (debug) {
         INS_CUDA(cudaMemsetAsync(d_misc.p + 4, 0, 3 * sizeof(uint32_t), st));
         check_rows_kernel<<<(ix->rows + 255) / 256, 256, 0, st>>>(ix->d_adj, ix->d_deg, ix->d_exists, ix->rows, R, d_misc.p + 4);
@@ -387,6 +416,7 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
     };
 
     uint64_t done = 0;
+    uint64_t stat_unlinked[2] = {0, 0};
     while (done < cn) {
       uint64_t total_in = inserted_before + c0 + done;
       uint64_t want = std::max<uint64_t>(ix->ins_min_batch, total_in / std::max<uint32_t>(1, ix->ins_growth_div));
@@ -396,15 +426,16 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
       const float* b_vecs = d_vecs.p + done * dim;
       INS_CHECK(run_batch(b_ids, b_vecs, m, c0 + done));
       if (repair && m > 1) {
-        // Re-insert the points nobody points at, in quarter-size mini-batches, until every point
-        // has an inbound edge or the batches are down to one point (= the sequential schedule,
-        // after which an orphan is what the reference would have produced too).
+        // Re-insert the points nobody points at, in quarter-size mini-batches: mutually close
+        // new points then find each other. At most two rounds — a point every neighbour prunes
+        // away again is an orphan the sequential schedule produces too (robustPrune(B) drops it).
         const uint32_t* cur_ids = b_ids;
         const float* cur_vecs = b_vecs;
         uint32_t cur_m = m;
-        for (int round = 0; cur_m > 1 && round < 16; ++round) {
+        for (int round = 0; cur_m > 1 && round < 2; ++round) {
           uint32_t un = 0;
           INS_CHECK(count_unlinked(cur_ids, cur_m, &un));
+          stat_unlinked[round] += un;
           if (un == 0) break;
           const int w = round & 1;
           gather_retry_kernel<<<un, 128, 0, st>>>(d_sel.p, un, cur_ids, cur_vecs, dim, d_retry_ids[w].p, d_retry_vecs[w].p);
@@ -420,6 +451,12 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
       }
       done += m;
     }
+    if (debug || getenv("SDB_DEBUG_INSERT_STATS"))
+      fprintf(stderr, "[sdb] insert chunk of %llu: %llu points without an inbound edge after their mini-batch, %llu after one repair round\n",
+              (unsigned long long)cn, (unsigned long long)stat_unlinked[0], (unsigned long long)stat_unlinked[1]);
+    if (timing)
+      fprintf(stderr, "[sdb] insert phases: search %.3fs, prune_new %.3fs, pair sort %.3fs, backedge %.3fs\n", t_phase[0],
+              t_phase[1], t_phase[2], t_phase[3]);
     INS_CUDA(cudaStreamSynchronize(st));
   }
   uint32_t h_misc[2] = {0, 0};

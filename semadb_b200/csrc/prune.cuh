@@ -84,20 +84,24 @@ __device__ __forceinline__ float row_dist(const StoreView& s, const unsigned cha
     }
   }
   float r = 0.0f;
-  if (g == 0) {
-    if (s.mode == 1) {
-      const uint64_t* a = reinterpret_cast<const uint64_t*>(x);
-      const uint64_t* b = reinterpret_cast<const uint64_t*>(y);
-      int c = 0, u = 0;
-      for (uint32_t w = 0; w < s.words; ++w) {
-        if (s.metric == METRIC_JACCARD) { c += __popcll(a[w] & b[w]); u += __popcll(a[w] | b[w]); }
-        else c += __popcll(a[w] ^ b[w]);
-      }
-      r = bits_finish(s.metric, c, u);
-    } else {
-      // SDC: sum_i centroidDists[i][cx[i]][cy[i]] sequential f32 (product.go:299-303)
-      for (uint32_t m = 0; m < s.pqM; ++m) r = __fadd_rn(r, __ldg(s.cdist + (size_t(m) * s.pqK + x[m]) * s.pqK + y[m]));
+  if (s.mode == 1) {
+    // bit rows: the 8 lanes split the words (integer sums: order-free)
+    const uint64_t* a = reinterpret_cast<const uint64_t*>(x);
+    const uint64_t* b = reinterpret_cast<const uint64_t*>(y);
+    int c = 0, u = 0;
+    for (uint32_t w = g; w < s.words; w += 8) {
+      if (s.metric == METRIC_JACCARD) { c += __popcll(a[w] & b[w]); u += __popcll(a[w] | b[w]); }
+      else c += __popcll(a[w] ^ b[w]);
     }
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1) {
+      c += __shfl_down_sync(SDB_FULL, c, o, 8);
+      u += __shfl_down_sync(SDB_FULL, u, o, 8);
+    }
+    r = bits_finish(s.metric, c, u);
+  } else if (g == 0) {
+    // SDC: sum_i centroidDists[i][cx[i]][cy[i]] sequential f32 (product.go:299-303)
+    for (uint32_t m = 0; m < s.pqM; ++m) r = __fadd_rn(r, __ldg(s.cdist + (size_t(m) * s.pqK + x[m]) * s.pqK + y[m]));
   }
   return r;
 }

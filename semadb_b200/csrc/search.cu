@@ -18,7 +18,7 @@ int launch_variant_x(sdb_index* ix, const SearchArgs& a, cudaStream_t stream) {
   constexpr bool QREG = (KIND == EVAL_FLOAT_FIXED) && !LEGACY && TRIPS <= 4;
   const uint32_t qfloats = (KIND == EVAL_ADC || QREG) ? 0 : (a.dim + 3) / 4 * 4;
   const uint32_t qwords = (KIND == EVAL_BITS) ? a.bits_pitch : 0;
-  const size_t smem = warp_smem_bytes<VT, FILTER>(qfloats, qwords);
+  const size_t smem = warp_smem_bytes<VT, FILTER>(qfloats, qwords, a.vt_slots);
   static thread_local int cached_dev = -1;
   static thread_local size_t cached_smem = 0;
   static thread_local int ctas_per_sm = 0;
@@ -67,14 +67,21 @@ int launch_variant(sdb_index* ix, const SearchArgs& a, cudaStream_t stream) {
   return launch_variant_x<KIND, METRIC, TRIPS, SETS, LEGACY, MERGE_MIN, VT, FILTER, RETRY, MINB, false>(ix, a, stream);
 }
 
-template <int KIND, int METRIC, int TRIPS, int SETS, bool LEGACY, int MERGE_MIN, bool FILTER, int MINB, class VT = VisitedCompactN<5888>>
+template <int KIND, int METRIC, int TRIPS, int SETS, bool LEGACY, int MERGE_MIN, bool FILTER, int MINB, class VT = VisitedCompactN>
 int launch_with_retry(sdb_index* ix, SearchArgs a, cudaStream_t stream) {
   int rc = launch_variant<KIND, METRIC, TRIPS, SETS, LEGACY, MERGE_MIN, VT, FILTER, false, MINB>(ix, a, stream);
   if (rc) return rc;
   // second pass over queries whose visited set overflowed (normally none): u32 table, 32768 slots
   a.work_counter = a.work_counter + 2;
   constexpr int RK = (KIND == EVAL_FLOAT_FIXED) ? EVAL_FLOAT_GENERIC : KIND;
-  return launch_variant<RK, METRIC, 1, 1, false, 0, VisitedTable<15>, FILTER, true, 1>(ix, a, stream);
+  constexpr int RT = (KIND == EVAL_BITS) ? TRIPS : 1;  // bit rows: chunks per row must still cover the row
+  if (getenv("SDB_DEBUG_RETRY")) {
+    uint32_t h[2] = {0, 0};
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, a.work_counter - 2, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[sdb] beam search: %u of %u queries overflowed the compact visited table -> retry launch\n", h[1], a.B);
+  }
+  return launch_variant<RK, METRIC, RT, 1, false, 0, VisitedTable<15>, FILTER, true, 1>(ix, a, stream);
 }
 
 // Tuning knob for A/B runs on the GPU (not part of the ABI): SDB_K1_VARIANT picks the
@@ -94,7 +101,7 @@ int launch_float(sdb_index* ix, const SearchArgs& a, bool filtered, cudaStream_t
           // round-1 baseline (unpipelined evaluator, sequential list update, 8192-slot table)
           case 0: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 4, 8, true, 0, false, 12, VisitedCompact>(ix, a, stream);
           case 1: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 4, 6, false, 0, false, 12>(ix, a, stream);
-          case 2: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 4, 5, false, 2, false, 12, VisitedCompactN<6144>>(ix, a, stream);
+          case 2: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 4, 5, false, 2, false, 12, VisitedCompactN>(ix, a, stream);
           default: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 4, 6, false, 2, false, 12>(ix, a, stream);
         }
       case 8: return launch_with_retry<EVAL_FLOAT_FIXED, METRIC, 8, 3, false, 2, false, 12>(ix, a, stream);
@@ -112,12 +119,24 @@ int launch_search(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k,
                   float* d_out_dists, uint32_t* d_out_counts, uint32_t* d_vis_ids, float* d_vis_dists,
                   uint32_t* d_vis_len, uint32_t vis_cap, const uint32_t* d_filter_seed, uint32_t n_filter_seed,
                   const uint32_t* d_filter_bits, cudaStream_t stream) {
+  // Visited-table size for this launch: start at 5888 slots; if the previous search on this
+  // handle sent more than 1 % of its queries to the RETRY launch (they visited more nodes than
+  // 87.5 % of the table), step up. Read only when the stream is idle: never adds a sync.
+  if (ix->retry_check_pending && cudaStreamQuery(ix->last_search_stream) == cudaSuccess) {
+    uint32_t h_retry = 0;
+    SDB_CUDA(cudaMemcpy(&h_retry, ix->d_work.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (uint64_t(h_retry) * 100 > ix->last_B && ix->vt_level < 2) ix->vt_level++;
+    ix->retry_check_pending = false;
+  }
   int rc;
   if ((rc = ix->d_hops.ensure(B))) return rc;
   if ((rc = ix->d_ndist.ensure(B))) return rc;
   if ((rc = ix->d_work.ensure(4 + size_t(B)))) return rc;
+  static const uint32_t kSlots[3] = {5888, 8192, 12288};
   SDB_CUDA(cudaMemsetAsync(ix->d_work.p, 0, 4 * sizeof(uint32_t), stream));
   SearchArgs a{};
+  a.vt_slots = kSlots[ix->vt_level];
+  if (const char* e = getenv("SDB_VT_SLOTS")) a.vt_slots = uint32_t(atoi(e)) / 8 * 8;
   a.vec = ix->d_vec;
   a.vec_pitch = ix->vec_pitch;
   a.bits = ix->d_bits;
@@ -159,18 +178,32 @@ int launch_search(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k,
   a.retry_count = ix->d_work.p + 1;
   a.retry_list = ix->d_work.p + 4;
   ix->last_B = B;
+  ix->retry_check_pending = true;
+  ix->last_search_stream = stream;
   const bool filtered = d_filter_bits != nullptr;
 
   if (ix->p.quantizer == SDB_QUANT_BINARY && ix->bq_fitted) {
-    return filtered ? launch_with_retry<EVAL_BITS, 0, 1, 1, false, 0, true, 1>(ix, a, stream)
-                    : launch_with_retry<EVAL_BITS, 0, 1, 1, false, 0, false, 12>(ix, a, stream);
+    // KIND = bits: METRIC = hamming / jaccard, TRIPS = 128-byte chunks per row, SETS = pipeline depth
+    const bool jac = ix->bq_metric == SDB_METRIC_JACCARD;
+    const uint32_t nch = (ix->bits_pitch + 15) / 16;
+    if (filtered) {
+      return jac ? launch_with_retry<EVAL_BITS, METRIC_JACCARD, 4, 2, false, 0, true, 1>(ix, a, stream)
+                 : launch_with_retry<EVAL_BITS, METRIC_HAMMING, 4, 2, false, 0, true, 1>(ix, a, stream);
+    }
+    if (jac) {
+      if (nch <= 1) return launch_with_retry<EVAL_BITS, METRIC_JACCARD, 1, 8, false, 2, false, 12>(ix, a, stream);
+      return launch_with_retry<EVAL_BITS, METRIC_JACCARD, 4, 2, false, 2, false, 12>(ix, a, stream);
+    }
+    if (nch <= 1) return launch_with_retry<EVAL_BITS, METRIC_HAMMING, 1, 8, false, 2, false, 12>(ix, a, stream);
+    if (nch <= 2) return launch_with_retry<EVAL_BITS, METRIC_HAMMING, 2, 4, false, 2, false, 12>(ix, a, stream);
+    return launch_with_retry<EVAL_BITS, METRIC_HAMMING, 4, 2, false, 2, false, 12>(ix, a, stream);
   }
   if (ix->p.quantizer == SDB_QUANT_PRODUCT && ix->pq_fitted) {
     if ((rc = ix->d_adc.ensure(size_t(B) * ix->pqM * ix->pqK))) return rc;
     if ((rc = launch_adc_tables(ix, B, d_queries, ix->d_adc.p, stream))) return rc;
     a.adc = ix->d_adc.p;
     return filtered ? launch_with_retry<EVAL_ADC, 0, 1, 1, false, 0, true, 1>(ix, a, stream)
-                    : launch_with_retry<EVAL_ADC, 0, 1, 1, false, 0, false, 12>(ix, a, stream);
+                    : launch_with_retry<EVAL_ADC, 0, 1, 1, false, 2, false, 12>(ix, a, stream);
   }
   switch (ix->store_metric) {
     case SDB_METRIC_EUCLIDEAN: return launch_float<METRIC_EUCLIDEAN>(ix, a, filtered, stream);

@@ -68,6 +68,7 @@ struct SearchArgs {
   const uint32_t* filter_bits;  // bitmask over rows
   // work distribution: work_counter hands out batch slots; a query whose visited table
   // overflows is appended to retry_list and re-run by the RETRY launch (bigger table).
+  uint32_t vt_slots;  // VisitedCompactN slot count for this launch
   uint32_t flags;  // tuning (A/B): bit 0 = probe the two ids of a lane one after the other
   uint32_t* work_counter;
   uint32_t* retry_list;
@@ -80,10 +81,11 @@ struct VisitedTable {
   static constexpr uint32_t SLOTS = 1u << HBITS;
   static constexpr uint32_t LIMIT = SLOTS - SLOTS / 8;  // refuse beyond 87.5 % load
   static constexpr size_t BYTES = size_t(SLOTS) * 4;
+  static __host__ __device__ constexpr size_t bytes(uint32_t) { return BYTES; }
   uint32_t* t;
   bool failed;
   __device__ __forceinline__ uint32_t limit() const { return LIMIT; }
-  __device__ __forceinline__ void init(unsigned char* base, uint32_t) { t = reinterpret_cast<uint32_t*>(base); }
+  __device__ __forceinline__ void init(unsigned char* base, uint32_t, uint32_t) { t = reinterpret_cast<uint32_t*>(base); }
   __device__ __forceinline__ void clear(int lane) {
     uint4 e = make_uint4(INVALID_ID, INVALID_ID, INVALID_ID, INVALID_ID);
     uint4* p = reinterpret_cast<uint4*>(t);
@@ -125,11 +127,12 @@ struct VisitedCompact {
   static constexpr uint32_t SLOTS = 1u << HB;
   static constexpr uint32_t LIMIT = SLOTS - SLOTS / 8;
   static constexpr size_t BYTES = SLOTS * 2;
+  static __host__ __device__ constexpr size_t bytes(uint32_t) { return BYTES; }
   unsigned short* t;
   uint32_t mask, rb, rmask, dmax;
   bool failed;
   __device__ __forceinline__ uint32_t limit() const { return LIMIT; }
-  __device__ __forceinline__ void init(unsigned char* base, uint32_t rows) {
+  __device__ __forceinline__ void init(unsigned char* base, uint32_t rows, uint32_t) {
     t = reinterpret_cast<unsigned short*>(base);
     uint32_t b = rows <= SLOTS ? HB : 32 - __clz(rows - 1);
     if (b < HB) b = HB;
@@ -225,28 +228,29 @@ struct VisitedCompact {
   }
 };
 
-// ---- exact visited set, compact form with a non-power-of-two slot count ------------------
-// Same quotienting idea as VisitedCompact with NSLOTS = 6144 (12 KB): together with the trimmed
-// list/staging areas a query-warp then needs 13.4 KB of shared memory, so 16 instead of 12
-// query-warps are resident per SM. pi(id) = id*A mod 2^b as before; span = ceil(2^b / NSLOTS),
-// home slot = pi / span, remainder = pi % span, entry = 1 + remainder + disp*span (16 bits).
-// disp <= dmax = (65535 - span) / span: 382 at 1M rows, 46 at 8M rows; beyond that (or above
-// 87.5 % load) the query goes to the RETRY launch.
-template <uint32_t NSLOTS>
+// ---- exact visited set, compact form with a launch-time slot count ------------------------
+// Same quotienting idea as VisitedCompact with any slot count (multiple of 8), chosen per launch
+// (SearchArgs::vt_slots): 5888 slots (11.5 KB) keep a dim-128 query-warp at 12.9 KB of shared
+// memory, which leaves more of the unified array to L1 — where in-flight loads land — than
+// 8192 did; workloads that visit more nodes per query (more hops, saturated degrees) get a
+// bigger table instead of falling into the RETRY launch (search.cu adapts the size).
+// pi(id) = id*A mod 2^b as before; span = ceil(2^b / slots), home slot = pi / span, remainder
+// = pi % span, entry = 1 + remainder + disp*span (16 bits). disp <= dmax = (65535 - span) /
+// span: 382 at 1M rows and 5888 slots; beyond that (or above 87.5 % load) -> RETRY launch.
 struct VisitedCompactN {
-  static constexpr uint32_t SLOTS = NSLOTS;
-  static constexpr size_t BYTES = size_t(NSLOTS) * 2;
+  static __host__ __device__ constexpr size_t bytes(uint32_t slots) { return size_t(slots) * 2; }
   unsigned short* t;
-  uint32_t mask, span, magic, used, dmax, lim;
+  uint32_t nslots, mask, span, magic, used, dmax, lim;
   bool failed;
   __device__ __forceinline__ uint32_t limit() const { return lim; }
-  __device__ __forceinline__ void init(unsigned char* base, uint32_t rows) {
+  __device__ __forceinline__ void init(unsigned char* base, uint32_t rows, uint32_t slots) {
     t = reinterpret_cast<unsigned short*>(base);
+    nslots = slots;
     uint32_t b = rows <= 2 ? 1 : 32 - __clz(rows - 1);
     if (b < 16) b = 16;
     mask = b >= 32 ? 0xFFFFFFFFu : ((1u << b) - 1);
     const uint64_t space = uint64_t(1) << b;
-    span = uint32_t((space + NSLOTS - 1) / NSLOTS);
+    span = uint32_t((space + slots - 1) / slots);
     magic = uint32_t((uint64_t(1) << 32) / span);
     used = uint32_t((space + span - 1) / span);
     dmax = span >= 32768 ? 0 : (65535u - span) / span;
@@ -256,7 +260,7 @@ struct VisitedCompactN {
   __device__ __forceinline__ void clear(int lane) {
     uint4 z = make_uint4(0, 0, 0, 0);
     uint4* p = reinterpret_cast<uint4*>(t);
-    for (uint32_t i = lane; i < NSLOTS * 2 / 16; i += 32) p[i] = z;
+    for (uint32_t i = lane; i < nslots * 2 / 16; i += 32) p[i] = z;
     failed = false;
   }
   __device__ __forceinline__ void home(uint32_t id, uint32_t& slot, uint32_t& code) const {
@@ -364,10 +368,14 @@ struct CandList {
   // that order: an element with d <= theta (the rank cap-1 distance) is never rejected
   // (worst >= theta whenever the list is full) and never evicted (that would need cap+1
   // elements with d <= theta); equal distances keep arrival order (strict '<' bubble).
-  // Otherwise (a tie straddles the cut — the reference then lets the newest equal win,
-  // distset.go:184-194) or if a candidate distance is NaN, nothing is modified and false is
-  // returned: the caller applies the sequential form. min_m: below this many surviving
-  // candidates the sequential form is cheaper — also returns false, untouched.
+  // If a tie straddles the cut the reference lets the newest equal win the last slot
+  // (distset.go:184-194); that one slot is fixed up exactly (see below), which matters for
+  // integer distances (hamming, PQ) where such ties are everywhere; with TIEFIX = false (float
+  // metrics, ties rare) a tie returns false instead. Also returns false, with the list
+  // untouched, if a candidate distance is NaN (then, and for the rest of the query, the caller
+  // applies the sequential form) or fewer than min_m candidates survive (the sequential form
+  // is cheaper).
+  template <bool TIEFIX>
   __device__ __forceinline__ bool merge(const uint32_t* cid, const float* cdist, int n, int lane, uint32_t lt, int min_m) {
     const int len0 = len;
     const bool full = (len0 == cap);
@@ -430,8 +438,18 @@ struct CandList {
       if (take[j]) { oid[j] = id[i]; od[j] = dist[i]; }
       below += __popc(x[j]);
     }
+    // Tie across the cut: ranks cap-1 (last kept) and cap (first dropped) share a distance
+    // theta. Sequential AddWithLimit then differs from the stable order in exactly one slot:
+    // once the list is all <= theta, a newcomer with d == theta overwrites the last slot
+    // (distset.go:184-194) and a newcomer with d < theta evicts it. So the last slot ends up
+    // holding the last candidate with d == theta that arrives after the last *strict* insert
+    // (a candidate with d < the worst of its time), if there is one. The last strict insert
+    // is the later of: the candidate whose arrival brings the number of elements <= theta to
+    // cap (every <= theta candidate up to it met a worst > theta), and the last candidate
+    // with d < theta. Everything else equals the stable order computed above.
+    int x_last = -1;
+    float theta = 0.0f;
     if (len0 + m > cap) {
-      // distances at ranks cap-1 (last kept) and cap (first dropped)
       float dcut[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
@@ -443,7 +461,36 @@ struct CandList {
         if (h1) v = __shfl_sync(SDB_FULL, d1, __ffs(h1) - 1);
         dcut[e] = v;
       }
-      if (dcut[0] == dcut[1]) return false;
+      if (dcut[0] == dcut[1]) {
+        // float metrics: ties are rare — hand the hop to the sequential form (list untouched)
+        if (!TIEFIX) return false;
+        theta = dcut[0];
+        // old items with dist <= theta (uniform binary search)
+        int lo = 0, hi = len0;
+#pragma unroll
+        for (int it = 0; it < 7; ++it) {
+          const int mid = (lo + hi) >> 1;
+          const float xm = dist[min(mid, LIST_SLOTS - 1)];
+          if (lo < hi) { if (xm <= theta) lo = mid + 1; else hi = mid; }
+        }
+        const int need = cap - lo;  // candidates <= theta still needed to fill the list
+        const uint32_t le0 = __ballot_sync(SDB_FULL, s0 && d0 <= theta), le1 = __ballot_sync(SDB_FULL, s1 && d1 <= theta);
+        const uint32_t ls0 = __ballot_sync(SDB_FULL, s0 && d0 < theta), ls1 = __ballot_sync(SDB_FULL, s1 && d1 < theta);
+        uint32_t eq0 = le0 & ~ls0, eq1 = le1 & ~ls1;
+        int c_t = -1;
+        if (need > 0) {
+          const int n0 = __popc(le0);
+          c_t = need <= n0 ? int(__fns(le0, 0, need)) : 32 + int(__fns(le1, 0, need - n0));
+        }
+        const int i1 = ls1 ? 63 - __clz(ls1) : (ls0 ? 31 - __clz(ls0) : -1);
+        const int t_last = max(c_t, i1);
+        // keep only d == theta candidates that arrive after t_last
+        if (t_last >= 0) {
+          eq0 = t_last >= 31 ? 0u : (eq0 & ~((2u << t_last) - 1u));
+          if (t_last >= 32) eq1 = t_last >= 63 ? 0u : (eq1 & ~((2u << (t_last - 32)) - 1u));
+        }
+        x_last = eq1 ? 63 - __clz(eq1) : (eq0 ? 31 - __clz(eq0) : -1);
+      }
     }
     __syncwarp();
     const int newlen = min(cap, len0 + m);
@@ -456,6 +503,10 @@ struct CandList {
     if (f1 < newlen) { id[f1] = cid[lane + 32]; dist[f1] = d1; }
     len = newlen;
     __syncwarp();
+    if (x_last >= 0) {
+      if (lane == 0) { id[cap - 1] = cid[x_last]; dist[cap - 1] = theta; }
+      __syncwarp();
+    }
     return true;
   }
 };
@@ -615,9 +666,13 @@ struct FloatEvalGeneric {
 
 // Bit-packed rows (binaryQuantizer.DistanceFromFloat, binary.go:187-201): the query is
 // encoded once (binary.go:103-129) into shared memory; hamming / jaccard by popcount
-// (distance.go:45-67). An 8-lane group covers a row 16 bytes per lane per step.
+// (distance.go:45-67). An 8-lane group owns a row, 16 bytes per lane per 128-byte chunk (one
+// full line per group per load); NCH chunks cover rows of up to NCH*1024 bits. Row sets are
+// pipelined like FloatEvalFixed (SETS sets = 4*SETS rows in flight). Integer sums: the
+// cross-lane reduction order is free.
+template <int BMETRIC, int NCH, int SETS>
 struct BitEval {
-  const uint64_t* qb;  // shared: encoded query, padded to bits_pitch words
+  uint64_t q[NCH][2];  // this lane's slice of the encoded query
   __device__ __forceinline__ void encode_query(const SearchArgs& a, const float* qsmem, uint64_t* qbits, int lane) {
     // bit i%64 of word i/64 = q[i] > thr[i]
     for (uint32_t w = 0; w < a.bits_pitch; ++w) {
@@ -632,45 +687,59 @@ struct BitEval {
       if (lane == 0) qbits[w] = word;
     }
     __syncwarp();
-    qb = qbits;
+    const int g = lane & 7;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const uint32_t w = c * 16 + 2 * g;
+      q[c][0] = w < a.bits_pitch ? qbits[w] : 0;
+      q[c][1] = w + 1 < a.bits_pitch ? qbits[w + 1] : 0;
+    }
+  }
+  __device__ __forceinline__ void issue(const SearchArgs& a, const uint32_t* cid, int n, int s, int g, int grp,
+                                        uint4 (&v)[NCH]) {
+    // groups past the end re-read the first candidate's row (result discarded)
+    const int ci = s * 4 + grp;
+    const uint64_t* row = a.bits + size_t(cid[ci < n ? ci : 0]) * a.bits_pitch;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const uint32_t w = c * 16 + 2 * g;
+      v[c] = w < a.bits_pitch ? ldg_u4_stream(row + w) : make_uint4(0, 0, 0, 0);
+    }
+  }
+  __device__ __forceinline__ void consume(float* cdist, int n, int s, int g, int grp, const uint4 (&v)[NCH]) {
+    int x = 0, u = 0;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const uint64_t r0 = (uint64_t(v[c].y) << 32) | v[c].x, r1 = (uint64_t(v[c].w) << 32) | v[c].z;
+      if (BMETRIC == METRIC_JACCARD) {
+        x += __popcll(q[c][0] & r0) + __popcll(q[c][1] & r1);
+        u += __popcll(q[c][0] | r0) + __popcll(q[c][1] | r1);
+      } else {
+        x += __popcll(q[c][0] ^ r0) + __popcll(q[c][1] ^ r1);
+      }
+    }
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1) {
+      x += __shfl_down_sync(SDB_FULL, x, o, 8);
+      if (BMETRIC == METRIC_JACCARD) u += __shfl_down_sync(SDB_FULL, u, o, 8);
+    }
+    const int ci = s * 4 + grp;
+    if (g == 0 && ci < n) cdist[ci] = bits_finish(BMETRIC, x, u);
   }
   __device__ __forceinline__ void eval(const SearchArgs& a, const uint32_t* cid, float* cdist, int n, int lane) {
     const int g = lane & 7, grp = lane >> 3;
-    const int steps = (a.bits_pitch + 15) / 16;  // 16 u64 (128 B) per group step
-    for (int base = 0; base < n; base += 8) {    // two rows per group in flight
-      int x0 = 0, u0 = 0, x1 = 0, u1 = 0;
-      int c0 = base + grp, c1 = base + 4 + grp;
-      const uint64_t* r0 = a.bits + size_t(c0 < n ? cid[c0] : cid[0]) * a.bits_pitch;
-      const uint64_t* r1 = a.bits + size_t(c1 < n ? cid[c1] : cid[0]) * a.bits_pitch;
-      for (int s = 0; s < steps; ++s) {
-        uint32_t w = s * 16 + 2 * g;
-        if (w < a.bits_pitch) {
-          uint4 v0 = ldg_u4_stream(r0 + w);
-          uint4 v1 = ldg_u4_stream(r1 + w);
-          uint64_t qa = qb[w], qc = qb[w + 1];
-          uint64_t a0 = (uint64_t(v0.y) << 32) | v0.x, b0 = (uint64_t(v0.w) << 32) | v0.z;
-          uint64_t a1 = (uint64_t(v1.y) << 32) | v1.x, b1 = (uint64_t(v1.w) << 32) | v1.z;
-          if (a.bit_metric == METRIC_JACCARD) {
-            x0 += __popcll(qa & a0) + __popcll(qc & b0);
-            u0 += __popcll(qa | a0) + __popcll(qc | b0);
-            x1 += __popcll(qa & a1) + __popcll(qc & b1);
-            u1 += __popcll(qa | a1) + __popcll(qc | b1);
-          } else {
-            x0 += __popcll(qa ^ a0) + __popcll(qc ^ b0);
-            x1 += __popcll(qa ^ a1) + __popcll(qc ^ b1);
-          }
-        }
-      }
+    const int nsets = (n + 3) >> 2;
+    uint4 v[SETS][NCH];
 #pragma unroll
-      for (int o = 4; o >= 1; o >>= 1) {
-        x0 += __shfl_down_sync(SDB_FULL, x0, o, 8);
-        u0 += __shfl_down_sync(SDB_FULL, u0, o, 8);
-        x1 += __shfl_down_sync(SDB_FULL, x1, o, 8);
-        u1 += __shfl_down_sync(SDB_FULL, u1, o, 8);
-      }
-      if (g == 0) {
-        if (c0 < n) cdist[c0] = bits_finish(a.bit_metric, x0, u0);
-        if (c1 < n) cdist[c1] = bits_finish(a.bit_metric, x1, u1);
+    for (int u = 0; u < SETS; ++u)
+      if (u < nsets) issue(a, cid, n, u, g, grp, v[u]);
+    for (int base = 0; base < nsets; base += SETS) {
+#pragma unroll
+      for (int u = 0; u < SETS; ++u) {
+        const int s = base + u;
+        if (s >= nsets) break;  // warp-uniform
+        consume(cdist, n, s, g, grp, v[u]);
+        if (s + SETS < nsets) issue(a, cid, n, s + SETS, g, grp, v[u]);
       }
     }
     __syncwarp();
@@ -708,8 +777,8 @@ enum EvalKind : int { EVAL_FLOAT_FIXED = 0, EVAL_FLOAT_GENERIC = 1, EVAL_BITS = 
 
 // ---- shared-memory layout per query-warp ------------------------------------------------
 template <class VT, bool FILTER>
-__host__ __device__ constexpr size_t warp_smem_bytes(uint32_t qfloats, uint32_t qwords) {
-  return ((VT::BYTES + 15) / 16) * 16 + LIST_SLOTS * 8 + (FILTER ? LIST_SLOTS * 8 : 0) + CAND_SLOTS * 8 +
+__host__ __device__ constexpr size_t warp_smem_bytes(uint32_t qfloats, uint32_t qwords, uint32_t vt_slots) {
+  return ((VT::bytes(vt_slots) + 15) / 16) * 16 + LIST_SLOTS * 8 + (FILTER ? LIST_SLOTS * 8 : 0) + CAND_SLOTS * 8 +
          ((size_t(qfloats) * 4 + 15) / 16) * 16 + ((size_t(qwords) * 8 + 15) / 16) * 16;
 }
 
@@ -727,8 +796,8 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
   const int lane = threadIdx.x & 31;
   unsigned char* base = smem_raw;
   VT vt;
-  vt.init(base, a.rows);
-  base += ((VT::BYTES + 15) / 16) * 16;
+  vt.init(base, a.rows, a.vt_slots);
+  base += ((VT::bytes(a.vt_slots) + 15) / 16) * 16;
   CandList list;
   list.id = reinterpret_cast<uint32_t*>(base);
   list.dist = reinterpret_cast<float*>(base + LIST_SLOTS * 4);
@@ -769,7 +838,8 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
     typename std::conditional<LEGACY, FloatEvalBatch<METRIC, (FIXED ? TRIPS : 1), (FIXED ? SETS : 1)>,
                               FloatEvalFixed<METRIC, (FIXED ? TRIPS : 1), (FIXED ? SETS : 1)>>::type ev_fixed;
     FloatEvalGeneric<METRIC> ev_gen;
-    BitEval ev_bits;
+    constexpr bool BITS = (KIND == EVAL_BITS);
+    BitEval<(BITS ? METRIC : METRIC_HAMMING), (BITS ? TRIPS : 1), (BITS ? SETS : 1)> ev_bits;
     AdcEval ev_adc;
     if (KIND == EVAL_FLOAT_FIXED) ev_fixed.load_query(qs, a.queries + size_t(qi) * a.dim, lane);
     if (KIND == EVAL_FLOAT_GENERIC) ev_gen.load_query(qs, lane);
@@ -921,7 +991,8 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
         if (nvisited > vt.limit() || vt.failed) { overflow = true; break; }
         if (nnew > 0) {
           evaluate(nnew);
-          if (MERGE_MIN == 0 || !list.merge(cid, cdist, nnew, lane, lt, MERGE_MIN)) add_with_limit(list, nnew);
+          constexpr bool TIEFIX = (KIND == EVAL_BITS || KIND == EVAL_ADC);  // integer-valued / coarse distances
+          if (MERGE_MIN == 0 || !list.template merge<TIEFIX>(cid, cdist, nnew, lane, lt, MERGE_MIN)) add_with_limit(list, nnew);
         }
         if (!XTRA || e != START_ID || x0 >= a.n_start_extra) break;
         const uint32_t j0 = x0 + lane, j1 = x0 + 32 + lane;
