@@ -153,6 +153,37 @@ def c5a():
                       "mean_out_degree": float(deg.mean()), "search_qps_on_built_graph": len(Q) / (ms * 1e-3)}), flush=True)
 
 
+def flat(n=1_000_000, B=10_000):
+    """K5: IndexFlat.Search for a 10k batch over 1M x 128: tensor-core candidate pass + exact
+    re-score vs the exact CUDA-core scan (same results), through the host-buffer C-ABI call."""
+    import os
+    from semadb_b200.vamana import IndexFlat, IndexVectorFlatParameters
+    X = synth.sift_shaped(n, 128, 3)
+    Q = synth.sift_shaped(B, 128, 4, w_seed=3)
+    g = IndexFlat(IndexVectorFlatParameters(128, "euclidean"))
+    g.set_vectors(np.arange(2, n + 2, dtype=np.uint64), X)
+    out = {}
+    for name, env in (("tensor_core", None), ("exact_cuda_core", "1")):
+        if env:
+            os.environ["SDB_FLAT_EXACT"] = env
+        else:
+            os.environ.pop("SDB_FLAT_EXACT", None)
+        nq = B if env is None else 2000
+        g.flat_search_batch(Q[:nq], K)  # warm-up: scratch allocation, bf16 shadow of the store
+        torch.cuda.synchronize()
+        reps = 3
+        t = time.time()
+        for _ in range(reps):
+            ids, d, c = g.flat_search_batch(Q[:nq], K)
+        dt = (time.time() - t) / reps
+        out[name] = {"queries": nq, "seconds": dt, "qps": nq / dt, "tflops_useful": 2.0 * nq * n * 128 / dt / 1e12}
+        out[name + "_ids"] = ids
+    os.environ.pop("SDB_FLAT_EXACT", None)
+    same = bool((out.pop("tensor_core_ids")[:2000] == out.pop("exact_cuda_core_ids")).all())
+    print(json.dumps({"config": "flat", "workload": f"IndexFlat.Search {B} queries x {n} x 128 f32 L2, k=10 (host buffers in and out)",
+                      "identical_ids_first_2000": same, **out}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("configs", nargs="?", default="c1,c3,c4,c5b,c5a")
@@ -162,7 +193,7 @@ def main():
     a = ap.parse_args()
     for c in a.configs.split(","):
         t = time.time()
-        {"c1": c1, "c3": lambda: c3(a.n_c3), "c4": lambda: c4(a.n_c4), "c5b": lambda: c5b(a.n_c5b), "c5a": c5a}[c]()
+        {"c1": c1, "c3": lambda: c3(a.n_c3), "c4": lambda: c4(a.n_c4), "c5b": lambda: c5b(a.n_c5b), "c5a": c5a, "flat": flat}[c]()
         log(f"{c} done in {time.time() - t:.1f}s")
 
 

@@ -414,6 +414,7 @@ int insert_update_delete_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, 
       ix->h_exists[id] = 0;
       ix->count--;
     }
+    ix->vec_epoch++;
   }
   if (!upd_ids.empty() && (rc = insert_batch_locked(ix, upd_ids.size(), upd_ids.data(), upd_vecs.data(), true))) return rc;
   return SDB_OK;

@@ -205,6 +205,17 @@ int launch_scan(sdb_index* ix, const FlatArgs& a, size_t smem, cudaStream_t stre
 
 int launch_flat(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k, const uint32_t* d_filter_bits,
                 uint64_t* d_out_ids, float* d_out_dists, uint32_t* d_out_counts, cudaStream_t stream) {
+  // f32 stores above a few sample sizes: tensor-core candidate pass + exact re-score (flat_tc.cu),
+  // bit-identical to the exact scan below
+  if (flat_tc_eligible(ix, k, d_filter_bits != nullptr))
+    return launch_flat_tc(ix, B, d_queries, k, d_out_ids, d_out_dists, d_out_counts, stream);
+  return launch_flat_exact(ix, B, d_queries, k, d_filter_bits, d_out_ids, d_out_dists, d_out_counts, stream, 2,
+                           std::max<uint32_t>(2, ix->max_node_id + 1));
+}
+
+int launch_flat_exact(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k, const uint32_t* d_filter_bits,
+                      uint64_t* d_out_ids, float* d_out_dists, uint32_t* d_out_counts, cudaStream_t stream,
+                      uint32_t first_id, uint32_t end_id) {
   FlatArgs a{};
   a.vec = ix->d_vec; a.vec_pitch = ix->vec_pitch;
   a.bits = ix->d_bits; a.bits_pitch = ix->bits_pitch; a.words = ix->words;
@@ -215,8 +226,8 @@ int launch_flat(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k, c
   a.filter_bits = d_filter_bits;
   a.queries = d_queries;
   a.dim = ix->p.dim; a.B = B; a.k = k;
-  a.first_id = 2;  // the start node is not a flat-index point
-  a.end_id = std::max<uint32_t>(2, ix->max_node_id + 1);
+  a.first_id = first_id;  // from 2: the start node is not a flat-index point
+  a.end_id = std::min(std::max(end_id, first_id), std::max<uint32_t>(2, ix->max_node_id + 1));
   uint32_t npts = a.end_id - a.first_id;
   uint32_t qblocks = (B + FQ - 1) / FQ;
   uint32_t want = std::max<uint32_t>(1, (uint32_t(ix->sm_count) * 4 + qblocks - 1) / qblocks);

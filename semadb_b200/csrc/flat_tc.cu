@@ -1,0 +1,451 @@
+// flat_tc.cu — K5 on tensor cores: IndexFlat.Search (shard/index/flat/flat.go:76-132) for a batch
+// of queries over an f32 store, exact results, dense contraction on the tensor pipe.
+//
+// bf16 products cannot be final distances (1e-5 tolerance, SURVEY.md §7.3-⑥), so the tensor
+// cores only *generate candidates*, with a guarantee:
+//   1. exact top-k of every query over the first 1024 points (the exact CUDA-core scan, flat.cu)
+//      gives tau_q >= the true k-th smallest distance; steps 2-3 then run over growing prefixes
+//      of the store (x32 per level: 32k points, 1M, ...), each level's exact top-k tightening
+//      tau for the next, so every level keeps ~32 k candidates per query;
+//   2. a bf16 GEMM (fp32 accumulate) scores every (query, point) pair: a(q,x) = |x|^2 - 2 q~.x~
+//      (+|q|^2) for squared-L2, -q~.x~ for dot/cosine. |a - d| <= eps_q, a bound from the bf16
+//      unit roundoff 2^-8 and the largest point norm: eps_q = c1 |q| xmax + c2 (|q|^2 + xmax^2).
+//      Every pair with a <= tau_q + eps_q is appended to the query's candidate list — a superset
+//      of the true top-k, because a true top-k member has d <= tau_q;
+//   3. candidates are re-scored with the reference's exact summation order (common.cuh) and the
+//      top-k taken by (distance asc, id asc) — flat.go:99,117 with ascending-id iteration.
+// A query whose candidate list overflows falls back to the exact scan. The result is therefore
+// bit-identical to flat.cu's, and tests compare the two.
+//
+// GEMM: mma.sync.m16n8k16 bf16 (CTA tile 128 queries x 128 points, 8 warps of 64x32, K chunks
+// of 64 double-buffered with cp.async, ldmatrix fragments). The accumulators stay in registers,
+// which is what the threshold filter wants: it looks at every score once and keeps ~0.05 %.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "common.cuh"
+#include "index.cuh"
+
+namespace sdb {
+
+namespace {
+
+constexpr int TM = 128, TN = 128, TK = 64;
+constexpr int TPAD = 8;                 // bf16 elements of row padding (16 B): conflict-free ldmatrix
+constexpr int TROW = TK + TPAD;         // 72 bf16 = 144 B per smem row
+constexpr int TC_THREADS = 256;
+constexpr uint32_t CAND_CAP = 4096;     // candidate ids kept per query
+constexpr uint32_t LEVEL0 = 1024;       // points scanned exactly to bound the k-th distance
+constexpr uint32_t LEVEL_RATIO = 32;    // each tensor-core level covers 32x more points than the one before
+constexpr size_t TC_SMEM = size_t(2) * (TM + TN) * TROW * 2 + TN * 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// rows of f32 -> bf16 [n][kp] (zero padded) and squared norms (fp32, sequential per lane then
+// tree: the norm only feeds the candidate bound, not a result)
+__global__ void to_bf16_kernel(const float* src, uint32_t src_pitch, uint32_t dim, uint32_t n, uint32_t n_pad,
+                               __nv_bfloat16* dst, uint32_t kp, float* norms) {
+  const uint32_t row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x & 31;
+  if (row >= n_pad) return;
+  float s = 0.0f;
+  for (uint32_t i = lane; i < kp; i += 32) {
+    float v = (row < n && i < dim) ? src[size_t(row) * src_pitch + i] : 0.0f;
+    s += v * v;
+    dst[size_t(row) * kp + i] = __float2bfloat16_rn(v);
+  }
+  for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(SDB_FULL, s, o);
+  if (lane == 0 && norms) norms[row] = s;
+}
+
+__global__ void xmax_kernel(const float* xn, const uint8_t* exists, uint32_t first, uint32_t end, uint32_t* out_bits) {
+  uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
+  float v = 0.0f;
+  if (i < end && exists[i]) v = xn[i];
+  for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(SDB_FULL, v, o));
+  if ((threadIdx.x & 31) == 0 && v > 0.0f) atomicMax(out_bits, __float_as_uint(v));  // v >= 0: bits are ordered
+}
+
+// per-query pass threshold in "score space": squared-L2 score = xn - 2 acc, dot/cosine score = -acc
+__global__ void thresh_kernel(const float* sample_d, const uint32_t* sample_cnt, uint32_t k, const float* qn,
+                              const uint32_t* xmax_bits, int metric, uint32_t dim, uint32_t B, uint32_t B_pad, float* thr) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= B_pad) return;
+  if (q >= B) { thr[q] = -INFINITY; return; }  // padding rows never pass
+  if (sample_cnt[q] < k) { thr[q] = INFINITY; return; }
+  const float tau = sample_d[size_t(q) * k + (k - 1)];
+  const float x2 = __uint_as_float(*xmax_bits), q2 = qn[q];
+  const float nq = sqrtf(q2), nx = sqrtf(x2);
+  const float c1 = 0.02f;                         // > 2 * 2.01 * 2^-8: bf16 unit roundoff 2^-8 on both factors of -2 q.x
+  const float c2 = float(dim + 16) * 2.4e-7f;     // fp32 accumulation of the GEMM, the norms and the exact kernel
+  float t;
+  if (metric == METRIC_EUCLIDEAN) t = tau + (c1 * nq * nx + c2 * (q2 + x2)) - q2;
+  else if (metric == METRIC_DOT) t = tau + (0.5f * c1 + c2) * nq * nx;
+  else t = tau + (0.5f * c1 + c2) * nq * nx - 1.0f;  // cosine distance = 1 - dot
+  thr[q] = t + fabsf(t) * 1e-6f;
+}
+
+struct TcArgs {
+  const __nv_bfloat16* q16;   // [B_pad][kp]
+  const __nv_bfloat16* x16;   // [rows_pad][kp]
+  const float* xn;            // [rows_pad]
+  const float* thr;           // [B_pad]
+  const uint8_t* exists;
+  uint32_t kp, first_id, end_id, tiles_per_cta;
+  int l2;                     // squared-L2: score = xn - 2 acc; else score = -acc
+  uint32_t* cand; uint32_t* cand_cnt;  // [B][CAND_CAP], [B]
+  uint32_t B;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 2) tc_filter_kernel(TcArgs a) {
+  extern __shared__ __align__(16) unsigned char tc_smem[];
+  __nv_bfloat16(*sA)[TM * TROW] = reinterpret_cast<__nv_bfloat16(*)[TM * TROW]>(tc_smem);
+  __nv_bfloat16(*sB)[TN * TROW] = reinterpret_cast<__nv_bfloat16(*)[TN * TROW]>(tc_smem + size_t(2) * TM * TROW * 2);
+  float* s_xn = reinterpret_cast<float*>(tc_smem + size_t(2) * (TM + TN) * TROW * 2);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps, warp tile 64 x 32
+  const uint32_t q0 = blockIdx.x * TM;
+  const uint32_t nk = a.kp / TK;
+  // this thread's 8 query rows and their thresholds
+  float thr[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) thr[i][h] = a.thr[q0 + wm * 64 + i * 16 + (lane >> 2) + h * 8];
+
+  const uint32_t tile0 = blockIdx.y * a.tiles_per_cta;
+  for (uint32_t t = 0; t < a.tiles_per_cta; ++t) {
+    const uint32_t p0 = a.first_id + (tile0 + t) * TN;
+    if (p0 >= a.end_id) break;
+    float acc[4][4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.0f;
+    auto load_chunk = [&](int buf, uint32_t kc) {
+      // 128 rows x 128 B per operand = 1024 16-byte pieces each: 4 per thread per operand
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int piece = tid + r * TC_THREADS, row = piece >> 3, seg = piece & 7;
+        cp_async16(&sA[buf][row * TROW + seg * 8], a.q16 + size_t(q0 + row) * a.kp + kc * TK + seg * 8);
+        cp_async16(&sB[buf][row * TROW + seg * 8], a.x16 + size_t(p0 + row) * a.kp + kc * TK + seg * 8);
+      }
+      cp_async_commit();
+    };
+    load_chunk(0, 0);
+    if (tid < TN) s_xn[tid] = a.xn[p0 + tid];
+    for (uint32_t kc = 0; kc < nk; ++kc) {
+      const int buf = kc & 1;
+      if (kc + 1 < nk) {
+        load_chunk(buf ^ 1, kc + 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+#pragma unroll
+      for (int ks = 0; ks < TK / 16; ++ks) {
+        uint32_t af[4][4], bf[2][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = wm * 64 + i * 16 + (lane & 15), col = ks * 16 + (lane >> 4) * 8;
+          ldmatrix_x4(af[i], &sA[buf][row * TROW + col]);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {  // two n8 blocks per ldmatrix.x4
+          const int mat = lane >> 3;
+          const int row = wn * 32 + jj * 16 + (lane & 7) + (mat >> 1) * 8, col = ks * 16 + (mat & 1) * 8;
+          ldmatrix_x4(bf[jj], &sB[buf][row * TROW + col]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mma_bf16(acc[i][j], af[i], bf[j >> 1][(j & 1) * 2], bf[j >> 1][(j & 1) * 2 + 1]);
+      }
+      __syncthreads();
+    }
+    // ---- filter: keep (query, point) pairs whose approximate score is under the threshold
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int col = wn * 32 + j * 8 + (lane & 3) * 2 + c2;
+        const float xn = a.l2 ? s_xn[col] : 0.0f;
+        const float scale = a.l2 ? -2.0f : -1.0f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float score = fmaf(scale, acc[i][j][h * 2 + c2], xn);
+            if (score <= thr[i][h]) {
+              const uint32_t pid = p0 + col;
+              const uint32_t q = q0 + wm * 64 + i * 16 + (lane >> 2) + h * 8;
+              if (pid < a.end_id && a.exists[pid] && q < a.B) {
+                const uint32_t slot = atomicAdd(&a.cand_cnt[q], 1u);
+                if (slot < CAND_CAP) a.cand[size_t(q) * CAND_CAP + slot] = pid;
+              }
+            }
+          }
+      }
+    }
+    __syncthreads();  // s_xn is rewritten by the next tile
+  }
+}
+
+// Exact re-score of one query's candidates + top-k by (distance asc, id asc). One CTA per query.
+template <int METRIC>
+__global__ void __launch_bounds__(128) rescore_kernel(const float* vec, uint32_t vec_pitch, uint32_t dim, const float* queries,
+                                                      const uint32_t* cand, const uint32_t* cand_cnt, uint32_t k,
+                                                      uint64_t* out_ids, float* out_d, uint32_t* out_cnt,
+                                                      uint32_t* overflow_list, uint32_t* overflow_cnt, int last_level) {
+  __shared__ float s_d[CAND_CAP];
+  __shared__ uint32_t s_id[CAND_CAP];
+  __shared__ float s_bd[4];
+  __shared__ uint32_t s_bi[4], s_bp[4];
+  extern __shared__ __align__(16) float s_q[];  // [dim rounded up to 4]
+  const uint32_t q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, g = lane & 7, grp = tid >> 3;  // 16 groups
+  const uint32_t n = cand_cnt[q];
+  if (n > CAND_CAP) {
+    // last level: the query goes to the exact scan. Earlier levels only produce a bound for the
+    // next one: keep the previous bound by reporting "fewer than k results" (threshold = +inf
+    // would let everything pass), i.e. leave the level's outputs as they were.
+    if (tid == 0 && last_level) {
+      overflow_list[atomicAdd(overflow_cnt, 1u)] = q;
+      out_cnt[q] = 0;
+    }
+    return;
+  }
+  for (uint32_t i = tid; i < ((dim + 3) & ~3u); i += blockDim.x) s_q[i] = i < dim ? queries[size_t(q) * dim + i] : 0.0f;
+  __syncthreads();
+  constexpr bool L2 = (METRIC == METRIC_EUCLIDEAN);
+  const int trips = dim >> 5;
+  for (uint32_t c0 = 0; c0 < n; c0 += 16) {
+    const uint32_t c = c0 + grp;
+    const bool act = c < n;
+    const uint32_t pid = cand[size_t(q) * CAND_CAP + (act ? c : 0)];
+    const float* row = vec + size_t(pid) * vec_pitch;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < trips; ++t) {
+      const float4 x = *reinterpret_cast<const float4*>(s_q + 32 * t + 4 * g);
+      const float4 y = ldg_f4(row + 32 * t + 4 * g);
+      trip_accum<L2>(x, y, acc);
+    }
+    float tail = 0.0f;
+    if (g == 0)
+      for (uint32_t i = trips << 5; i < dim; ++i) tail = tail_accum<L2>(s_q[i], __ldg(row + i), tail);
+    const float r = group_reduce(acc, tail);
+    if (g == 0 && act) {
+      s_d[c] = metric_epilogue<METRIC>(r);
+      s_id[c] = pid;
+    }
+  }
+  __syncthreads();
+  // k rounds of block-wide arg-min over (distance, id)
+  const uint32_t kk = min(k, n);
+  for (uint32_t r = 0; r < kk; ++r) {
+    float bd = INFINITY;
+    uint32_t bi = 0xFFFFFFFFu, bp = 0xFFFFFFFFu;
+    for (uint32_t i = tid; i < n; i += blockDim.x) {
+      const float d = s_d[i];
+      const uint32_t id = s_id[i];
+      if (id != 0xFFFFFFFFu && (d < bd || (d == bd && id < bi) || bp == 0xFFFFFFFFu)) { bd = d; bi = id; bp = i; }
+    }
+    for (int o = 16; o >= 1; o >>= 1) {
+      const float od = __shfl_xor_sync(SDB_FULL, bd, o);
+      const uint32_t oi = __shfl_xor_sync(SDB_FULL, bi, o), op = __shfl_xor_sync(SDB_FULL, bp, o);
+      if (op != 0xFFFFFFFFu && (bp == 0xFFFFFFFFu || od < bd || (od == bd && oi < bi))) { bd = od; bi = oi; bp = op; }
+    }
+    if (lane == 0) { s_bd[tid >> 5] = bd; s_bi[tid >> 5] = bi; s_bp[tid >> 5] = bp; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < 4; ++w)
+        if (s_bp[w] != 0xFFFFFFFFu && (bp == 0xFFFFFFFFu || s_bd[w] < bd || (s_bd[w] == bd && s_bi[w] < bi))) {
+          bd = s_bd[w]; bi = s_bi[w]; bp = s_bp[w];
+        }
+      out_ids[size_t(q) * k + r] = bi;
+      out_d[size_t(q) * k + r] = bd;
+      s_id[bp] = 0xFFFFFFFFu;  // taken
+    }
+    __syncthreads();
+  }
+  for (uint32_t r = kk + tid; r < k; r += blockDim.x) {
+    out_ids[size_t(q) * k + r] = 0;
+    out_d[size_t(q) * k + r] = __int_as_float(0x7f800000);
+  }
+  if (tid == 0) out_cnt[q] = kk;
+}
+
+__global__ void gather_queries_kernel(const uint32_t* list, uint32_t n, const float* src, uint32_t dim, float* dst) {
+  const uint32_t i = blockIdx.x;
+  if (i >= n) return;
+  for (uint32_t t = threadIdx.x; t < dim; t += blockDim.x) dst[size_t(i) * dim + t] = src[size_t(list[i]) * dim + t];
+}
+__global__ void scatter_results_kernel(const uint32_t* list, uint32_t n, uint32_t k, const uint64_t* ids, const float* d,
+                                       const uint32_t* cnt, uint64_t* out_ids, float* out_d, uint32_t* out_cnt) {
+  const uint32_t i = blockIdx.x;
+  if (i >= n) return;
+  const uint32_t q = list[i];
+  for (uint32_t t = threadIdx.x; t < k; t += blockDim.x) {
+    out_ids[size_t(q) * k + t] = ids[size_t(i) * k + t];
+    out_d[size_t(q) * k + t] = d[size_t(i) * k + t];
+  }
+  if (threadIdx.x == 0) out_cnt[q] = cnt[i];
+}
+
+}  // namespace
+
+bool flat_tc_eligible(const sdb_index* ix, uint32_t k, bool filtered) {
+  if (getenv("SDB_FLAT_EXACT")) return false;
+  if (filtered || ix->quant_active()) return false;
+  if (ix->store_metric != SDB_METRIC_EUCLIDEAN && ix->store_metric != SDB_METRIC_DOT && ix->store_metric != SDB_METRIC_COSINE)
+    return false;
+  const uint32_t end_id = std::max<uint32_t>(2, ix->max_node_id + 1);
+  return end_id - 2 >= LEVEL0 * LEVEL_RATIO && k <= 75;
+}
+
+int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k, uint64_t* d_out_ids, float* d_out_dists,
+                   uint32_t* d_out_counts, cudaStream_t stream) {
+  const uint32_t dim = ix->p.dim, kp = (dim + TK - 1) / TK * TK;
+  const uint32_t first_id = 2, end_id = std::max<uint32_t>(2, ix->max_node_id + 1);
+  const uint32_t rows_pad = ix->rows + TN;  // the last point tile may read past end_id
+  const uint32_t B_pad = (B + TM - 1) / TM * TM;
+  const bool debug = getenv("SDB_DEBUG_FLAT") != nullptr;
+  int rc;
+  // ---- bf16 shadow of the store (rebuilt when the store changed)
+  if (ix->tc_epoch != ix->vec_epoch || ix->d_x16.n < size_t(rows_pad) * kp) {
+    if ((rc = ix->d_x16.ensure(size_t(rows_pad) * kp)) || (rc = ix->d_xn.ensure(rows_pad))) return rc;
+    to_bf16_kernel<<<(rows_pad + 7) / 8, 256, 0, stream>>>(ix->d_vec, ix->vec_pitch, dim, ix->rows, rows_pad,
+                                                          reinterpret_cast<__nv_bfloat16*>(ix->d_x16.p), kp, ix->d_xn.p);
+    ix->launches++;
+    SDB_CUDA(cudaGetLastError());
+    ix->tc_epoch = ix->vec_epoch;
+  }
+  if ((rc = ix->d_q16.ensure(size_t(B_pad) * kp)) || (rc = ix->d_qn.ensure(B_pad)) || (rc = ix->d_thr.ensure(B_pad)) ||
+      (rc = ix->d_cand.ensure(size_t(B) * CAND_CAP)) || (rc = ix->d_candcnt.ensure(size_t(B) * 2 + 8)) ||
+      (rc = ix->d_sample_ids.ensure(size_t(B) * k)) || (rc = ix->d_sample_d.ensure(size_t(B) * k)) ||
+      (rc = ix->d_sample_cnt.ensure(B)))
+    return rc;
+  uint32_t* d_cnt = ix->d_candcnt.p;            // [B] candidate counts
+  uint32_t* d_ovf_list = ix->d_candcnt.p + B;   // [B] overflowed queries
+  uint32_t* d_misc = ix->d_candcnt.p + 2 * size_t(B);  // [0] xmax bits, [1] overflow count
+  SDB_CUDA(cudaMemsetAsync(d_misc, 0, 8 * sizeof(uint32_t), stream));
+  to_bf16_kernel<<<(B_pad + 7) / 8, 256, 0, stream>>>(d_queries, dim, dim, B, B_pad, reinterpret_cast<__nv_bfloat16*>(ix->d_q16.p),
+                                                     kp, ix->d_qn.p);
+  xmax_kernel<<<(end_id - first_id + 255) / 256, 256, 0, stream>>>(ix->d_xn.p, ix->d_exists, first_id, end_id, d_misc);
+  ix->launches += 2;
+  SDB_CUDA(cudaGetLastError());
+  static bool attr_set = false;
+  if (!attr_set) {
+    SDB_CUDA(cudaFuncSetAttribute(tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM)));
+    attr_set = true;
+  }
+  // ---- level 0: exact scan of the first LEVEL0 points bounds every query's k-th distance
+  if ((rc = launch_flat_exact(ix, B, d_queries, k, nullptr, ix->d_sample_ids.p, ix->d_sample_d.p, ix->d_sample_cnt.p, stream,
+                              first_id, first_id + LEVEL0)))
+    return rc;
+  // ---- levels 1..: tensor-core pass over a 32x larger prefix, thresholds from the level before
+  const uint32_t npts = end_id - first_id;
+  const uint32_t qtiles = B_pad / TM;
+  const size_t qsmem = size_t((dim + 3) & ~3u) * sizeof(float);
+  uint64_t covered = LEVEL0;
+  while (covered < npts) {
+    covered = std::min<uint64_t>(npts, covered * LEVEL_RATIO);
+    const bool last = covered >= npts;
+    const uint32_t lvl_end = last ? end_id : first_id + uint32_t(covered);
+    // thresholds from the previous level's exact top-k
+    thresh_kernel<<<(B_pad + 127) / 128, 128, 0, stream>>>(ix->d_sample_d.p, ix->d_sample_cnt.p, k, ix->d_qn.p, d_misc,
+                                                           ix->store_metric, dim, B, B_pad, ix->d_thr.p);
+    SDB_CUDA(cudaMemsetAsync(d_cnt, 0, size_t(B) * sizeof(uint32_t), stream));
+    TcArgs ta{};
+    ta.q16 = reinterpret_cast<const __nv_bfloat16*>(ix->d_q16.p);
+    ta.x16 = reinterpret_cast<const __nv_bfloat16*>(ix->d_x16.p);
+    ta.xn = ix->d_xn.p; ta.thr = ix->d_thr.p; ta.exists = ix->d_exists;
+    ta.kp = kp; ta.first_id = first_id; ta.end_id = lvl_end;
+    ta.l2 = ix->store_metric == SDB_METRIC_EUCLIDEAN;
+    ta.cand = ix->d_cand.p; ta.cand_cnt = d_cnt; ta.B = B;
+    const uint32_t ntiles = (lvl_end - first_id + TN - 1) / TN;
+    // ~6 waves of CTAs (2 resident per SM) so the last wave's imbalance stays small
+    uint32_t ysplit = std::max<uint32_t>(1, (uint32_t(ix->sm_count) * 12 + qtiles - 1) / qtiles);
+    ysplit = std::min(ysplit, ntiles);
+    ta.tiles_per_cta = (ntiles + ysplit - 1) / ysplit;
+    ysplit = (ntiles + ta.tiles_per_cta - 1) / ta.tiles_per_cta;
+    tc_filter_kernel<<<dim3(qtiles, ysplit), TC_THREADS, TC_SMEM, stream>>>(ta);
+    SDB_CUDA(cudaGetLastError());
+    // exact re-score + top-k of the level; the last level writes the caller's outputs
+    uint64_t* o_ids = last ? d_out_ids : ix->d_sample_ids.p;
+    float* o_d = last ? d_out_dists : ix->d_sample_d.p;
+    uint32_t* o_c = last ? d_out_counts : ix->d_sample_cnt.p;
+    switch (ix->store_metric) {
+      case SDB_METRIC_EUCLIDEAN:
+        rescore_kernel<METRIC_EUCLIDEAN><<<B, 128, qsmem, stream>>>(ix->d_vec, ix->vec_pitch, dim, d_queries, ix->d_cand.p, d_cnt, k,
+                                                                    o_ids, o_d, o_c, d_ovf_list, d_misc + 1, last ? 1 : 0);
+        break;
+      case SDB_METRIC_DOT:
+        rescore_kernel<METRIC_DOT><<<B, 128, qsmem, stream>>>(ix->d_vec, ix->vec_pitch, dim, d_queries, ix->d_cand.p, d_cnt, k, o_ids,
+                                                              o_d, o_c, d_ovf_list, d_misc + 1, last ? 1 : 0);
+        break;
+      default:
+        rescore_kernel<METRIC_COSINE><<<B, 128, qsmem, stream>>>(ix->d_vec, ix->vec_pitch, dim, d_queries, ix->d_cand.p, d_cnt, k,
+                                                                 o_ids, o_d, o_c, d_ovf_list, d_misc + 1, last ? 1 : 0);
+        break;
+    }
+    ix->launches += 3;
+    SDB_CUDA(cudaGetLastError());
+    if (debug) {
+      std::vector<uint32_t> h(B);
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(h.data(), d_cnt, B * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+      uint64_t tot = 0;
+      uint32_t mx = 0;
+      for (uint32_t v : h) { tot += v; mx = std::max(mx, v); }
+      fprintf(stderr, "[sdb] flat tc level over %u points: %u queries, %.1f candidates/query (max %u, cap %u)\n",
+              lvl_end - first_id, B, double(tot) / B, mx, CAND_CAP);
+    }
+  }
+  // ---- queries whose candidate list overflowed on the last level: exact scan
+  uint32_t h_ovf = 0;
+  SDB_CUDA(cudaMemcpyAsync(&h_ovf, d_misc + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+  SDB_CUDA(cudaStreamSynchronize(stream));
+  if (debug) fprintf(stderr, "[sdb] flat tc: %u of %u queries overflowed -> exact scan\n", h_ovf, B);
+  if (h_ovf) {
+    DevBuf<float> d_q2, d_d2;
+    DevBuf<uint64_t> d_i2;
+    DevBuf<uint32_t> d_c2;
+    struct Rel { DevBuf<float>&a, &b; DevBuf<uint64_t>& c; DevBuf<uint32_t>& d; ~Rel() { a.release(); b.release(); c.release(); d.release(); } } rel{d_q2, d_d2, d_i2, d_c2};
+    if ((rc = d_q2.ensure(size_t(h_ovf) * dim)) || (rc = d_d2.ensure(size_t(h_ovf) * k)) || (rc = d_i2.ensure(size_t(h_ovf) * k)) ||
+        (rc = d_c2.ensure(h_ovf)))
+      return rc;
+    gather_queries_kernel<<<h_ovf, 128, 0, stream>>>(d_ovf_list, h_ovf, d_queries, dim, d_q2.p);
+    if ((rc = launch_flat_exact(ix, h_ovf, d_q2.p, k, nullptr, d_i2.p, d_d2.p, d_c2.p, stream, first_id, end_id))) return rc;
+    scatter_results_kernel<<<h_ovf, 128, 0, stream>>>(d_ovf_list, h_ovf, k, d_i2.p, d_d2.p, d_c2.p, d_out_ids, d_out_dists, d_out_counts);
+    ix->launches += 2;
+    SDB_CUDA(cudaGetLastError());
+    SDB_CUDA(cudaStreamSynchronize(stream));
+  }
+  return SDB_OK;
+}
+
+}  // namespace sdb

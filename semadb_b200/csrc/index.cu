@@ -90,11 +90,13 @@ int index_reserve_locked(sdb_index* ix, uint64_t max_node_id) {
   if ((rc = grow(&ix->d_dirty, o, n, ix->stream))) return rc;
   ix->h_exists.resize(n, 0);
   ix->rows = uint32_t(n);
+  ix->vec_epoch++;
   return SDB_OK;
 }
 
 int set_rows_device(sdb_index* ix, uint32_t n, const uint32_t* d_ids, const float* d_vecs, cudaStream_t stream) {
   if (n == 0) return SDB_OK;
+  ix->vec_epoch++;
   scatter_vectors_kernel<<<n, 128, 0, stream>>>(ix->d_vec, ix->vec_pitch, ix->d_exists, d_ids, d_vecs, ix->p.dim, n);
   ix->launches++;
   SDB_CUDA(cudaGetLastError());
@@ -258,6 +260,8 @@ void sdb_index_destroy(sdb_index* ix) {
   cudaFree(ix->d_exists);
   cudaFree(ix->d_dirty);
   ix->d_start_extra.release();
+  ix->d_x16.release(); ix->d_q16.release(); ix->d_xn.release(); ix->d_qn.release(); ix->d_thr.release();
+  ix->d_sample_d.release(); ix->d_cand.release(); ix->d_candcnt.release(); ix->d_sample_cnt.release(); ix->d_sample_ids.release();
   cudaFree(ix->d_bq_thr);
   cudaFree(ix->d_pq_centroids);
   cudaFree(ix->d_pq_cdist);
@@ -303,6 +307,7 @@ static int set_vectors_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, co
   size_t bytes = size_t(n) * ix->p.dim * sizeof(float);
   if ((rc = ix->d_tmpf.ensure(size_t(n) * ix->p.dim))) return rc;
   SDB_CUDA(cudaMemcpyAsync(ix->d_tmpf.p, vectors, bytes, cudaMemcpyHostToDevice, ix->stream));
+  ix->vec_epoch++;
   scatter_vectors_kernel<<<uint32_t(n), 128, 0, ix->stream>>>(ix->d_vec, ix->vec_pitch, ix->d_exists, ix->d_tmp32.p,
                                                               ix->d_tmpf.p, ix->p.dim, uint32_t(n));
   ix->launches++;
@@ -445,6 +450,7 @@ int sdb_index_delete(sdb_index* ix, uint64_t n, const uint64_t* ids) {
     uint32_t id = uint32_t(ids[i]);
     ix->h_exists[id] = 0;
     ix->count--;
+    ix->vec_epoch++;
     SDB_CUDA(cudaMemsetAsync(ix->d_exists + id, 0, 1, ix->stream));
     SDB_CUDA(cudaMemsetAsync(ix->d_adj + size_t(id) * ix->p.degree_bound, 0xFF, ix->p.degree_bound * 4, ix->stream));
     SDB_CUDA(cudaMemsetAsync(ix->d_deg + id, 0, 4, ix->stream));

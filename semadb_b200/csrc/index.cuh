@@ -127,6 +127,12 @@ struct sdb_index {
   sdb::DevBuf<float> d_tmpf;
   sdb::DevBuf<uint8_t> d_tmp8;
   sdb::PinBuf<uint8_t> h_stage;
+  // tensor-core flat scan (flat_tc.cu): bf16 shadow of the store + per-call scratch
+  uint64_t vec_epoch = 1, tc_epoch = 0;  // vec_epoch: bumped by every change to vec / exists
+  sdb::DevBuf<uint16_t> d_x16, d_q16;
+  sdb::DevBuf<float> d_xn, d_qn, d_thr, d_sample_d;
+  sdb::DevBuf<uint32_t> d_cand, d_candcnt, d_sample_cnt;
+  sdb::DevBuf<uint64_t> d_sample_ids;
   uint32_t last_B = 0;
   int vt_level = 0;                  // visited-table size step (search.cu)
   bool retry_check_pending = false;  // d_work holds the retry count of the last search
@@ -149,6 +155,12 @@ int launch_search(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k,
                   const uint32_t* d_filter_bits, cudaStream_t stream);
 int launch_flat(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k, const uint32_t* d_filter_bits,
                 uint64_t* d_out_ids, float* d_out_dists, uint32_t* d_out_counts, cudaStream_t stream);
+int launch_flat_exact(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k, const uint32_t* d_filter_bits,
+                      uint64_t* d_out_ids, float* d_out_dists, uint32_t* d_out_counts, cudaStream_t stream,
+                      uint32_t first_id, uint32_t end_id);
+bool flat_tc_eligible(const sdb_index* ix, uint32_t k, bool filtered);
+int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k, uint64_t* d_out_ids, float* d_out_dists,
+                   uint32_t* d_out_counts, cudaStream_t stream);
 int launch_encode_rows(sdb_index* ix, uint32_t n, const uint32_t* d_ids, cudaStream_t stream);
 int launch_adc_tables(sdb_index* ix, uint32_t B, const float* d_queries, float* d_out, cudaStream_t stream);
 int launch_merge(uint32_t S, uint32_t B, uint32_t k, const uint64_t* in_ids, const float* in_d, const uint32_t* in_c,

@@ -181,6 +181,7 @@ __global__ void pq_finalize_kernel(const float* vec, uint32_t pitch, const uint3
 }  // namespace
 
 int fit_locked(sdb_index* ix, uint64_t pq_first_row, int32_t* fitted) {
+  ix->vec_epoch++;  // k-means writes centroid means through aliased rows (kmeans.go:144)
   *fitted = 0;
   if (ix->p.quantizer == SDB_QUANT_NONE) return SDB_OK;  // plainStore.Fit (plain.go:72-74)
   cudaStream_t st = ix->stream;

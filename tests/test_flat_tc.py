@@ -1,0 +1,68 @@
+"""K5 on tensor cores (csrc/flat_tc.cu): bf16 GEMM candidate pass + exact re-score must return
+exactly what the exact CUDA-core scan (csrc/flat.cu) and the oracle's brute force return —
+ids and distances bit for bit, ties by ascending id (flat.go:99,117 with ascending-id order)."""
+import os
+
+import numpy as np
+import pytest
+
+from semadb_b200 import synth
+from semadb_b200.vamana import IndexFlat, IndexVectorFlatParameters
+
+pytestmark = pytest.mark.gpu
+
+
+def _both(g, Q, k):
+    os.environ.pop("SDB_FLAT_EXACT", None)
+    a = g.flat_search_batch(Q, k)
+    os.environ["SDB_FLAT_EXACT"] = "1"
+    try:
+        b = g.flat_search_batch(Q, k)
+    finally:
+        os.environ.pop("SDB_FLAT_EXACT", None)
+    return a, b
+
+
+@pytest.mark.parametrize("metric,dim,kind", [("euclidean", 128, "sift"), ("euclidean", 100, "gauss"), ("dot", 96, "gauss"),
+                                             ("cosine", 384, "unit"), ("euclidean", 2, "uniform")])
+def test_flat_tc_equals_exact_scan(metric, dim, kind):
+    n = 70_000  # above the tensor-core path's threshold (4 x 16384 sample points)
+    if kind == "sift":
+        X, Q = synth.sift_shaped(n, dim, 3), synth.sift_shaped(300, dim, 4, w_seed=3)
+    elif kind == "uniform":
+        X, Q = synth.uniform(n, dim, 1), synth.uniform(300, dim, 2)
+    else:
+        X = synth.latent_gaussian(n, dim, seed=dim, latent=8, normalize=(kind == "unit"))
+        Q = synth.latent_gaussian(300, dim, seed=dim + 1, w_seed=dim, latent=8, normalize=(kind == "unit"))
+    X[5000:5100] = X[:100]  # exact duplicates: ties must resolve by ascending id
+    g = IndexFlat(IndexVectorFlatParameters(dim, metric))
+    ids = np.arange(2, n + 2, dtype=np.uint64)
+    g.set_vectors(ids, X)
+    for k in (10, 1, 75):
+        (ti, td, tc), (ei, ed, ec) = _both(g, Q, k)
+        assert (tc == ec).all() and (ti == ei).all()
+        assert td.tobytes() == ed.tobytes()
+    # queries that are stored points: distance 0 (L2) and the duplicate with the lower id first
+    (ti, td, tc), (ei, ed, ec) = _both(g, X[:100], 10)
+    assert (ti == ei).all() and td.tobytes() == ed.tobytes()
+    if metric == "euclidean":
+        assert (ti[:, 0] == ids[:100]).all() and (ti[:, 1] == ids[5000:5100]).all() and (td[:, :2] == 0).all()
+    # deleted rows never come back
+    g.delete_rows(ids[:50])
+    (ti, td, tc), (ei, ed, ec) = _both(g, X[:100], 10)
+    assert (ti == ei).all() and td.tobytes() == ed.tobytes() and not np.isin(ti, ids[:50]).any()
+
+
+def test_flat_tc_matches_oracle():
+    from oracle import oraclelib as O
+    n, dim = 70_000, 64
+    X = synth.latent_gaussian(n, dim, seed=9, latent=8)
+    Q = synth.latent_gaussian(100, dim, seed=10, w_seed=9, latent=8)
+    oix = O.OracleIndex(dim, "euclidean")
+    ids = np.arange(2, n + 2, dtype=np.uint32)
+    oix.set_vectors(ids, X)
+    gt = oix.flat_search(Q, k=10, threads=8)
+    g = IndexFlat(IndexVectorFlatParameters(dim, "euclidean"))
+    g.set_vectors(ids.astype(np.uint64), X)
+    fi, fd, fc = g.flat_search_batch(Q, 10)
+    assert (fi == gt["ids"].astype(np.uint64)).all() and fd.tobytes() == gt["dists"].tobytes()
