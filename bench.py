@@ -144,6 +144,7 @@ def run_reference(args):
         return
     from oracle import oraclelib as O
     threads = O.hw_threads()
+    args.graph = "oracle"
     X, Q, start = make_data(args.n, 0, args.queries)
     oix, ids, tb = build_oracle_index(X, start, threads)
     log(f"[reference] graph built in {tb:.1f}s with {threads} threads")
@@ -173,7 +174,7 @@ def workload_config(args, world):
             "points_per_gpu": args.n, "dim": DIM, "batch": args.queries, "k": K, "search_size": L,
             "degree_bound": R, "graph": args.graph,
             "l2_policy": "dataset (vectors+adjacency 768 MB/GPU) >> 126 MB L2, no explicit flush",
-            "parallelism": f"shard-per-gpu x{world}, queries broadcast, NCCL all-gather + merge" if world > 1
+            "parallelism": f"shard-per-gpu x{world}, queries broadcast, per-GPU top-k exchanged and merged on every GPU" if world > 1
             else "single shard"}
 
 
@@ -197,7 +198,8 @@ def main():
     ap.add_argument("--n", type=int, default=1_000_000, help="points per GPU shard")
     ap.add_argument("--queries", type=int, default=10_000)
     ap.add_argument("--ref-queries", type=int, default=10_000)
-    ap.add_argument("--graph", default="oracle", choices=["oracle", "gpu"])
+    ap.add_argument("--graph", default="auto", choices=["auto", "oracle", "gpu"])
+    ap.add_argument("--exchange", default=os.environ.get("SDB_EXCHANGE", "auto"), choices=["auto", "p2p", "nccl"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--recall-queries", type=int, default=2000)
     args = ap.parse_args()
@@ -229,6 +231,12 @@ def main():
     ids = np.arange(2, args.n + 2, dtype=np.uint64)
     oix = None
     ncpu = os.cpu_count() or 1
+    if args.graph == "auto":
+        # C2 asks for the reference-built graph. Its CPU build needs ~28 s x 16 threads per 1M-point
+        # shard; when N ranks share the host cores and fewer than 4 threads are left per rank the
+        # shards are built by the CUDA batched insert (K8) instead — same search QPS within 1 %
+        # (profiles/r01_ab_k1.txt), and stated in config.graph.
+        args.graph = "oracle" if ncpu // world >= 4 else "gpu"
     if args.graph == "oracle":
         oix, _, tb = build_oracle_index(X, start, max(1, ncpu // world))
         log(f"[rank {rank}] reference-built graph: {tb:.1f}s on {max(1, ncpu // world)} threads")
@@ -241,10 +249,10 @@ def main():
         gix.insert_batch(ids, X)
         log(f"[rank {rank}] GPU-built graph (K8): {time.time() - t0:.1f}s")
 
-    from semadb_b200.sharded import SHARD_SHIFT, ShardedSearcher, exchange_topk, pack_global_ids
+    from semadb_b200.sharded import ShardedSearcher
     B = args.queries
     d_q = torch.from_numpy(Q).to(dev)  # the broadcast query batch, resident on every rank
-    searcher = ShardedSearcher(gix, rank, world)
+    searcher = ShardedSearcher(gix, rank, world, exchange=args.exchange)
     stream = torch.cuda.current_stream()
     launches = [0]
     result = [None]
@@ -252,7 +260,8 @@ def main():
     def step():
         before = gix.launch_count
         result[0] = searcher.search_batch_device(d_q, K, L)  # K1 (+ all-gather + K6 at N>1)
-        launches[0] += gix.launch_count - before + (1 if world > 1 else 0)
+        # + K6 merge, + the peer barrier kernel when the exchange is fused (NCCL's kernels are not ours)
+        launches[0] += gix.launch_count - before + (0 if world == 1 else 2 if searcher.exchange != "nccl" else 1)
 
     def barrier():
         if world > 1:
@@ -299,26 +308,23 @@ def main():
     h_c = torch.zeros((B,), dtype=torch.int32).pin_memory()
     import ctypes as C
 
-    m_ids = torch.zeros((B, K), dtype=torch.int64, device=dev)
-    m_d = torch.zeros((B, K), dtype=torch.float32, device=dev)
-    m_c = torch.zeros((B,), dtype=torch.int32, device=dev)
+    d_q2 = torch.empty_like(d_q)
 
     def e2e_step():
-        _capi.check(lib.sdb_search_batch(gix._h, B, C.cast(h_q.data_ptr(), _capi.f32p), K, L, None, 0,
-                                         C.cast(h_ids.data_ptr(), _capi.u64p), C.cast(h_d.data_ptr(), _capi.f32p),
-                                         C.cast(h_c.data_ptr(), _capi.u32p)))
-        if world > 1:
-            # The host fan-in of per-shard lists is the Go cluster layer's job
-            # (cluster/actions.go:357-376); here the lists go back to the device and through
-            # the same all-gather + merge (K6), and the merged list returns to the host.
-            g_ids, g_d, g_c = exchange_topk(pack_global_ids(h_ids.to(dev, non_blocking=True), rank),
-                                            h_d.to(dev, non_blocking=True), h_c.to(dev, non_blocking=True))
-            _capi.check(lib.sdb_merge_topk_device(local_rank, world, B, K, g_ids.data_ptr(), g_d.data_ptr(),
-                                                  g_c.data_ptr(), m_ids.data_ptr(), m_d.data_ptr(), m_c.data_ptr(),
-                                                  stream.cuda_stream))
-            h_ids.copy_(m_ids)
-            h_d.copy_(m_d)
-            h_c.copy_(m_c)
+        if world == 1:
+            _capi.check(lib.sdb_search_batch(gix._h, B, C.cast(h_q.data_ptr(), _capi.f32p), K, L, None, 0,
+                                             C.cast(h_ids.data_ptr(), _capi.u64p), C.cast(h_d.data_ptr(), _capi.f32p),
+                                             C.cast(h_c.data_ptr(), _capi.u32p)))
+            return
+        # N > 1: every rank receives the broadcast query batch in host memory (the Go cluster layer
+        # fans requests out to shards, cluster/actions.go:316-351), copies it in, runs the sharded
+        # search (K1 with the fused peer gather, barrier, K6) and reads the merged lists back.
+        d_q2.copy_(h_q, non_blocking=True)
+        r_ids, r_d, r_c = searcher.search_batch_device(d_q2, K, L)
+        h_ids.copy_(r_ids, non_blocking=True)
+        h_d.copy_(r_d, non_blocking=True)
+        h_c.copy_(r_c, non_blocking=True)
+        torch.cuda.synchronize()
 
     for _ in range(2):
         e2e_step()
@@ -374,6 +380,10 @@ def main():
         achieved = bytes_q * B / (kern_ms * 1e-3) / 1e9
         peak, peak_kind = measured_peaks()
         cfg = workload_config(args, world)
+        if world > 1:
+            cfg.update(exchange="fused peer stores over NVLink + flag barrier (sdb_search_batch_gather_device)"
+                       if searcher.exchange != "nccl" else "NCCL all-gather per result tensor",
+                       peer_barrier_timed_out=(searcher._peer.barrier_failed() if searcher._peer is not None else None))
         cfg.update(user_qps=B / (ms_step * 1e-3), recall_at_10=recall, mean_hops=float(hops.mean()),
                    mean_ndist=float(ndist.mean()), bytes_per_query=bytes_q, parity=parity,
                    host_cores=os.cpu_count())

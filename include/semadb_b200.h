@@ -221,6 +221,33 @@ int sdb_merge_topk(int32_t device, uint32_t S, uint32_t B, uint32_t k, const uin
 int sdb_merge_topk_device(int32_t device, uint32_t S, uint32_t B, uint32_t k, const uint64_t* d_in_ids,
                           const float* d_in_dists, const uint32_t* d_in_counts, uint64_t* d_out_ids,
                           float* d_out_dists, uint32_t* d_out_counts, void* stream);
+/* ---- cross-shard exchange fused into the search kernel (replaces the fan-in of
+ * ClusterNode.SearchPoints, cluster/actions.go:316-376, without a separate collective).
+ * Every GPU owns a gather buffer ids[S][B][k] / dists[S][B][k] / counts[S][B] that its peers
+ * can write: peer-mapped device pointers (cudaDeviceEnablePeerAccess inside one process, CUDA
+ * IPC / symmetric memory between processes). sdb_search_batch_gather_device runs the beam
+ * search on this GPU's shard and its epilogue stores each query's top-k, node ids tagged as
+ * (shard << 40 | id), into slot [shard][query] of EVERY peer's buffer over NVLink.
+ * sdb_peer_barrier_device then publishes `epoch` to every peer's flag word [me] and waits for
+ * every peer's epoch in its own words (flags: >= 2*SDB_MAX_PEERS u32 per GPU, zeroed once;
+ * epochs must grow by 1 per step), after which sdb_merge_topk_device reads the local gather
+ * buffer. Callers alternate two gather buffers (epoch parity) so a fast peer's next step
+ * cannot overwrite a buffer still being merged. */
+#define SDB_MAX_PEERS 16
+typedef struct sdb_peer_gather {
+  uint32_t n_peers;          /* destination GPUs, this one included (= S with one shard per GPU) */
+  uint32_t shard;            /* shard index of this search: slot [shard] of every buffer, tag of its ids */
+  uint32_t per_shard_limit;  /* sdb_shard_limit(k, S, ...); 0 = k */
+  uint32_t reserved;
+  uint64_t* ids[SDB_MAX_PEERS];     /* peer p's ids    [S][B][k] */
+  float* dists[SDB_MAX_PEERS];      /* peer p's dists  [S][B][k] */
+  uint32_t* counts[SDB_MAX_PEERS];  /* peer p's counts [S][B] */
+} sdb_peer_gather;
+int sdb_search_batch_gather_device(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k, uint32_t search_size,
+                                   uint64_t* d_out_ids, float* d_out_dists, uint32_t* d_out_counts,
+                                   const sdb_peer_gather* peers, void* stream);
+int sdb_peer_barrier_device(int32_t device, uint32_t n_peers, uint32_t me, uint32_t* const* peer_flags, uint32_t epoch,
+                            void* stream);
 /* Per-shard request limit (cluster/actions.go:291-299). Pure host arithmetic. */
 uint32_t sdb_shard_limit(uint32_t limit, uint32_t n_shards, uint32_t max_search_limit);
 

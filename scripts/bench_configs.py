@@ -14,6 +14,7 @@ usage: python scripts/bench_configs.py c1,c3,c4,c5b,c5a [--n-c3 N] [--n-c4 N] [-
 """
 import argparse
 import json
+import os
 import sys
 import time
 from pathlib import Path
@@ -57,6 +58,11 @@ def time_search(g, Q, steps=10, warmup=3):
     e1.record(st)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    if os.environ.get("SDB_PROFILE"):  # ncu --profile-from-start off: capture exactly one search
+        torch.cuda.profiler.start()
+        g.search_batch_device(d_q, K, L, ids, d, c, st.cuda_stream)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     hops, nd = g.last_search_stats(B)
     return ms, hops, nd, ids.cpu().numpy()
 
@@ -67,7 +73,7 @@ def recall(g, Q, got, nq=1000):
     return float(np.mean([len(set(got[b].tolist()) & set(fi[b].tolist())) / K for b in range(nq)]))
 
 
-def report(name, workload, g, Q, row_bytes, build_s, extra=None):
+def report(name, workload, g, Q, row_bytes, build_s, extra=None, want_ids=False):
     ms, hops, nd, got = time_search(g, Q)
     B = len(Q)
     bytes_q = float(nd.mean()) * row_bytes + float(hops.mean()) * R * 4
@@ -79,6 +85,7 @@ def report(name, workload, g, Q, row_bytes, build_s, extra=None):
     if extra:
         out.update(extra)
     print(json.dumps(out), flush=True)
+    return got if want_ids else None
 
 
 def c1():
@@ -115,8 +122,15 @@ def c4(n):
     g.insert_batch(ids[10000:], X[10000:])
     build = time.time() - t
     log(f"c4: fit={fitted} in {t_fit:.2f}s, build {build:.1f}s")
-    report("c4", f"C4-shaped: {n} x 768 latent-64, dot, PQ M=96 K=256 (ADC search, codes 96 B/row), 10k queries", g, Q, M,
-           build, {"pq_fit_s": t_fit, "note": "bytes/query counts code rows + adjacency; ADC tables (98 KB/query) are read through L2"})
+    wl = f"C4-shaped: {n} x 768 latent-64, dot, PQ M=96 K=256 (ADC search, codes 96 B/row), 10k queries"
+    a = report("c4", wl, g, Q, M, build,
+               {"pq_fit_s": t_fit, "adc_table": "shared memory (bulk-copied once per query, 2 query-warps per SM)",
+                "note": "bytes/query counts code rows + adjacency, not the 98 KB/query table copy"}, want_ids=True)
+    os.environ["SDB_ADC_GLOBAL"] = "1"
+    b = report("c4_global_table", wl, g, Q, M, build, {"adc_table": "global memory, read through L1/L2 (12 query-warps per SM)"},
+               want_ids=True)
+    os.environ.pop("SDB_ADC_GLOBAL")
+    log(f"c4: shared-memory table ids identical to global-table ids: {bool((a == b).all())}")
 
 
 def c5b(n):
@@ -134,6 +148,14 @@ def c5b(n):
         log(f"c5b: {s + m} points in, {t_build:.1f}s of insert")
     Q = synth.planted_bits(10_000, dim, seed=1234567, proto_seed=7)
     report("c5b", f"C5b-shaped: {n} x 1024-bit planted clusters, hamming, 10k queries, GPU-built graph", g, Q, dim // 8, t_build)
+    for slots in [int(x) for x in os.environ.get("SDB_SWEEP_SLOTS", "").split(",") if x]:
+        os.environ["SDB_VT_SLOTS"] = str(slots)
+        os.environ["SDB_DEBUG_RETRY"] = "1"
+        ms, hops, nd, _ = time_search(g, Q, steps=5, warmup=2)
+        os.environ.pop("SDB_DEBUG_RETRY")
+        ms, hops, nd, _ = time_search(g, Q, steps=10, warmup=2)
+        log(f"c5b sweep: visited slots {slots}: {len(Q) / ms * 1e3:.0f} QPS, {ms:.3f} ms/batch")
+    os.environ.pop("SDB_VT_SLOTS", None)
 
 
 def c5a():

@@ -36,6 +36,17 @@ class SdbParams(C.Structure):
     ]
 
 
+MAX_PEERS = 16
+
+
+class SdbPeerGather(C.Structure):
+    """sdb_peer_gather (include/semadb_b200.h): peer-mapped gather buffers of every GPU."""
+    _fields_ = [
+        ("n_peers", C.c_uint32), ("shard", C.c_uint32), ("per_shard_limit", C.c_uint32), ("reserved", C.c_uint32),
+        ("ids", C.c_void_p * MAX_PEERS), ("dists", C.c_void_p * MAX_PEERS), ("counts", C.c_void_p * MAX_PEERS),
+    ]
+
+
 f32p = C.POINTER(C.c_float)
 u64p = C.POINTER(C.c_uint64)
 u32p = C.POINTER(C.c_uint32)
@@ -62,6 +73,10 @@ _SIGS = {
     "sdb_search_batch": (C.c_int, [H, C.c_uint32, f32p, C.c_uint32, C.c_uint32, u64p, C.c_uint64, u64p, f32p, u32p]),
     "sdb_search_batch_device": (C.c_int, [H, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p]),
+    "sdb_search_batch_gather_device": (C.c_int, [H, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p, C.POINTER(SdbPeerGather), C.c_void_p]),
+    "sdb_peer_barrier_device": (C.c_int, [C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.c_uint32,
+                                          C.c_void_p]),
     "sdb_last_search_stats": (C.c_int, [H, C.c_uint32, u32p, u32p]),
     "sdb_launch_count": (C.c_uint64, [H]),
     "sdb_search_visited": (C.c_int, [H, C.c_uint32, f32p, C.c_uint32, C.c_uint32, u64p, f32p, u32p]),

@@ -230,6 +230,31 @@ int launch_merge(uint32_t S, uint32_t B, uint32_t k, const uint64_t* in_ids, con
   return SDB_OK;
 }
 
+// Cross-GPU barrier on peer-mapped flag words (NVLink): thread p publishes `epoch` into peer
+// p's flags[me] with a system-scope release (the peer stores of the kernels before it on this
+// stream are ordered first), then waits until peer p's epoch has arrived in flags_me[p].
+// Epochs only grow, so the words are never reset. A peer that never arrives (a crashed rank)
+// is given ~20 s, then the kernel records the failure in flags_me[SDB_MAX_PEERS + p] and returns.
+struct PeerFlags { uint32_t* f[SDB_MAX_PEERS]; };
+__global__ void peer_barrier_kernel(PeerFlags pf, uint32_t n, uint32_t me, uint32_t epoch) {
+  const uint32_t p = threadIdx.x;
+  if (p >= n) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf.f[p] + me), "r"(epoch) : "memory");
+  const uint32_t* mine = pf.f[me] + p;
+  const long long t0 = clock64();
+  uint32_t v;
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if (int32_t(v - epoch) >= 0) break;
+    if (clock64() - t0 > 40000000000LL) {
+      pf.f[me][SDB_MAX_PEERS + p] = epoch;
+      break;
+    }
+    __nanosleep(200);
+  }
+}
+
 }  // namespace sdb
 
 using namespace sdb;
@@ -412,6 +437,22 @@ int sdb_merge_topk(int32_t device, uint32_t S, uint32_t B, uint32_t k, const uin
   SDB_CUDA(cudaMemcpy(out_ids, oi.p, size_t(B) * k * 8, cudaMemcpyDeviceToHost));
   SDB_CUDA(cudaMemcpy(out_dists, od.p, size_t(B) * k * 4, cudaMemcpyDeviceToHost));
   SDB_CUDA(cudaMemcpy(out_counts, oc.p, size_t(B) * 4, cudaMemcpyDeviceToHost));
+  return SDB_OK;
+}
+
+int sdb_peer_barrier_device(int32_t device, uint32_t n_peers, uint32_t me, uint32_t* const* peer_flags, uint32_t epoch,
+                            void* stream) {
+  if (!peer_flags || n_peers == 0 || n_peers > SDB_MAX_PEERS || me >= n_peers)
+    return fail(SDB_ERR_INVALID, "peer barrier: n_peers must be 1..16 and me < n_peers");
+  int rc = set_device_checked(device);
+  if (rc) return rc;
+  PeerFlags pf{};
+  for (uint32_t p = 0; p < n_peers; ++p) {
+    if (!peer_flags[p]) return fail(SDB_ERR_INVALID, "peer barrier: null flag pointer");
+    pf.f[p] = peer_flags[p];
+  }
+  peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pf, n_peers, me, epoch);
+  SDB_CUDA(cudaGetLastError());
   return SDB_OK;
 }
 

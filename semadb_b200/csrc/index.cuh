@@ -76,8 +76,11 @@ struct PinBuf {  // grow-only pinned host staging
 //   adj   [rows][R]           u32, unused slots = 0xFFFFFFFF
 //   deg   [rows]              u32
 //   exists[rows]              u8
+namespace sdb { struct PeerGather; }
+
 struct sdb_index {
   sdb_params p{};
+  const sdb::PeerGather* gather = nullptr;  // set for the duration of sdb_search_batch_gather_device
   int device = 0;
   cudaStream_t stream = nullptr;
   int sm_count = 148;

@@ -16,9 +16,10 @@ int launch_variant_x(sdb_index* ix, const SearchArgs& a, cudaStream_t stream) {
   auto kern = beam_search_kernel<KIND, METRIC, TRIPS, SETS, LEGACY, MERGE_MIN, VT, FILTER, RETRY, MINB, XTRA>;
   // FloatEvalGrouped keeps short queries (<= 4 float4 per lane) in registers: no shared copy
   constexpr bool QREG = (KIND == EVAL_FLOAT_FIXED) && !LEGACY && TRIPS <= 4;
-  const uint32_t qfloats = (KIND == EVAL_ADC || QREG) ? 0 : (a.dim + 3) / 4 * 4;
+  const uint32_t qfloats = (KIND == EVAL_ADC || KIND == EVAL_ADC_SMEM || QREG) ? 0 : (a.dim + 3) / 4 * 4;
   const uint32_t qwords = (KIND == EVAL_BITS) ? a.bits_pitch : 0;
-  const size_t smem = warp_smem_bytes<VT, FILTER>(qfloats, qwords, a.vt_slots);
+  const uint32_t table_floats = (KIND == EVAL_ADC_SMEM) ? a.pqM * a.pqK : 0;
+  const size_t smem = warp_smem_bytes<VT, FILTER>(qfloats, qwords, a.vt_slots, table_floats);
   static thread_local int cached_dev = -1;
   static thread_local size_t cached_smem = 0;
   static thread_local int ctas_per_sm = 0;
@@ -73,7 +74,7 @@ int launch_with_retry(sdb_index* ix, SearchArgs a, cudaStream_t stream) {
   if (rc) return rc;
   // second pass over queries whose visited set overflowed (normally none): u32 table, 32768 slots
   a.work_counter = a.work_counter + 2;
-  constexpr int RK = (KIND == EVAL_FLOAT_FIXED) ? EVAL_FLOAT_GENERIC : KIND;
+  constexpr int RK = (KIND == EVAL_FLOAT_FIXED) ? EVAL_FLOAT_GENERIC : (KIND == EVAL_ADC_SMEM) ? EVAL_ADC : KIND;
   constexpr int RT = (KIND == EVAL_BITS) ? TRIPS : 1;  // bit rows: chunks per row must still cover the row
   if (getenv("SDB_DEBUG_RETRY")) {
     uint32_t h[2] = {0, 0};
@@ -174,6 +175,7 @@ int launch_search(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k,
     const char* e = getenv("SDB_K1_FLAGS");
     a.flags = e ? uint32_t(atoi(e)) : 0u;
   }
+  if (ix->gather) a.pg = *ix->gather;
   a.work_counter = ix->d_work.p;
   a.retry_count = ix->d_work.p + 1;
   a.retry_list = ix->d_work.p + 4;
@@ -202,6 +204,18 @@ int launch_search(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k,
     if ((rc = ix->d_adc.ensure(size_t(B) * ix->pqM * ix->pqK))) return rc;
     if ((rc = launch_adc_tables(ix, B, d_queries, ix->d_adc.p, stream))) return rc;
     a.adc = ix->d_adc.p;
+    // ADC table in shared memory when at least two query-warps per SM can hold theirs (C4:
+    // 96 x 256 x 4 B = 96 KB => exactly two); otherwise the table is read through L1/L2
+    const size_t fixed = warp_smem_bytes<VisitedCompactN, false>(0, 0, 0, ix->pqM * ix->pqK) + 1024;
+    const size_t room = ix->smem_per_sm / 2 > fixed ? (ix->smem_per_sm / 2 - fixed) / 2 : 0;  // 16-bit visited slots
+    if (!filtered && room >= 4096 && !getenv("SDB_ADC_GLOBAL")) {
+      if (a.vt_slots > room) a.vt_slots = uint32_t(room) / 8 * 8;
+      const uint32_t nch = (ix->pqM + 15) / 16;
+      if (nch <= 2) return launch_with_retry<EVAL_ADC_SMEM, 0, 2, 1, false, 2, false, 12>(ix, a, stream);
+      if (nch <= 4) return launch_with_retry<EVAL_ADC_SMEM, 0, 4, 1, false, 2, false, 12>(ix, a, stream);
+      if (nch <= 6) return launch_with_retry<EVAL_ADC_SMEM, 0, 6, 1, false, 2, false, 12>(ix, a, stream);
+      return launch_with_retry<EVAL_ADC_SMEM, 0, 8, 1, false, 2, false, 12>(ix, a, stream);
+    }
     return filtered ? launch_with_retry<EVAL_ADC, 0, 1, 1, false, 0, true, 1>(ix, a, stream)
                     : launch_with_retry<EVAL_ADC, 0, 1, 1, false, 2, false, 12>(ix, a, stream);
   }
@@ -214,3 +228,35 @@ int launch_search(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k,
 }
 
 }  // namespace sdb
+
+using namespace sdb;
+
+extern "C" int sdb_search_batch_gather_device(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k,
+                                              uint32_t search_size, uint64_t* d_out_ids, float* d_out_dists,
+                                              uint32_t* d_out_counts, const sdb_peer_gather* pg, void* stream) {
+  if (!ix || !pg) return fail(SDB_ERR_INVALID, "null argument");
+  if (B == 0) return SDB_OK;
+  if (!d_queries || !d_out_ids || !d_out_dists || !d_out_counts) return fail(SDB_ERR_INVALID, "null argument");
+  if (pg->n_peers == 0 || pg->n_peers > SDB_MAX_PEERS || pg->shard >= (1u << 24))
+    return fail(SDB_ERR_INVALID, "peer gather: n_peers must be 1..16");
+  if (k == 0 || search_size < k) return fail(SDB_ERR_INVALID, "searchSize must be greater than or equal to k");
+  PeerGather g{};
+  g.n = pg->n_peers;
+  g.shard = pg->shard;
+  g.limit = pg->per_shard_limit == 0 || pg->per_shard_limit > k ? k : pg->per_shard_limit;
+  g.tag = uint64_t(pg->shard) << 40;
+  for (uint32_t p = 0; p < pg->n_peers; ++p) {
+    if (!pg->ids[p] || !pg->dists[p] || !pg->counts[p]) return fail(SDB_ERR_INVALID, "peer gather: null peer buffer");
+    g.ids[p] = pg->ids[p];
+    g.dists[p] = pg->dists[p];
+    g.counts[p] = pg->counts[p];
+  }
+  std::lock_guard<std::mutex> lk(ix->mu);
+  SDB_CUDA(cudaSetDevice(ix->device));
+  ix->gather = &g;
+  int rc = launch_search(ix, B, d_queries, k, search_size, d_out_ids, d_out_dists, d_out_counts, nullptr, nullptr, nullptr, 0,
+                         nullptr, 0, nullptr, static_cast<cudaStream_t>(stream));
+  ix->gather = nullptr;
+  return rc;
+}
+

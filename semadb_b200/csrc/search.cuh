@@ -27,7 +27,23 @@ constexpr uint32_t EXPANDED_FLAG = 0x80000000u;
 constexpr uint32_t ID_MASK = 0x7FFFFFFFu;
 constexpr uint32_t COUNT_OVERFLOW = 0xFFFFFFFFu;  // out_counts marker: visited table overflowed
 
+// Cross-shard exchange fused into the epilogue (replaces the fan-in of cluster/actions.go:357-376
+// + one all-gather per result tensor): a query-warp stores its shard's top-k straight into every
+// peer GPU's gather buffer over NVLink — peer-mapped pointers, slot [shard][query], ids tagged
+// with the shard index — so that after one cross-GPU barrier every GPU holds all S lists.
+constexpr int MAX_PEERS = 16;
+struct PeerGather {
+  uint32_t n;        // peers (0 = off), including this GPU
+  uint32_t shard;    // this GPU's shard index
+  uint32_t limit;    // per-shard result limit (actions.go:291-299), <= k
+  uint64_t tag;      // shard << 40, or'ed into the node ids
+  uint64_t* ids[MAX_PEERS];     // peer p's [S][B][k]
+  float* dists[MAX_PEERS];      // peer p's [S][B][k]
+  uint32_t* counts[MAX_PEERS];  // peer p's [S][B]
+};
+
 struct SearchArgs {
+  PeerGather pg;
   // store
   const float* vec;        // [rows][vec_pitch]
   uint32_t vec_pitch;      // floats per row (multiple of 4)
@@ -773,13 +789,140 @@ struct AdcEval {
   }
 };
 
-enum EvalKind : int { EVAL_FLOAT_FIXED = 0, EVAL_FLOAT_GENERIC = 1, EVAL_BITS = 2, EVAL_ADC = 3 };
+// PQ codes with the query's ADC table resident in shared memory (the table is what every
+// distance touches: M lookups per candidate, 288 k per query at C4 — through L1/L2 that was the
+// bound). The table is pulled from global memory once per query by bulk async copies
+// (cp.async.bulk, completion on an mbarrier). One lane owns two candidates (adjacency slots
+// lane, lane+32): their code rows (NCH 16-byte chunks each) are all in flight before the first
+// lookup, and the two sums advance as independent sequential f32 chains in sub-vector order
+// (product.go:271-275), so the result is the same float the global-table path and the reference
+// produce.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+
+template <int NCH>
+struct AdcEvalSmem {
+  const float* table;  // [M*K] for this query (shared memory)
+  // pull the query's table into shared memory; returns after it has landed
+  __device__ __forceinline__ void load_table(float* tab, const float* src, uint32_t nfloats, uint64_t* bar, uint32_t& phase,
+                                             int lane) {
+    table = tab;
+    // earlier generic-proxy reads of the old table are ordered before the async-proxy writes
+    __syncwarp();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if ((nfloats & 3u) == 0) {
+      const uint32_t bytes = nfloats * 4;
+      constexpr uint32_t CHUNK = 8192;
+      if (lane == 0) mbar_expect_tx(bar, bytes);
+      __syncwarp();
+      for (uint32_t off = uint32_t(lane) * CHUNK; off < bytes; off += 32 * CHUNK)
+        bulk_g2s(reinterpret_cast<unsigned char*>(tab) + off, reinterpret_cast<const unsigned char*>(src) + off,
+                 min(CHUNK, bytes - off), bar);
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+    } else {  // table rows not 16-byte sized: plain copy
+      for (uint32_t i = lane; i < nfloats; i += 32) tab[i] = __ldg(src + i);
+    }
+    __syncwarp();
+  }
+  // TWO: the hop staged more than 32 candidates, lanes run a second chain for slot lane+32.
+  // K256: K = 256 (the reference's maximum and the C4 shape): the table offset of sub-vector i
+  // is the compile-time constant i*1024 B, so a lookup is shift/mask + LDS + FADD.
+  template <bool TWO, bool K256>
+  __device__ __forceinline__ void chains(const SearchArgs& a, const uint32_t* cid, float* cdist, int n, int lane) {
+    const bool h0 = lane < n, h1 = TWO && lane + 32 < n;
+    const uint8_t* r0 = a.codes + size_t(h0 ? cid[lane] : cid[0]) * a.codes_pitch;
+    const uint8_t* r1 = a.codes + size_t(h1 ? cid[lane + 32] : cid[0]) * a.codes_pitch;
+    const uint32_t nch = (a.pqM + 15) >> 4;
+    const uint32_t K = K256 ? 256u : a.pqK;
+    float d0 = 0.0f, d1 = 0.0f;
+    for (uint32_t cb = 0; cb < nch; cb += NCH) {
+      uint4 v0[NCH], v1[NCH];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const bool in = cb + c < nch;  // warp-uniform
+        v0[c] = in ? ldg_u4_stream(r0 + (cb + c) * 16) : make_uint4(0, 0, 0, 0);
+        if (TWO) v1[c] = in ? ldg_u4_stream(r1 + (cb + c) * 16) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const uint32_t w0[4] = {v0[c].x, v0[c].y, v0[c].z, v0[c].w};
+        const uint32_t w1[4] = {TWO ? v1[c].x : 0u, TWO ? v1[c].y : 0u, TWO ? v1[c].z : 0u, TWO ? v1[c].w : 0u};
+        const uint32_t ibase = (cb + c) * 16;
+        if (ibase + 16 <= a.pqM) {
+          const float* t = table + ibase * K;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t c0 = (w0[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+            d0 = __fadd_rn(d0, t[j * K + c0]);
+            if (TWO) {
+              const uint32_t c1 = (w1[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+              d1 = __fadd_rn(d1, t[j * K + c1]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t i = ibase + j;
+            if (i < a.pqM) {
+              const uint32_t c0 = (w0[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+              d0 = __fadd_rn(d0, table[i * K + c0]);
+              if (TWO) {
+                const uint32_t c1 = (w1[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                d1 = __fadd_rn(d1, table[i * K + c1]);
+              }
+            }
+          }
+        }
+      }
+    }
+    if (h0) cdist[lane] = d0;
+    if (h1) cdist[lane + 32] = d1;
+    __syncwarp();
+  }
+  __device__ __forceinline__ void eval(const SearchArgs& a, const uint32_t* cid, float* cdist, int n, int lane) {
+    if (a.pqK == 256) {
+      if (n > 32) chains<true, true>(a, cid, cdist, n, lane);
+      else chains<false, true>(a, cid, cdist, n, lane);
+    } else {
+      if (n > 32) chains<true, false>(a, cid, cdist, n, lane);
+      else chains<false, false>(a, cid, cdist, n, lane);
+    }
+  }
+};
+
+enum EvalKind : int { EVAL_FLOAT_FIXED = 0, EVAL_FLOAT_GENERIC = 1, EVAL_BITS = 2, EVAL_ADC = 3, EVAL_ADC_SMEM = 4 };
 
 // ---- shared-memory layout per query-warp ------------------------------------------------
 template <class VT, bool FILTER>
-__host__ __device__ constexpr size_t warp_smem_bytes(uint32_t qfloats, uint32_t qwords, uint32_t vt_slots) {
+__host__ __device__ constexpr size_t warp_smem_bytes(uint32_t qfloats, uint32_t qwords, uint32_t vt_slots,
+                                                     uint32_t table_floats = 0) {
   return ((VT::bytes(vt_slots) + 15) / 16) * 16 + LIST_SLOTS * 8 + (FILTER ? LIST_SLOTS * 8 : 0) + CAND_SLOTS * 8 +
-         ((size_t(qfloats) * 4 + 15) / 16) * 16 + ((size_t(qwords) * 8 + 15) / 16) * 16;
+         ((size_t(qfloats) * 4 + 15) / 16) * 16 + ((size_t(qwords) * 8 + 15) / 16) * 16 +
+         (table_floats ? 16 + ((size_t(table_floats) * 4 + 15) / 16) * 16 : 0);
 }
 
 // ---- the kernel ---------------------------------------------------------------------
@@ -816,6 +959,15 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
   float* qs = reinterpret_cast<float*>(base);
   base += ((size_t(qfloats) * 4 + 15) / 16) * 16;
   uint64_t* qbits = reinterpret_cast<uint64_t*>(base);
+  base += ((size_t(qwords) * 8 + 15) / 16) * 16;
+  uint64_t* tbar = reinterpret_cast<uint64_t*>(base);  // EVAL_ADC_SMEM: mbarrier + the query's ADC table
+  float* tab = reinterpret_cast<float*>(base + 16);
+  uint32_t tphase = 0;
+  if (KIND == EVAL_ADC_SMEM) {
+    if (lane == 0) mbar_init(tbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+  }
   const uint32_t lt = (1u << lane) - 1;
 
   for (;;) {
@@ -829,7 +981,7 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
 
     // ---- per-query setup
     vt.clear(lane);
-    if (KIND != EVAL_ADC) {
+    if (KIND != EVAL_ADC && KIND != EVAL_ADC_SMEM) {
       const float* qg = a.queries + size_t(qi) * a.dim;
       for (uint32_t i = lane; i < qfloats; i += 32) qs[i] = i < a.dim ? __ldg(qg + i) : 0.0f;
     }
@@ -841,6 +993,9 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
     constexpr bool BITS = (KIND == EVAL_BITS);
     BitEval<(BITS ? METRIC : METRIC_HAMMING), (BITS ? TRIPS : 1), (BITS ? SETS : 1)> ev_bits;
     AdcEval ev_adc;
+    AdcEvalSmem<(KIND == EVAL_ADC_SMEM ? TRIPS : 1)> ev_adcs;
+    if (KIND == EVAL_ADC_SMEM)
+      ev_adcs.load_table(tab, a.adc + size_t(qi) * a.pqM * a.pqK, a.pqM * a.pqK, tbar, tphase, lane);
     if (KIND == EVAL_FLOAT_FIXED) ev_fixed.load_query(qs, a.queries + size_t(qi) * a.dim, lane);
     if (KIND == EVAL_FLOAT_GENERIC) ev_gen.load_query(qs, lane);
     if (KIND == EVAL_BITS) ev_bits.encode_query(a, qs, qbits, lane);
@@ -850,6 +1005,7 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
       if (KIND == EVAL_FLOAT_GENERIC) ev_gen.eval(a, cid, cdist, n, lane);
       if (KIND == EVAL_BITS) ev_bits.eval(a, cid, cdist, n, lane);
       if (KIND == EVAL_ADC) ev_adc.eval(a, cid, cdist, n, lane);
+      if (KIND == EVAL_ADC_SMEM) ev_adcs.eval(a, cid, cdist, n, lane);
     };
 
     list.len = 0;
@@ -991,7 +1147,7 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
         if (nvisited > vt.limit() || vt.failed) { overflow = true; break; }
         if (nnew > 0) {
           evaluate(nnew);
-          constexpr bool TIEFIX = (KIND == EVAL_BITS || KIND == EVAL_ADC);  // integer-valued / coarse distances
+          constexpr bool TIEFIX = (KIND == EVAL_BITS || KIND == EVAL_ADC || KIND == EVAL_ADC_SMEM);  // integer-valued / coarse distances
           if (MERGE_MIN == 0 || !list.template merge<TIEFIX>(cid, cdist, nnew, lane, lt, MERGE_MIN)) add_with_limit(list, nnew);
         }
         if (!XTRA || e != START_ID || x0 >= a.n_start_extra) break;
@@ -1041,8 +1197,16 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
         uint32_t b = __ballot_sync(SDB_FULL, keep);
         int r = written + __popc(b & lt);
         if (keep && r < int(a.k)) {
+          const float dd = out.dist[p];
           a.out_ids[size_t(qi) * a.k + r] = uint64_t(nid);
-          a.out_dists[size_t(qi) * a.k + r] = out.dist[p];
+          a.out_dists[size_t(qi) * a.k + r] = dd;
+          if (a.pg.n) {
+            const size_t o = (size_t(a.pg.shard) * a.B + qi) * a.k + r;
+            for (uint32_t s = 0; s < a.pg.n; ++s) {
+              a.pg.ids[s][o] = uint64_t(nid) | a.pg.tag;
+              a.pg.dists[s][o] = dd;
+            }
+          }
         }
         written += __popc(b);
       }
@@ -1050,7 +1214,15 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
       for (int r = cnt + lane; r < int(a.k); r += 32) {
         a.out_ids[size_t(qi) * a.k + r] = 0;
         a.out_dists[size_t(qi) * a.k + r] = __int_as_float(0x7f800000);
+        if (a.pg.n) {
+          const size_t o = (size_t(a.pg.shard) * a.B + qi) * a.k + r;
+          for (uint32_t s = 0; s < a.pg.n; ++s) {
+            a.pg.ids[s][o] = 0;
+            a.pg.dists[s][o] = __int_as_float(0x7f800000);
+          }
+        }
       }
+      if (a.pg.n && lane < int(a.pg.n)) a.pg.counts[lane][size_t(a.pg.shard) * a.B + qi] = uint32_t(min(cnt, int(a.pg.limit)));
       if (lane == 0) {
         a.out_counts[qi] = uint32_t(cnt);
         a.out_hops[qi] = hops;

@@ -17,6 +17,7 @@ tensors, the collective). The merge runs through the C ABI.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Optional
 
 import numpy as np
@@ -67,13 +68,73 @@ def exchange_topk(ids, dists, counts, group=None):
     return g_ids, g_d, g_c
 
 
-class ShardedSearcher:
-    """One rank's view of a sharded collection."""
+class PeerGatherBuffers:
+    """Peer-mapped gather buffers for the exchange fused into the search kernel
+    (sdb_search_batch_gather_device): one symmetric allocation per rank, laid out as
+    [flag words | buffer 0 | buffer 1], each buffer = ids [S][B][k] u64, dists [S][B][k] f32,
+    counts [S][B] u32. torch symmetric memory only allocates and maps the pages across the
+    processes (the job cudaDeviceEnablePeerAccess does inside one Go process); the stores, the
+    barrier and the merge are this library's kernels."""
 
-    def __init__(self, index, rank: Optional[int] = None, world: Optional[int] = None, group=None):
+    FLAG_BYTES = 256  # 2 * SDB_MAX_PEERS u32 words, padded
+
+    def __init__(self, rank: int, world: int, B: int, k: int, device, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.world, self.B, self.k = rank, world, B, k
+        ids_b, d_b, c_b = world * B * k * 8, world * B * k * 4, world * B * 4
+        self.buf_bytes = (ids_b + d_b + c_b + 255) // 256 * 256
+        self.off_d, self.off_c = ids_b, ids_b + d_b
+        total = self.FLAG_BYTES + 2 * self.buf_bytes
+        grp = group if group is not None else dist.group.WORLD
+        self.t = symm.empty(total, dtype=torch.uint8, device=device)
+        self.t.zero_()
+        torch.cuda.synchronize(device)
+        self.hdl = symm.rendezvous(self.t, grp)
+        self.peer_base = [int(p) for p in self.hdl.buffer_ptrs]
+        if len(self.peer_base) != world:
+            raise RuntimeError("symmetric memory rendezvous returned the wrong number of peers")
+        dist.barrier(grp)  # every rank has zeroed its flags before anyone signals
+        self.epoch = 0
+        self.device = device
+        self._flags = (C.c_void_p * world)(*self.peer_base)
+        self._pg = []
+        for par in range(2):
+            pg = _capi.SdbPeerGather()
+            pg.n_peers, pg.shard, pg.per_shard_limit = world, rank, 0
+            for p, base in enumerate(self.peer_base):
+                b = base + self.FLAG_BYTES + par * self.buf_bytes
+                pg.ids[p], pg.dists[p], pg.counts[p] = b, b + self.off_d, b + self.off_c
+            self._pg.append(pg)
+
+    def local(self, parity: int):
+        b = self.peer_base[self.rank] + self.FLAG_BYTES + parity * self.buf_bytes
+        return b, b + self.off_d, b + self.off_c
+
+    def barrier_failed(self) -> bool:
+        """True if a peer_barrier_kernel on this rank ever timed out (a peer never arrived)."""
+        import torch
+        w = self.t[:self.FLAG_BYTES].view(torch.int32)[_capi.MAX_PEERS:2 * _capi.MAX_PEERS]
+        return bool((w != 0).any().item())
+
+
+class ShardedSearcher:
+    """One rank's view of a sharded collection.
+
+    exchange = "p2p": the search kernel's epilogue stores each query's top-k into every peer
+    GPU's gather buffer over NVLink, one cross-GPU flag barrier, merge (K6) — no collective
+    call on the data path. exchange = "nccl": one all-gather per result tensor, then K6 (also
+    the path the gloo CPU tests drive). "auto" = p2p on CUDA, falling back to nccl with a
+    warning on stderr if symmetric memory cannot be set up on this box."""
+
+    def __init__(self, index, rank: Optional[int] = None, world: Optional[int] = None, group=None,
+                 exchange: str = "auto"):
         import torch.distributed as dist
         self.index = index
         self.group = group
+        self.exchange = exchange
+        self._peer = None
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
         self._bufs = None
@@ -101,6 +162,32 @@ class ShardedSearcher:
         # the reference asks each shard for min(k, floor(k/S*1.42+10)) results; the local
         # search still fills k slots and the merge reads only the first `per_shard`
         per_shard = shard_limit(k, self.world, max_search_limit)
+        if self.world > 1 and self.exchange in ("auto", "p2p") and d_queries.is_cuda:
+            if self._peer is None or (self._peer.B, self._peer.k) != (B, k):
+                try:
+                    self._peer = PeerGatherBuffers(self.rank, self.world, B, k, dev, self.group)
+                except Exception as e:  # noqa: BLE001
+                    if self.exchange == "p2p":
+                        raise
+                    import sys
+                    print(f"[semadb_b200] peer-mapped gather buffers unavailable ({e!r}); using the NCCL all-gather",
+                          file=sys.stderr, flush=True)
+                    self.exchange = "nccl"
+        if self.world > 1 and self._peer is not None and self.exchange != "nccl":
+            pb = self._peer
+            pb.epoch += 1
+            par = pb.epoch & 1
+            pg = pb._pg[par]
+            pg.per_shard_limit = per_shard
+            lib = _capi.lib()
+            _capi.check(lib.sdb_search_batch_gather_device(self.index._h, B, d_queries.data_ptr(), k, search_size,
+                                                           l_ids.data_ptr(), l_d.data_ptr(), l_c.data_ptr(),
+                                                           C.byref(pg), stream))
+            _capi.check(lib.sdb_peer_barrier_device(dev.index or 0, self.world, self.rank, pb._flags, pb.epoch, stream))
+            g_i, g_dd, g_cc = pb.local(par)
+            _capi.check(lib.sdb_merge_topk_device(dev.index or 0, self.world, B, k, g_i, g_dd, g_cc, m_ids.data_ptr(),
+                                                  m_d.data_ptr(), m_c.data_ptr(), stream))
+            return m_ids, m_d, m_c
         self.index.search_batch_device(d_queries, k, search_size, l_ids, l_d, l_c, stream)
         if per_shard < k:
             l_c.clamp_(max=per_shard)
