@@ -147,6 +147,12 @@ int sdb_search_visited(sdb_index* ix, uint32_t B, const float* queries, uint32_t
 int sdb_flat_search_batch(sdb_index* ix, uint32_t B, const float* queries, uint32_t k, const uint64_t* filter_ids,
                           uint64_t n_filter, uint64_t* out_ids, float* out_dists, uint32_t* out_counts);
 
+/* Diagnostics of the most recent sdb_flat_search_batch on this handle: path = 0 exact CUDA-core
+ * scan, 1 tensor-core candidate pass (mma.sync), 2 tensor-core candidate pass (tcgen05 + TMA);
+ * candidates = (query, point) pairs the last candidate level kept for exact re-scoring, summed
+ * over the batch; overflowed = queries that fell back to the exact scan. */
+int sdb_flat_last_stats(sdb_index* ix, int32_t* path, uint64_t* candidates, uint32_t* overflowed);
+
 /* ---- insert: replaces IndexVamana.InsertUpdateDelete's insert branch (vamana.go:136-201,
  * insert.go:16-68): greedySearch + robustPrune + back-edges for n new points, batched. */
 int sdb_insert_batch(sdb_index* ix, uint64_t n, const uint64_t* ids, const float* vectors);

@@ -81,6 +81,7 @@ _SIGS = {
     "sdb_launch_count": (C.c_uint64, [H]),
     "sdb_search_visited": (C.c_int, [H, C.c_uint32, f32p, C.c_uint32, C.c_uint32, u64p, f32p, u32p]),
     "sdb_flat_search_batch": (C.c_int, [H, C.c_uint32, f32p, C.c_uint32, u64p, C.c_uint64, u64p, f32p, u32p]),
+    "sdb_flat_last_stats": (C.c_int, [H, i32p, u64p, u32p]),
     "sdb_insert_batch": (C.c_int, [H, C.c_uint64, u64p, f32p]),
     "sdb_insert_config": (C.c_int, [H, C.c_uint32, C.c_uint32, C.c_uint32]),
     "sdb_insert_update_delete": (C.c_int, [H, C.c_uint64, u64p, f32p, u8p]),

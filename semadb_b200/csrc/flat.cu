@@ -209,6 +209,7 @@ int launch_flat(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k, c
   // bit-identical to the exact scan below
   if (flat_tc_eligible(ix, k, d_filter_bits != nullptr))
     return launch_flat_tc(ix, B, d_queries, k, d_out_ids, d_out_dists, d_out_counts, stream);
+  ix->flat_last_path = 0;
   return launch_flat_exact(ix, B, d_queries, k, d_filter_bits, d_out_ids, d_out_dists, d_out_counts, stream, 2,
                            std::max<uint32_t>(2, ix->max_node_id + 1));
 }

@@ -20,6 +20,8 @@
 // GEMM: mma.sync.m16n8k16 bf16 (CTA tile 128 queries x 128 points, 8 warps of 64x32, K chunks
 // of 64 double-buffered with cp.async, ldmatrix fragments). The accumulators stay in registers,
 // which is what the threshold filter wants: it looks at every score once and keeps ~0.05 %.
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <cuda_bf16.h>
 
 #include <algorithm>
@@ -115,6 +117,7 @@ struct TcArgs {
   int l2;                     // squared-L2: score = xn - 2 acc; else score = -acc
   uint32_t* cand; uint32_t* cand_cnt;  // [B][CAND_CAP], [B]
   uint32_t B;
+  uint32_t rows_alloc;        // rows of x16 / xn (tcgen05 path: point tiles may reach past end_id)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 2) tc_filter_kernel(TcArgs a) {
@@ -212,6 +215,325 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_filter_kernel(TcArgs a) {
     }
     __syncthreads();  // s_xn is rewritten by the next tile
   }
+}
+
+
+// ================================================================================================
+// tcgen05 form of the candidate pass (the default for dim <= 512): the same GEMM + threshold
+// filter as tc_filter_kernel, on the 5th-generation tensor cores.
+//   * warp 0 (one lane): TMA producer. The CTA's 128-query tile of q16 is loaded once
+//     (kp/64 boxes of 128 rows x 128 B, SWIZZLE_128B); point tiles of 256 rows stream through a
+//     ring of 32 KB stages (one 64-wide K block per stage), cp.async.bulk.tensor + mbarrier.
+//   * warp 1 (one lane): issues tcgen05.mma.kind::f16 M128 x N256 x K16 (bf16 in, f32 out),
+//     A and B straight from shared memory through matrix descriptors; the accumulator of a point
+//     tile is 256 TMEM columns, two tiles (512 columns = all of TMEM) are in flight so the
+//     filter of tile t overlaps the MMAs of tile t+1. tcgen05.commit frees a stage / publishes
+//     an accumulator.
+//   * warps 2..9: epilogue. A thread owns one query (TMEM lane) and half of the tile's columns:
+//     tcgen05.ld 32 columns at a time, score = xn - 2 acc (or -acc), compare with the query's
+//     threshold, append the rare survivors to the query's candidate list.
+// One CTA per SM (192 KB of shared memory, all 512 TMEM columns).
+constexpr int T5_M = 128, T5_N = 256, T5_KB = 64;
+constexpr int T5_THREADS = 320;
+constexpr int T5_EPI_THREADS = 256;
+constexpr uint32_t T5_QBLK_BYTES = T5_M * 128;  // one K block of the query tile
+constexpr uint32_t T5_XBLK_BYTES = T5_N * 128;  // one K block of a point tile = one stage
+constexpr uint32_t T5_IDESC = (1u << 4)                      // D format f32
+                              | (1u << 7) | (1u << 10)        // A, B format bf16; both K-major
+                              | (uint32_t(T5_N >> 3) << 17)   // N
+                              | (uint32_t(T5_M >> 4) << 24);  // M
+
+__device__ __forceinline__ void t5_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void t5_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void t5_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded wait: a protocol error traps instead of hanging the GPU
+__device__ __forceinline__ void t5_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void t5_tma_load_2d(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+// K-major operand, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1
+__device__ __forceinline__ uint64_t t5_smem_desc(uint32_t addr) {
+  return uint64_t((addr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
+         (uint64_t(2) << 61);
+}
+__device__ __forceinline__ void t5_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(T5_IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void t5_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void t5_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void t5_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void t5_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void t5_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+struct T5Smem {  // offsets from the 1024-byte aligned base
+  uint32_t q, x, xn, bars, tmem_slot, total;
+  int stages;
+};
+__host__ __device__ inline T5Smem t5_layout(uint32_t nkb, int stages) {
+  T5Smem L;
+  L.stages = stages;
+  L.q = 0;
+  L.x = nkb * T5_QBLK_BYTES;
+  L.xn = L.x + uint32_t(stages) * T5_XBLK_BYTES;
+  L.bars = L.xn + 2 * T5_N * 4;
+  L.tmem_slot = L.bars + (2 * uint32_t(stages) + 5) * 8;
+  L.total = L.tmem_slot + 16;
+  return L;
+}
+
+__global__ void __launch_bounds__(T5_THREADS, 1)
+tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, TcArgs a, int stages) {
+  extern __shared__ unsigned char t5_raw[];
+  const uint32_t raw = smem_u32(t5_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  unsigned char* gbase = t5_raw + (base - raw);
+  const uint32_t nkb = a.kp / T5_KB;
+  const T5Smem L = t5_layout(nkb, stages);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // barriers: full[s], empty[s], q_full, tmem_full[2], tmem_empty[2]
+  auto bar_full = [&](int s) { return base + L.bars + uint32_t(s) * 8; };
+  auto bar_empty = [&](int s) { return base + L.bars + uint32_t(stages + s) * 8; };
+  const uint32_t bar_q = base + L.bars + uint32_t(2 * stages) * 8;
+  auto bar_tfull = [&](int i) { return base + L.bars + uint32_t(2 * stages + 1 + i) * 8; };
+  auto bar_tempty = [&](int i) { return base + L.bars + uint32_t(2 * stages + 3 + i) * 8; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + L.tmem_slot);
+  float* s_xn = reinterpret_cast<float*>(gbase + L.xn);
+
+  const uint32_t q0 = blockIdx.x * T5_M;
+  const uint32_t tile_begin = blockIdx.y * a.tiles_per_cta;
+  const uint32_t ntiles_total = (a.end_id - a.first_id + T5_N - 1) / T5_N;
+  const uint32_t tile_end = min(tile_begin + a.tiles_per_cta, ntiles_total);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      t5_mbar_init(bar_full(s), 1);
+      t5_mbar_init(bar_empty(s), 1);
+    }
+    t5_mbar_init(bar_q, 1);
+    for (int i = 0; i < 2; ++i) {
+      t5_mbar_init(bar_tfull(i), 1);
+      t5_mbar_init(bar_tempty(i), T5_EPI_THREADS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: all 512 columns (two 256-column accumulators)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + L.tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  t5_fence_before();
+  __syncthreads();
+  t5_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      t5_mbar_expect_tx(bar_q, nkb * T5_QBLK_BYTES);
+      for (uint32_t kb = 0; kb < nkb; ++kb)
+        t5_tma_load_2d(base + L.q + kb * T5_QBLK_BYTES, &map_q, int32_t(kb * T5_KB), int32_t(q0), bar_q);
+      int s = 0;
+      uint32_t ph = 0;
+      for (uint32_t t = tile_begin; t < tile_end; ++t) {
+        const int32_t p0 = int32_t(a.first_id + t * T5_N);
+        for (uint32_t kb = 0; kb < nkb; ++kb) {
+          t5_mbar_wait(bar_empty(s), ph ^ 1u);
+          t5_mbar_expect_tx(bar_full(s), T5_XBLK_BYTES);
+          t5_tma_load_2d(base + L.x + uint32_t(s) * T5_XBLK_BYTES, &map_x, int32_t(kb * T5_KB), p0, bar_full(s));
+          if (++s == stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      t5_mbar_wait(bar_q, 0);
+      t5_fence_after();
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t it = 0;
+      for (uint32_t t = tile_begin; t < tile_end; ++t, ++it) {
+        const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
+        t5_mbar_wait(bar_tempty(acc), aph ^ 1u);  // the epilogue has drained this accumulator
+        t5_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * T5_N;
+        for (uint32_t kb = 0; kb < nkb; ++kb) {
+          t5_mbar_wait(bar_full(s), ph);
+          t5_fence_after();
+          const uint64_t adesc = t5_smem_desc(base + L.q + kb * T5_QBLK_BYTES);
+          const uint64_t bdesc = t5_smem_desc(base + L.x + uint32_t(s) * T5_XBLK_BYTES);
+#pragma unroll
+          for (uint32_t k = 0; k < T5_KB / 16; ++k)  // +32 B per K step inside the swizzle row
+            t5_mma(d_tmem, adesc + 2 * k, bdesc + 2 * k, (kb | k) != 0 ? 1u : 0u);
+          t5_commit(bar_empty(s));  // stage free once these MMAs have read it
+          if (++s == stages) { s = 0; ph ^= 1u; }
+        }
+        t5_commit(bar_tfull(acc));  // accumulator complete
+      }
+    }
+  } else {
+    // ===== epilogue: threshold filter =====
+    const int e = warp - 2;                 // 0..7
+    const int quad = warp & 3;              // TMEM lanes 32*quad .. 32*quad+31 are this warp's
+    const int half = e >> 2;                // columns [128*half, 128*half + 128)
+    const int etid = threadIdx.x - 64;      // 0..255: xn staging slot
+    const uint32_t q = q0 + uint32_t(quad) * 32 + lane;
+    const float thr = a.thr[q];             // B_pad rows; padding rows hold -inf
+    const bool q_ok = q < a.B;
+    const float scale = a.l2 ? -2.0f : -1.0f;
+    uint32_t it = 0;
+    float xn_next = 0.0f;
+    if (tile_begin < tile_end && a.l2) {
+      const uint32_t pid = a.first_id + tile_begin * T5_N + etid;
+      xn_next = pid < a.rows_alloc ? a.xn[pid] : 0.0f;
+    }
+    for (uint32_t t = tile_begin; t < tile_end; ++t, ++it) {
+      const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
+      const uint32_t p0 = a.first_id + t * T5_N;
+      s_xn[acc * T5_N + etid] = xn_next;
+      if (t + 1 < tile_end && a.l2) {
+        const uint32_t pid = p0 + T5_N + etid;
+        xn_next = pid < a.rows_alloc ? a.xn[pid] : 0.0f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(T5_EPI_THREADS) : "memory");
+      t5_mbar_wait(bar_tfull(acc), aph);
+      t5_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * T5_N + uint32_t(half) * 128;
+      const float* xs = s_xn + acc * T5_N + half * 128;
+      uint32_t v[2][32];
+      t5_ld32(taddr, v[0]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        t5_wait_ld();
+        if (c + 1 < 4) t5_ld32(taddr + uint32_t(c + 1) * 32, v[(c + 1) & 1]);
+        uint32_t mask = 0;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 x4 = *reinterpret_cast<const float4*>(xs + c * 32 + j4 * 4);
+          const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const float score = fmaf(scale, __uint_as_float(v[c & 1][j4 * 4 + jj]), xv[jj]);
+            if (score <= thr) mask |= 1u << (j4 * 4 + jj);
+          }
+        }
+        while (mask) {
+          const int j = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const uint32_t pid = p0 + uint32_t(half) * 128 + uint32_t(c) * 32 + uint32_t(j);
+          if (q_ok && pid < a.end_id && a.exists[pid]) {
+            const uint32_t slot = atomicAdd(&a.cand_cnt[q], 1u);
+            if (slot < CAND_CAP) a.cand[size_t(q) * CAND_CAP + slot] = pid;
+          }
+        }
+      }
+      t5_fence_before();
+      __syncwarp();
+      if (lane == 0) t5_mbar_arrive(bar_tempty(acc));
+    }
+  }
+  t5_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    t5_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 t5_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// [rows][kp] bf16 row-major -> boxes of box_rows x 64 elements, 128-byte swizzle
+int t5_make_map(CUtensorMap* map, const void* ptr, uint32_t rows, uint32_t kp, uint32_t box_rows) {
+  auto fn = t5_encode_fn();
+  if (!fn) return fail(SDB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[2] = {kp, rows};
+  cuuint64_t gstride[1] = {cuuint64_t(kp) * 2};
+  cuuint32_t box[2] = {T5_KB, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SDB_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(int(r)));
+  return SDB_OK;
+}
+
+bool t5_eligible(uint32_t kp) { return kp <= 512 && !getenv("SDB_FLAT_MMA_SYNC"); }
+
+int launch_tc5_filter(sdb_index* ix, TcArgs ta, uint32_t B_pad, cudaStream_t stream) {
+  const uint32_t nkb = ta.kp / T5_KB;
+  int stages = int((220u * 1024u - nkb * T5_QBLK_BYTES) / T5_XBLK_BYTES);
+  if (stages > 6) stages = 6;
+  const T5Smem L = t5_layout(nkb, stages);
+  const size_t smem = size_t(L.total) + 1024;
+  CUtensorMap mq, mx;
+  int rc;
+  if ((rc = t5_make_map(&mq, ta.q16, B_pad, ta.kp, T5_M)) || (rc = t5_make_map(&mx, ta.x16, ta.rows_alloc, ta.kp, T5_N))) return rc;
+  static size_t attr_smem = 0;
+  if (attr_smem < smem) {
+    SDB_CUDA(cudaFuncSetAttribute(tc5_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    attr_smem = smem;
+  }
+  const uint32_t qtiles = B_pad / T5_M;
+  const uint32_t ntiles = (ta.end_id - ta.first_id + T5_N - 1) / T5_N;
+  // one CTA per SM; a few waves so that the last one's imbalance stays small
+  uint32_t ysplit = std::max<uint32_t>(1, (uint32_t(ix->sm_count) * 4 + qtiles - 1) / qtiles);
+  ysplit = std::min(ysplit, ntiles);
+  ta.tiles_per_cta = (ntiles + ysplit - 1) / ysplit;
+  ysplit = (ntiles + ta.tiles_per_cta - 1) / ta.tiles_per_cta;
+  tc5_filter_kernel<<<dim3(qtiles, ysplit), T5_THREADS, smem, stream>>>(mq, mx, ta, stages);
+  SDB_CUDA(cudaGetLastError());
+  return SDB_OK;
 }
 
 // Exact re-score of one query's candidates + top-k by (distance asc, id asc). One CTA per query.
@@ -330,7 +652,7 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
                    uint32_t* d_out_counts, cudaStream_t stream) {
   const uint32_t dim = ix->p.dim, kp = (dim + TK - 1) / TK * TK;
   const uint32_t first_id = 2, end_id = std::max<uint32_t>(2, ix->max_node_id + 1);
-  const uint32_t rows_pad = ix->rows + TN;  // the last point tile may read past end_id
+  const uint32_t rows_pad = ix->rows + T5_N;  // the last point tile may read past end_id
   const uint32_t B_pad = (B + TM - 1) / TM * TM;
   const bool debug = getenv("SDB_DEBUG_FLAT") != nullptr;
   int rc;
@@ -392,7 +714,12 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
     ysplit = std::min(ysplit, ntiles);
     ta.tiles_per_cta = (ntiles + ysplit - 1) / ysplit;
     ysplit = (ntiles + ta.tiles_per_cta - 1) / ta.tiles_per_cta;
-    tc_filter_kernel<<<dim3(qtiles, ysplit), TC_THREADS, TC_SMEM, stream>>>(ta);
+    ta.rows_alloc = rows_pad;
+    if (t5_eligible(kp)) {
+      if ((rc = launch_tc5_filter(ix, ta, B_pad, stream))) return rc;
+    } else {
+      tc_filter_kernel<<<dim3(qtiles, ysplit), TC_THREADS, TC_SMEM, stream>>>(ta);
+    }
     SDB_CUDA(cudaGetLastError());
     // exact re-score + top-k of the level; the last level writes the caller's outputs
     uint64_t* o_ids = last ? d_out_ids : ix->d_sample_ids.p;
@@ -428,7 +755,18 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
   // ---- queries whose candidate list overflowed on the last level: exact scan
   uint32_t h_ovf = 0;
   SDB_CUDA(cudaMemcpyAsync(&h_ovf, d_misc + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-  SDB_CUDA(cudaStreamSynchronize(stream));
+  {
+    // diagnostic (sdb_flat_last_stats): candidates the last level kept, summed over the batch
+    static thread_local std::vector<uint32_t> h_cnt;
+    h_cnt.resize(B);
+    SDB_CUDA(cudaMemcpyAsync(h_cnt.data(), d_cnt, size_t(B) * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    SDB_CUDA(cudaStreamSynchronize(stream));
+    uint64_t tot = 0;
+    for (uint32_t v : h_cnt) tot += v;
+    ix->flat_last_candidates = tot;
+    ix->flat_last_overflow = h_ovf;
+    ix->flat_last_path = t5_eligible(kp) ? 2 : 1;
+  }
   if (debug) fprintf(stderr, "[sdb] flat tc: %u of %u queries overflowed -> exact scan\n", h_ovf, B);
   if (h_ovf) {
     DevBuf<float> d_q2, d_d2;
@@ -449,3 +787,12 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
 }
 
 }  // namespace sdb
+
+extern "C" int sdb_flat_last_stats(sdb_index* ix, int32_t* path, uint64_t* candidates, uint32_t* overflowed) {
+  if (!ix) return sdb::fail(SDB_ERR_INVALID, "null index");
+  std::lock_guard<std::mutex> g(ix->mu);
+  if (path) *path = ix->flat_last_path;
+  if (candidates) *candidates = ix->flat_last_candidates;
+  if (overflowed) *overflowed = ix->flat_last_overflow;
+  return SDB_OK;
+}

@@ -131,6 +131,9 @@ struct sdb_index {
   sdb::DevBuf<uint8_t> d_tmp8;
   sdb::PinBuf<uint8_t> h_stage;
   // tensor-core flat scan (flat_tc.cu): bf16 shadow of the store + per-call scratch
+  uint64_t flat_last_candidates = 0;  // tensor-core flat scan: candidates kept by the last level, all queries
+  uint32_t flat_last_overflow = 0;    // ... and queries that fell back to the exact scan
+  int flat_last_path = 0;             // 0 exact scan, 1 mma.sync candidate pass, 2 tcgen05 candidate pass
   uint64_t vec_epoch = 1, tc_epoch = 0;  // vec_epoch: bumped by every change to vec / exists
   sdb::DevBuf<uint16_t> d_x16, d_q16;
   sdb::DevBuf<float> d_xn, d_qn, d_thr, d_sample_d;

@@ -339,6 +339,14 @@ class _DeviceIndex:
                                               _ptr(cnt, u32p)))
         return ids, d, cnt
 
+    def flat_last_stats(self):
+        """(path, candidates, overflowed) of the last flat_search_batch: path 0 = exact CUDA-core
+        scan, 1 = mma.sync candidate pass, 2 = tcgen05 + TMA candidate pass."""
+        import ctypes as C
+        path, cand, ovf = C.c_int32(0), C.c_uint64(0), C.c_uint32(0)
+        check(self._lib.sdb_flat_last_stats(self._h, C.byref(path), C.byref(cand), C.byref(ovf)))
+        return path.value, cand.value, ovf.value
+
     def insert_batch(self, ids, vectors):
         ids, v = _u64(ids), _f32(vectors)
         if v.shape != (len(ids), self.dim):

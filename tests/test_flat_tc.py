@@ -66,3 +66,30 @@ def test_flat_tc_matches_oracle():
     g.set_vectors(ids.astype(np.uint64), X)
     fi, fd, fc = g.flat_search_batch(Q, 10)
     assert (fi == gt["ids"].astype(np.uint64)).all() and fd.tobytes() == gt["dists"].tobytes()
+
+
+@pytest.mark.parametrize("metric,dim", [("euclidean", 128), ("dot", 96), ("euclidean", 200), ("cosine", 384)])
+def test_tcgen05_candidate_pass_matches_mma_sync_pass(metric, dim):
+    """The tcgen05 + TMA candidate pass (default for dim <= 512) and the mma.sync pass compute the
+    same bf16 GEMM: the candidate sets they keep must have (almost) the same size — only the fp32
+    accumulation order differs — nobody may fall back to the exact scan, and the results are
+    bit-identical. A wrong descriptor / swizzle would either flood the candidate lists (overflow
+    -> exact scan) or starve them (wrong results); both are caught here."""
+    n = 70_000
+    X = synth.latent_gaussian(n, dim, seed=dim, latent=8, normalize=(metric == "cosine"))
+    Q = synth.latent_gaussian(500, dim, seed=dim + 1, w_seed=dim, latent=8, normalize=(metric == "cosine"))
+    g = IndexFlat(IndexVectorFlatParameters(dim, metric))
+    g.set_vectors(np.arange(2, n + 2, dtype=np.uint64), X)
+    os.environ.pop("SDB_FLAT_MMA_SYNC", None)
+    a = g.flat_search_batch(Q, 10)
+    pa, ca, oa = g.flat_last_stats()
+    os.environ["SDB_FLAT_MMA_SYNC"] = "1"
+    try:
+        b = g.flat_search_batch(Q, 10)
+        pb, cb, ob = g.flat_last_stats()
+    finally:
+        os.environ.pop("SDB_FLAT_MMA_SYNC", None)
+    assert pa == 2 and pb == 1
+    assert oa == 0 and ob == 0
+    assert ca >= 10 * len(Q) and abs(ca - cb) <= 0.01 * cb + 5
+    assert (a[0] == b[0]).all() and a[1].tobytes() == b[1].tobytes()
