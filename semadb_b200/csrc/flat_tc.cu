@@ -80,6 +80,14 @@ __global__ void to_bf16_kernel(const float* src, uint32_t src_pitch, uint32_t di
   if (lane == 0 && norms) norms[row] = s;
 }
 
+// tcgen05 pass: score = scale * acc + bias[point]; bias = |x|^2 (squared-L2) or 0 (dot, cosine),
+// +inf for rows that hold no point (deleted, never set, beyond the last id) so they never pass
+__global__ void bias_kernel(const float* xn, const uint8_t* exists, uint32_t rows, uint32_t rows_pad, int l2, float* bias) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows_pad) return;
+  bias[i] = (i >= 2 && i < rows && exists[i]) ? (l2 ? xn[i] : 0.0f) : INFINITY;
+}
+
 __global__ void xmax_kernel(const float* xn, const uint8_t* exists, uint32_t first, uint32_t end, uint32_t* out_bits) {
   uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
   float v = 0.0f;
@@ -117,7 +125,8 @@ struct TcArgs {
   int l2;                     // squared-L2: score = xn - 2 acc; else score = -acc
   uint32_t* cand; uint32_t* cand_cnt;  // [B][CAND_CAP], [B]
   uint32_t B;
-  uint32_t rows_alloc;        // rows of x16 / xn (tcgen05 path: point tiles may reach past end_id)
+  uint32_t rows_alloc;        // rows of x16 / bias (tcgen05 path: point tiles may reach past end_id)
+  const float* bias;          // [rows_alloc] tcgen05 path
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 2) tc_filter_kernel(TcArgs a) {
@@ -307,8 +316,9 @@ __device__ __forceinline__ void t5_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ void t5_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void t5_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+constexpr int T5_HITS = 16;  // survivors parked per epilogue thread between flushes
 struct T5Smem {  // offsets from the 1024-byte aligned base
-  uint32_t q, x, xn, bars, tmem_slot, total;
+  uint32_t q, x, xn, hits, bars, tmem_slot, total;
   int stages;
 };
 __host__ __device__ inline T5Smem t5_layout(uint32_t nkb, int stages) {
@@ -317,7 +327,8 @@ __host__ __device__ inline T5Smem t5_layout(uint32_t nkb, int stages) {
   L.q = 0;
   L.x = nkb * T5_QBLK_BYTES;
   L.xn = L.x + uint32_t(stages) * T5_XBLK_BYTES;
-  L.bars = L.xn + 2 * T5_N * 4;
+  L.hits = L.xn + (T5_EPI_THREADS / 32) * 2 * 128 * 4;
+  L.bars = L.hits + T5_EPI_THREADS * T5_HITS * 4;
   L.tmem_slot = L.bars + (2 * uint32_t(stages) + 5) * 8;
   L.total = L.tmem_slot + 16;
   return L;
@@ -339,7 +350,6 @@ tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   auto bar_tfull = [&](int i) { return base + L.bars + uint32_t(2 * stages + 1 + i) * 8; };
   auto bar_tempty = [&](int i) { return base + L.bars + uint32_t(2 * stages + 3 + i) * 8; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + L.tmem_slot);
-  float* s_xn = reinterpret_cast<float*>(gbase + L.xn);
 
   const uint32_t q0 = blockIdx.x * T5_M;
   const uint32_t tile_begin = blockIdx.y * a.tiles_per_cta;
@@ -414,33 +424,50 @@ tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
   } else {
     // ===== epilogue: threshold filter =====
+    // No block-level synchronisation here: a warp stages the bias values of its own 128 columns
+    // in its own shared-memory strip, so a warp that is busy appending survivors never holds
+    // the other seven back; the only coupling is the accumulator hand-off with the MMA warp.
     const int e = warp - 2;                 // 0..7
     const int quad = warp & 3;              // TMEM lanes 32*quad .. 32*quad+31 are this warp's
     const int half = e >> 2;                // columns [128*half, 128*half + 128)
-    const int etid = threadIdx.x - 64;      // 0..255: xn staging slot
+    const int etid = threadIdx.x - 64;      // 0..255
     const uint32_t q = q0 + uint32_t(quad) * 32 + lane;
     const float thr = a.thr[q];             // B_pad rows; padding rows hold -inf
     const bool q_ok = q < a.B;
     const float scale = a.l2 ? -2.0f : -1.0f;
+    float* my_bias = reinterpret_cast<float*>(gbase + L.xn) + e * 2 * 128;  // [2][128] per warp
+    uint32_t* my_hits = reinterpret_cast<uint32_t*>(gbase + L.hits) + etid * T5_HITS;
+    int nh = 0;
+    auto flush_hits = [&]() {
+      if (nh && q_ok) {
+        uint32_t slot = atomicAdd(&a.cand_cnt[q], uint32_t(nh));
+        for (int i = 0; i < nh; ++i, ++slot)
+          if (slot < CAND_CAP) a.cand[size_t(q) * CAND_CAP + slot] = my_hits[i];
+      }
+      nh = 0;
+    };
+    auto load_bias = [&](uint32_t t) -> float4 {  // this lane's 4 of the warp's 128 columns of tile t
+      const uint32_t pid = a.first_id + t * T5_N + uint32_t(half) * 128 + 4 * lane;
+      float4 r;
+      r.x = pid + 0 < a.rows_alloc ? a.bias[pid + 0] : INFINITY;
+      r.y = pid + 1 < a.rows_alloc ? a.bias[pid + 1] : INFINITY;
+      r.z = pid + 2 < a.rows_alloc ? a.bias[pid + 2] : INFINITY;
+      r.w = pid + 3 < a.rows_alloc ? a.bias[pid + 3] : INFINITY;
+      return r;
+    };
     uint32_t it = 0;
-    float xn_next = 0.0f;
-    if (tile_begin < tile_end && a.l2) {
-      const uint32_t pid = a.first_id + tile_begin * T5_N + etid;
-      xn_next = pid < a.rows_alloc ? a.xn[pid] : 0.0f;
-    }
+    float4 bias_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tile_begin < tile_end) bias_next = load_bias(tile_begin);
     for (uint32_t t = tile_begin; t < tile_end; ++t, ++it) {
       const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
       const uint32_t p0 = a.first_id + t * T5_N;
-      s_xn[acc * T5_N + etid] = xn_next;
-      if (t + 1 < tile_end && a.l2) {
-        const uint32_t pid = p0 + T5_N + etid;
-        xn_next = pid < a.rows_alloc ? a.xn[pid] : 0.0f;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(T5_EPI_THREADS) : "memory");
+      float* xs = my_bias + acc * 128;
+      *reinterpret_cast<float4*>(xs + 4 * lane) = bias_next;
+      if (t + 1 < tile_end) bias_next = load_bias(t + 1);
+      __syncwarp();
       t5_mbar_wait(bar_tfull(acc), aph);
       t5_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * T5_N + uint32_t(half) * 128;
-      const float* xs = s_xn + acc * T5_N + half * 128;
       uint32_t v[2][32];
       t5_ld32(taddr, v[0]);
 #pragma unroll
@@ -458,20 +485,20 @@ tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             if (score <= thr) mask |= 1u << (j4 * 4 + jj);
           }
         }
+        // survivors are rare (~k * LEVEL_RATIO per query per level): park them in this thread's
+        // shared-memory list; one atomicAdd per flush instead of one global round trip per hit
         while (mask) {
           const int j = __ffs(mask) - 1;
           mask &= mask - 1;
-          const uint32_t pid = p0 + uint32_t(half) * 128 + uint32_t(c) * 32 + uint32_t(j);
-          if (q_ok && pid < a.end_id && a.exists[pid]) {
-            const uint32_t slot = atomicAdd(&a.cand_cnt[q], 1u);
-            if (slot < CAND_CAP) a.cand[size_t(q) * CAND_CAP + slot] = pid;
-          }
+          my_hits[nh++] = p0 + uint32_t(half) * 128 + uint32_t(c) * 32 + uint32_t(j);
+          if (nh == T5_HITS) flush_hits();
         }
       }
       t5_fence_before();
       __syncwarp();
       if (lane == 0) t5_mbar_arrive(bar_tempty(acc));
     }
+    flush_hits();
   }
   t5_fence_before();
   __syncthreads();
@@ -512,7 +539,7 @@ bool t5_eligible(uint32_t kp) { return kp <= 512 && !getenv("SDB_FLAT_MMA_SYNC")
 
 int launch_tc5_filter(sdb_index* ix, TcArgs ta, uint32_t B_pad, cudaStream_t stream) {
   const uint32_t nkb = ta.kp / T5_KB;
-  int stages = int((220u * 1024u - nkb * T5_QBLK_BYTES) / T5_XBLK_BYTES);
+  int stages = int((198u * 1024u - nkb * T5_QBLK_BYTES) / T5_XBLK_BYTES);
   if (stages > 6) stages = 6;
   const T5Smem L = t5_layout(nkb, stages);
   const size_t smem = size_t(L.total) + 1024;
@@ -663,6 +690,11 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
                                                           reinterpret_cast<__nv_bfloat16*>(ix->d_x16.p), kp, ix->d_xn.p);
     ix->launches++;
     SDB_CUDA(cudaGetLastError());
+    if ((rc = ix->d_bias.ensure(rows_pad))) return rc;
+    bias_kernel<<<(rows_pad + 255) / 256, 256, 0, stream>>>(ix->d_xn.p, ix->d_exists, ix->rows, rows_pad,
+                                                            ix->store_metric == SDB_METRIC_EUCLIDEAN ? 1 : 0, ix->d_bias.p);
+    ix->launches++;
+    SDB_CUDA(cudaGetLastError());
     ix->tc_epoch = ix->vec_epoch;
   }
   if ((rc = ix->d_q16.ensure(size_t(B_pad) * kp)) || (rc = ix->d_qn.ensure(B_pad)) || (rc = ix->d_thr.ensure(B_pad)) ||
@@ -715,6 +747,7 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
     ta.tiles_per_cta = (ntiles + ysplit - 1) / ysplit;
     ysplit = (ntiles + ta.tiles_per_cta - 1) / ta.tiles_per_cta;
     ta.rows_alloc = rows_pad;
+    ta.bias = ix->d_bias.p;
     if (t5_eligible(kp)) {
       if ((rc = launch_tc5_filter(ix, ta, B_pad, stream))) return rc;
     } else {

@@ -137,6 +137,7 @@ struct sdb_index {
   uint64_t vec_epoch = 1, tc_epoch = 0;  // vec_epoch: bumped by every change to vec / exists
   sdb::DevBuf<uint16_t> d_x16, d_q16;
   sdb::DevBuf<float> d_xn, d_qn, d_thr, d_sample_d;
+  sdb::DevBuf<float> d_bias;  // tcgen05 flat pass: per-point score bias (|x|^2 or 0; +inf = no such point)
   sdb::DevBuf<uint32_t> d_cand, d_candcnt, d_sample_cnt;
   sdb::DevBuf<uint64_t> d_sample_ids;
   uint32_t last_B = 0;
