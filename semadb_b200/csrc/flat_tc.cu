@@ -63,29 +63,52 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// rows of f32 -> bf16 [n][kp] (zero padded) and squared norms (fp32, sequential per lane then
+// rows of f32 -> bf16 [n][pitch]: columns [0, kp) = scale * v (zero padded; scale is a power of two,
+// so the rounding is that of v), columns [kp, pitch) = 0 (the K extension, filled in by
+// bias_kernel / thresh_kernel); squared norms of the unscaled rows (fp32, sequential per lane then
 // tree: the norm only feeds the candidate bound, not a result)
 __global__ void to_bf16_kernel(const float* src, uint32_t src_pitch, uint32_t dim, uint32_t n, uint32_t n_pad,
-                               __nv_bfloat16* dst, uint32_t kp, float* norms) {
+                               __nv_bfloat16* dst, uint32_t kp, uint32_t pitch, float scale, float* norms) {
   const uint32_t row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x & 31;
   if (row >= n_pad) return;
   float s = 0.0f;
-  for (uint32_t i = lane; i < kp; i += 32) {
+  for (uint32_t i = lane; i < pitch; i += 32) {
     float v = (row < n && i < dim) ? src[size_t(row) * src_pitch + i] : 0.0f;
     s += v * v;
-    dst[size_t(row) * kp + i] = __float2bfloat16_rn(v);
+    dst[size_t(row) * pitch + i] = __float2bfloat16_rn(scale * v);
   }
   for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(SDB_FULL, s, o);
   if (lane == 0 && norms) norms[row] = s;
 }
 
-// tcgen05 pass: score = scale * acc + bias[point]; bias = |x|^2 (squared-L2) or 0 (dot, cosine),
-// +inf for rows that hold no point (deleted, never set, beyond the last id) so they never pass
-__global__ void bias_kernel(const float* xn, const uint8_t* exists, uint32_t rows, uint32_t rows_pad, int l2, float* bias) {
+// v = hi + mid + lo with three bf16 pieces (24 significant bits: exact for an f32)
+__device__ __forceinline__ void split3(float v, __nv_bfloat16& hi, __nv_bfloat16& mid, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  const float r1 = v - __bfloat162float(hi);
+  mid = __float2bfloat16_rn(r1);
+  lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+}
+constexpr float T5_NO_POINT = 3.0e38f;   // bias of a row that holds no point: never passes
+constexpr float T5_PASS_ALL = 1.0e38f;   // threshold of a query without a bound yet: every point passes
+constexpr float T5_PASS_NONE = -1.0e38f; // padding query rows
+
+// tcgen05 pass: the per-point bias and the per-query threshold ride in the GEMM as a K extension,
+//   x~ = [ x (bf16) | b_hi b_mid b_lo  1 1 1 | 0 ... ]      b = |x|^2 (squared-L2) or 0 (dot, cosine)
+//   q~ = [ s*q      |  1    1     1   -t_hi -t_mid -t_lo | 0 ... ]   s = -2 or -1, t = threshold
+// so the accumulator is score - threshold and the filter is its sign bit. Rows that hold no point
+// (deleted, never set, beyond the last id) get b = 3e38: never negative against any threshold.
+__global__ void bias_kernel(const float* xn, const uint8_t* exists, uint32_t rows, uint32_t rows_pad, int l2, float* bias,
+                            __nv_bfloat16* x16, uint32_t kp, uint32_t pitch) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows_pad) return;
-  bias[i] = (i >= 2 && i < rows && exists[i]) ? (l2 ? xn[i] : 0.0f) : INFINITY;
+  const float b = (i >= 2 && i < rows && exists[i]) ? (l2 ? xn[i] : 0.0f) : T5_NO_POINT;
+  bias[i] = b;
+  __nv_bfloat16 h, m, l;
+  split3(b, h, m, l);
+  __nv_bfloat16* e = x16 + size_t(i) * pitch + kp;
+  const __nv_bfloat16 one = __float2bfloat16_rn(1.0f);
+  e[0] = h; e[1] = m; e[2] = l; e[3] = one; e[4] = one; e[5] = one;
 }
 
 __global__ void xmax_kernel(const float* xn, const uint8_t* exists, uint32_t first, uint32_t end, uint32_t* out_bits) {
@@ -98,26 +121,39 @@ __global__ void xmax_kernel(const float* xn, const uint8_t* exists, uint32_t fir
 
 // per-query pass threshold in "score space": squared-L2 score = xn - 2 acc, dot/cosine score = -acc
 __global__ void thresh_kernel(const float* sample_d, const uint32_t* sample_cnt, uint32_t k, const float* qn,
-                              const uint32_t* xmax_bits, int metric, uint32_t dim, uint32_t B, uint32_t B_pad, float* thr) {
+                              const uint32_t* xmax_bits, int metric, uint32_t dim, uint32_t B, uint32_t B_pad, float* thr,
+                              __nv_bfloat16* q16, uint32_t kp, uint32_t pitch) {
   uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= B_pad) return;
-  if (q >= B) { thr[q] = -INFINITY; return; }  // padding rows never pass
-  if (sample_cnt[q] < k) { thr[q] = INFINITY; return; }
+  auto put = [&](float t_plain, float t_ext) {  // thr[]: mma.sync pass; K extension of q16: tcgen05 pass
+    thr[q] = t_plain;
+    __nv_bfloat16 h, m, l;
+    split3(-t_ext, h, m, l);
+    __nv_bfloat16* e = q16 + size_t(q) * pitch + kp;
+    const __nv_bfloat16 one = __float2bfloat16_rn(1.0f);
+    e[0] = one; e[1] = one; e[2] = one; e[3] = h; e[4] = m; e[5] = l;
+  };
+  if (q >= B) { put(-INFINITY, T5_PASS_NONE); return; }  // padding rows never pass
+  if (sample_cnt[q] < k) { put(INFINITY, T5_PASS_ALL); return; }
   const float tau = sample_d[size_t(q) * k + (k - 1)];
   const float x2 = __uint_as_float(*xmax_bits), q2 = qn[q];
   const float nq = sqrtf(q2), nx = sqrtf(x2);
   const float c1 = 0.02f;                         // > 2 * 2.01 * 2^-8: bf16 unit roundoff 2^-8 on both factors of -2 q.x
-  const float c2 = float(dim + 16) * 2.4e-7f;     // fp32 accumulation of the GEMM, the norms and the exact kernel
+  const float c2 = float(dim + 32) * 4.8e-7f;     // fp32 accumulation of the GEMM (tensor cores may truncate), the K
+                                                  // extension, the norms and the exact kernel
   float t;
   if (metric == METRIC_EUCLIDEAN) t = tau + (c1 * nq * nx + c2 * (q2 + x2)) - q2;
   else if (metric == METRIC_DOT) t = tau + (0.5f * c1 + c2) * nq * nx;
   else t = tau + (0.5f * c1 + c2) * nq * nx - 1.0f;  // cosine distance = 1 - dot
-  thr[q] = t + fabsf(t) * 1e-6f;
+  // strictly above t: the tcgen05 pass keeps score - threshold < 0, the mma.sync pass score <= threshold
+  const float tt = fminf(t + fabsf(t) * 1e-6f + 1e-30f, T5_PASS_ALL);
+  put(tt, tt);
 }
 
 struct TcArgs {
-  const __nv_bfloat16* q16;   // [B_pad][kp]
-  const __nv_bfloat16* x16;   // [rows_pad][kp]
+  const __nv_bfloat16* q16;   // [B_pad][pitch]: scale * q, then the K extension
+  const __nv_bfloat16* x16;   // [rows_pad][pitch]
+  uint32_t pitch;             // kp + 64
   const float* xn;            // [rows_pad]
   const float* thr;           // [B_pad]
   const uint8_t* exists;
@@ -161,8 +197,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_filter_kernel(TcArgs a) {
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int piece = tid + r * TC_THREADS, row = piece >> 3, seg = piece & 7;
-        cp_async16(&sA[buf][row * TROW + seg * 8], a.q16 + size_t(q0 + row) * a.kp + kc * TK + seg * 8);
-        cp_async16(&sB[buf][row * TROW + seg * 8], a.x16 + size_t(p0 + row) * a.kp + kc * TK + seg * 8);
+        cp_async16(&sA[buf][row * TROW + seg * 8], a.q16 + size_t(q0 + row) * a.pitch + kc * TK + seg * 8);
+        cp_async16(&sB[buf][row * TROW + seg * 8], a.x16 + size_t(p0 + row) * a.pitch + kc * TK + seg * 8);
       }
       cp_async_commit();
     };
@@ -204,13 +240,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_filter_kernel(TcArgs a) {
 #pragma unroll
       for (int c2 = 0; c2 < 2; ++c2) {
         const int col = wn * 32 + j * 8 + (lane & 3) * 2 + c2;
-        const float xn = a.l2 ? s_xn[col] : 0.0f;
-        const float scale = a.l2 ? -2.0f : -1.0f;
+        const float xn = a.l2 ? s_xn[col] : 0.0f;  // q16 holds -2 q (squared-L2) or -q: score = acc + bias
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const float score = fmaf(scale, acc[i][j][h * 2 + c2], xn);
+            const float score = acc[i][j][h * 2 + c2] + xn;
             if (score <= thr[i][h]) {
               const uint32_t pid = p0 + col;
               const uint32_t q = q0 + wm * 64 + i * 16 + (lane >> 2) + h * 8;
@@ -228,24 +263,34 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_filter_kernel(TcArgs a) {
 
 
 // ================================================================================================
-// tcgen05 form of the candidate pass (the default for dim <= 512): the same GEMM + threshold
-// filter as tc_filter_kernel, on the 5th-generation tensor cores.
+// tcgen05 form of the candidate pass (the default for dim <= 384): the same bf16 GEMM + threshold
+// filter as tc_filter_kernel, on the 5th-generation tensor cores, with the bias (|x|^2) and the
+// per-query threshold folded into the GEMM as a K extension (bias_kernel / thresh_kernel) so the
+// accumulator is score - threshold and the filter is a sign test.
 //   * warp 0 (one lane): TMA producer. The CTA's 128-query tile of q16 is loaded once
-//     (kp/64 boxes of 128 rows x 128 B, SWIZZLE_128B); point tiles of 256 rows stream through a
-//     ring of 32 KB stages (one 64-wide K block per stage), cp.async.bulk.tensor + mbarrier.
+//     (pitch/64 boxes of 128 rows x 128 B, SWIZZLE_128B); point tiles of 256 rows stream through
+//     a ring of 32 KB stages (one 64-wide K block per stage), cp.async.bulk.tensor + mbarrier.
 //   * warp 1 (one lane): issues tcgen05.mma.kind::f16 M128 x N256 x K16 (bf16 in, f32 out),
 //     A and B straight from shared memory through matrix descriptors; the accumulator of a point
 //     tile is 256 TMEM columns, two tiles (512 columns = all of TMEM) are in flight so the
 //     filter of tile t overlaps the MMAs of tile t+1. tcgen05.commit frees a stage / publishes
 //     an accumulator.
 //   * warps 2..9: epilogue. A thread owns one query (TMEM lane) and half of the tile's columns:
-//     tcgen05.ld 32 columns at a time, score = xn - 2 acc (or -acc), compare with the query's
-//     threshold, append the rare survivors to the query's candidate list.
-// One CTA per SM (192 KB of shared memory, all 512 TMEM columns).
-constexpr int T5_M = 128, T5_N = 256, T5_KB = 64;
+//     tcgen05.ld 32 columns at a time, one funnel shift per element gathers the sign bits, the
+//     rare survivors are parked in shared memory and appended to the query's candidate list
+//     with one atomicAdd per flush. No block-wide barrier in the steady state.
+// One CTA per SM (~200 KB of shared memory, all 512 TMEM columns).
+constexpr int T5_M = 128;   // UMMA M = query rows per MMA = TMEM lanes
+// Query tiles per CTA x points per tile (UMMA N); T5_QT * T5_N = 256 accumulator columns per stage.
+// Measured on B200, 10k x 1M x 128: 1 x 256 runs the pass in 2.9 ms, 2 x 128 (two query tiles
+// sharing each point stage: half the L2->SM traffic, but N = 128 MMAs re-read A from shared
+// memory twice as often) in 3.5 ms — the pass is not L2-bound.
+constexpr int T5_QT = 1;
+constexpr int T5_N = 256;
+constexpr int T5_KB = 64;
 constexpr int T5_THREADS = 320;
 constexpr int T5_EPI_THREADS = 256;
-constexpr uint32_t T5_QBLK_BYTES = T5_M * 128;  // one K block of the query tile
+constexpr uint32_t T5_QBLK_BYTES = T5_M * 128;  // one K block of one query tile
 constexpr uint32_t T5_XBLK_BYTES = T5_N * 128;  // one K block of a point tile = one stage
 constexpr uint32_t T5_IDESC = (1u << 4)                      // D format f32
                               | (1u << 7) | (1u << 10)        // A, B format bf16; both K-major
@@ -325,9 +370,9 @@ __host__ __device__ inline T5Smem t5_layout(uint32_t nkb, int stages) {
   T5Smem L;
   L.stages = stages;
   L.q = 0;
-  L.x = nkb * T5_QBLK_BYTES;
+  L.x = T5_QT * nkb * T5_QBLK_BYTES;
   L.xn = L.x + uint32_t(stages) * T5_XBLK_BYTES;
-  L.hits = L.xn + (T5_EPI_THREADS / 32) * 2 * 128 * 4;
+  L.hits = L.xn;
   L.bars = L.hits + T5_EPI_THREADS * T5_HITS * 4;
   L.tmem_slot = L.bars + (2 * uint32_t(stages) + 5) * 8;
   L.total = L.tmem_slot + 16;
@@ -340,7 +385,7 @@ tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   const uint32_t raw = smem_u32(t5_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   unsigned char* gbase = t5_raw + (base - raw);
-  const uint32_t nkb = a.kp / T5_KB;
+  const uint32_t nkb = a.pitch / T5_KB;  // data K blocks + the extension block (bias, threshold)
   const T5Smem L = t5_layout(nkb, stages);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // barriers: full[s], empty[s], q_full, tmem_full[2], tmem_empty[2]
@@ -351,7 +396,7 @@ tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   auto bar_tempty = [&](int i) { return base + L.bars + uint32_t(2 * stages + 3 + i) * 8; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + L.tmem_slot);
 
-  const uint32_t q0 = blockIdx.x * T5_M;
+  const uint32_t q0 = blockIdx.x * (T5_M * T5_QT);
   const uint32_t tile_begin = blockIdx.y * a.tiles_per_cta;
   const uint32_t ntiles_total = (a.end_id - a.first_id + T5_N - 1) / T5_N;
   const uint32_t tile_end = min(tile_begin + a.tiles_per_cta, ntiles_total);
@@ -380,9 +425,10 @@ tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      t5_mbar_expect_tx(bar_q, nkb * T5_QBLK_BYTES);
-      for (uint32_t kb = 0; kb < nkb; ++kb)
-        t5_tma_load_2d(base + L.q + kb * T5_QBLK_BYTES, &map_q, int32_t(kb * T5_KB), int32_t(q0), bar_q);
+      t5_mbar_expect_tx(bar_q, T5_QT * nkb * T5_QBLK_BYTES);
+      for (uint32_t qt = 0; qt < T5_QT; ++qt)
+        for (uint32_t kb = 0; kb < nkb; ++kb)
+          t5_tma_load_2d(base + L.q + (qt * nkb + kb) * T5_QBLK_BYTES, &map_q, int32_t(kb * T5_KB), int32_t(q0 + qt * T5_M), bar_q);
       int s = 0;
       uint32_t ph = 0;
       for (uint32_t t = tile_begin; t < tile_end; ++t) {
@@ -407,15 +453,17 @@ tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
         t5_mbar_wait(bar_tempty(acc), aph ^ 1u);  // the epilogue has drained this accumulator
         t5_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * T5_N;
+        const uint32_t d_tmem = tmem_base + acc * (T5_QT * T5_N);
         for (uint32_t kb = 0; kb < nkb; ++kb) {
           t5_mbar_wait(bar_full(s), ph);
           t5_fence_after();
-          const uint64_t adesc = t5_smem_desc(base + L.q + kb * T5_QBLK_BYTES);
           const uint64_t bdesc = t5_smem_desc(base + L.x + uint32_t(s) * T5_XBLK_BYTES);
-#pragma unroll
-          for (uint32_t k = 0; k < T5_KB / 16; ++k)  // +32 B per K step inside the swizzle row
-            t5_mma(d_tmem, adesc + 2 * k, bdesc + 2 * k, (kb | k) != 0 ? 1u : 0u);
+          const uint32_t ksteps = kb + 1 == nkb ? 1u : uint32_t(T5_KB / 16);  // the extension is one K16 step
+          for (uint32_t qt = 0; qt < T5_QT; ++qt) {
+            const uint64_t adesc = t5_smem_desc(base + L.q + (qt * nkb + kb) * T5_QBLK_BYTES);
+            for (uint32_t k = 0; k < ksteps; ++k)  // +32 B per K step inside the swizzle row
+              t5_mma(d_tmem + qt * T5_N, adesc + 2 * k, bdesc + 2 * k, (kb | k) != 0 ? 1u : 0u);
+          }
           t5_commit(bar_empty(s));  // stage free once these MMAs have read it
           if (++s == stages) { s = 0; ph ^= 1u; }
         }
@@ -423,19 +471,18 @@ tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
     }
   } else {
-    // ===== epilogue: threshold filter =====
-    // No block-level synchronisation here: a warp stages the bias values of its own 128 columns
-    // in its own shared-memory strip, so a warp that is busy appending survivors never holds
-    // the other seven back; the only coupling is the accumulator hand-off with the MMA warp.
+    // ===== epilogue: sign filter =====
+    // The accumulator already is score - threshold (K extension): a pair survives iff its sign
+    // bit is set. One funnel shift per element collects the 32 sign bits of a chunk. No
+    // block-level synchronisation: a warp that is busy appending survivors never holds the other
+    // seven back; the only coupling is the accumulator hand-off with the MMA warp.
     const int e = warp - 2;                 // 0..7
     const int quad = warp & 3;              // TMEM lanes 32*quad .. 32*quad+31 are this warp's
-    const int half = e >> 2;                // columns [128*half, 128*half + 128)
+    const int qt = T5_QT == 2 ? (e >> 2) : 0;        // query tile of this warp
+    const int col0 = T5_QT == 2 ? 0 : (e >> 2) * 128;  // its 128 of the tile's columns
     const int etid = threadIdx.x - 64;      // 0..255
-    const uint32_t q = q0 + uint32_t(quad) * 32 + lane;
-    const float thr = a.thr[q];             // B_pad rows; padding rows hold -inf
+    const uint32_t q = q0 + uint32_t(qt) * T5_M + uint32_t(quad) * 32 + lane;
     const bool q_ok = q < a.B;
-    const float scale = a.l2 ? -2.0f : -1.0f;
-    float* my_bias = reinterpret_cast<float*>(gbase + L.xn) + e * 2 * 128;  // [2][128] per warp
     uint32_t* my_hits = reinterpret_cast<uint32_t*>(gbase + L.hits) + etid * T5_HITS;
     int nh = 0;
     auto flush_hits = [&]() {
@@ -446,51 +493,28 @@ tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
       nh = 0;
     };
-    auto load_bias = [&](uint32_t t) -> float4 {  // this lane's 4 of the warp's 128 columns of tile t
-      const uint32_t pid = a.first_id + t * T5_N + uint32_t(half) * 128 + 4 * lane;
-      float4 r;
-      r.x = pid + 0 < a.rows_alloc ? a.bias[pid + 0] : INFINITY;
-      r.y = pid + 1 < a.rows_alloc ? a.bias[pid + 1] : INFINITY;
-      r.z = pid + 2 < a.rows_alloc ? a.bias[pid + 2] : INFINITY;
-      r.w = pid + 3 < a.rows_alloc ? a.bias[pid + 3] : INFINITY;
-      return r;
-    };
     uint32_t it = 0;
-    float4 bias_next = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tile_begin < tile_end) bias_next = load_bias(tile_begin);
     for (uint32_t t = tile_begin; t < tile_end; ++t, ++it) {
       const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
       const uint32_t p0 = a.first_id + t * T5_N;
-      float* xs = my_bias + acc * 128;
-      *reinterpret_cast<float4*>(xs + 4 * lane) = bias_next;
-      if (t + 1 < tile_end) bias_next = load_bias(t + 1);
-      __syncwarp();
       t5_mbar_wait(bar_tfull(acc), aph);
       t5_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * T5_N + uint32_t(half) * 128;
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * (T5_QT * T5_N) + uint32_t(qt) * T5_N + uint32_t(col0);
       uint32_t v[2][32];
       t5_ld32(taddr, v[0]);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         t5_wait_ld();
         if (c + 1 < 4) t5_ld32(taddr + uint32_t(c + 1) * 32, v[(c + 1) & 1]);
-        uint32_t mask = 0;
+        uint32_t mask = 0;  // bit 31 - j = sign of column j
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 x4 = *reinterpret_cast<const float4*>(xs + c * 32 + j4 * 4);
-          const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const float score = fmaf(scale, __uint_as_float(v[c & 1][j4 * 4 + jj]), xv[jj]);
-            if (score <= thr) mask |= 1u << (j4 * 4 + jj);
-          }
-        }
+        for (int j = 0; j < 32; ++j) mask = __funnelshift_l(v[c & 1][j], mask, 1);
         // survivors are rare (~k * LEVEL_RATIO per query per level): park them in this thread's
         // shared-memory list; one atomicAdd per flush instead of one global round trip per hit
         while (mask) {
-          const int j = __ffs(mask) - 1;
-          mask &= mask - 1;
-          my_hits[nh++] = p0 + uint32_t(half) * 128 + uint32_t(c) * 32 + uint32_t(j);
+          const int j = __clz(mask);
+          mask &= ~(0x80000000u >> j);
+          my_hits[nh++] = p0 + uint32_t(col0) + uint32_t(c) * 32 + uint32_t(j);
           if (nh == T5_HITS) flush_hits();
         }
       }
@@ -535,27 +559,39 @@ int t5_make_map(CUtensorMap* map, const void* ptr, uint32_t rows, uint32_t kp, u
   return SDB_OK;
 }
 
-bool t5_eligible(uint32_t kp) { return kp <= 512 && !getenv("SDB_FLAT_MMA_SYNC"); }
+// the query tile (all K blocks + the extension) stays resident next to at least two point stages
+bool t5_eligible(uint32_t kp) { return kp <= 384 && !getenv("SDB_FLAT_MMA_SYNC"); }
 
 int launch_tc5_filter(sdb_index* ix, TcArgs ta, uint32_t B_pad, cudaStream_t stream) {
-  const uint32_t nkb = ta.kp / T5_KB;
-  int stages = int((198u * 1024u - nkb * T5_QBLK_BYTES) / T5_XBLK_BYTES);
-  if (stages > 6) stages = 6;
+  const uint32_t nkb = ta.pitch / T5_KB;
+  int stages = int((206u * 1024u - T5_QT * nkb * T5_QBLK_BYTES) / T5_XBLK_BYTES);
+  if (stages > 8) stages = 8;
   const T5Smem L = t5_layout(nkb, stages);
   const size_t smem = size_t(L.total) + 1024;
   CUtensorMap mq, mx;
   int rc;
-  if ((rc = t5_make_map(&mq, ta.q16, B_pad, ta.kp, T5_M)) || (rc = t5_make_map(&mx, ta.x16, ta.rows_alloc, ta.kp, T5_N))) return rc;
+  if ((rc = t5_make_map(&mq, ta.q16, B_pad, ta.pitch, T5_M)) || (rc = t5_make_map(&mx, ta.x16, ta.rows_alloc, ta.pitch, T5_N))) return rc;
   static size_t attr_smem = 0;
   if (attr_smem < smem) {
     SDB_CUDA(cudaFuncSetAttribute(tc5_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     attr_smem = smem;
   }
-  const uint32_t qtiles = B_pad / T5_M;
+  const uint32_t qtiles = B_pad / (T5_M * T5_QT);
   const uint32_t ntiles = (ta.end_id - ta.first_id + T5_N - 1) / T5_N;
-  // one CTA per SM; a few waves so that the last one's imbalance stays small
-  uint32_t ysplit = std::max<uint32_t>(1, (uint32_t(ix->sm_count) * 4 + qtiles - 1) / qtiles);
-  ysplit = std::min(ysplit, ntiles);
+  // one CTA per SM: split the point range so that the CTAs fill whole waves of sm_count (the
+  // fewest waves >= 3 whose last wave is at least 97 % full; each CTA keeps >= 16 tiles)
+  uint32_t ysplit = 1;
+  {
+    const uint32_t sms = uint32_t(ix->sm_count);
+    const uint32_t ymax = std::max<uint32_t>(1, std::min<uint32_t>(64, ntiles / 16));
+    double best = -1.0;
+    for (uint32_t y = 1; y <= ymax; ++y) {
+      const uint32_t ctas = qtiles * y, waves = (ctas + sms - 1) / sms;
+      const double eff = double(ctas) / (double(waves) * sms);
+      if (eff > best) { best = eff; ysplit = y; }
+      if (eff >= 0.97 && waves >= 3) { ysplit = y; break; }
+    }
+  }
   ta.tiles_per_cta = (ntiles + ysplit - 1) / ysplit;
   ysplit = (ntiles + ta.tiles_per_cta - 1) / ta.tiles_per_cta;
   tc5_filter_kernel<<<dim3(qtiles, ysplit), T5_THREADS, smem, stream>>>(mq, mx, ta, stages);
@@ -680,24 +716,24 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
   const uint32_t dim = ix->p.dim, kp = (dim + TK - 1) / TK * TK;
   const uint32_t first_id = 2, end_id = std::max<uint32_t>(2, ix->max_node_id + 1);
   const uint32_t rows_pad = ix->rows + T5_N;  // the last point tile may read past end_id
-  const uint32_t B_pad = (B + TM - 1) / TM * TM;
+  const uint32_t B_pad = (B + 255) / 256 * 256;  // a multiple of both kernels' query tiles
   const bool debug = getenv("SDB_DEBUG_FLAT") != nullptr;
   int rc;
   // ---- bf16 shadow of the store (rebuilt when the store changed)
-  if (ix->tc_epoch != ix->vec_epoch || ix->d_x16.n < size_t(rows_pad) * kp) {
-    if ((rc = ix->d_x16.ensure(size_t(rows_pad) * kp)) || (rc = ix->d_xn.ensure(rows_pad))) return rc;
+  const uint32_t pitch = kp + T5_KB;  // one more 64-wide K block: the extension (bias / threshold pieces)
+  const bool l2 = ix->store_metric == SDB_METRIC_EUCLIDEAN;
+  if (ix->tc_epoch != ix->vec_epoch || ix->d_x16.n < size_t(rows_pad) * pitch) {
+    if ((rc = ix->d_x16.ensure(size_t(rows_pad) * pitch)) || (rc = ix->d_xn.ensure(rows_pad)) || (rc = ix->d_bias.ensure(rows_pad)))
+      return rc;
     to_bf16_kernel<<<(rows_pad + 7) / 8, 256, 0, stream>>>(ix->d_vec, ix->vec_pitch, dim, ix->rows, rows_pad,
-                                                          reinterpret_cast<__nv_bfloat16*>(ix->d_x16.p), kp, ix->d_xn.p);
-    ix->launches++;
-    SDB_CUDA(cudaGetLastError());
-    if ((rc = ix->d_bias.ensure(rows_pad))) return rc;
-    bias_kernel<<<(rows_pad + 255) / 256, 256, 0, stream>>>(ix->d_xn.p, ix->d_exists, ix->rows, rows_pad,
-                                                            ix->store_metric == SDB_METRIC_EUCLIDEAN ? 1 : 0, ix->d_bias.p);
-    ix->launches++;
+                                                          reinterpret_cast<__nv_bfloat16*>(ix->d_x16.p), kp, pitch, 1.0f, ix->d_xn.p);
+    bias_kernel<<<(rows_pad + 255) / 256, 256, 0, stream>>>(ix->d_xn.p, ix->d_exists, ix->rows, rows_pad, l2 ? 1 : 0, ix->d_bias.p,
+                                                            reinterpret_cast<__nv_bfloat16*>(ix->d_x16.p), kp, pitch);
+    ix->launches += 2;
     SDB_CUDA(cudaGetLastError());
     ix->tc_epoch = ix->vec_epoch;
   }
-  if ((rc = ix->d_q16.ensure(size_t(B_pad) * kp)) || (rc = ix->d_qn.ensure(B_pad)) || (rc = ix->d_thr.ensure(B_pad)) ||
+  if ((rc = ix->d_q16.ensure(size_t(B_pad) * pitch)) || (rc = ix->d_qn.ensure(B_pad)) || (rc = ix->d_thr.ensure(B_pad)) ||
       (rc = ix->d_cand.ensure(size_t(B) * CAND_CAP)) || (rc = ix->d_candcnt.ensure(size_t(B) * 2 + 8)) ||
       (rc = ix->d_sample_ids.ensure(size_t(B) * k)) || (rc = ix->d_sample_d.ensure(size_t(B) * k)) ||
       (rc = ix->d_sample_cnt.ensure(B)))
@@ -707,7 +743,7 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
   uint32_t* d_misc = ix->d_candcnt.p + 2 * size_t(B);  // [0] xmax bits, [1] overflow count
   SDB_CUDA(cudaMemsetAsync(d_misc, 0, 8 * sizeof(uint32_t), stream));
   to_bf16_kernel<<<(B_pad + 7) / 8, 256, 0, stream>>>(d_queries, dim, dim, B, B_pad, reinterpret_cast<__nv_bfloat16*>(ix->d_q16.p),
-                                                     kp, ix->d_qn.p);
+                                                     kp, pitch, l2 ? -2.0f : -1.0f, ix->d_qn.p);
   xmax_kernel<<<(end_id - first_id + 255) / 256, 256, 0, stream>>>(ix->d_xn.p, ix->d_exists, first_id, end_id, d_misc);
   ix->launches += 2;
   SDB_CUDA(cudaGetLastError());
@@ -731,14 +767,15 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
     const uint32_t lvl_end = last ? end_id : first_id + uint32_t(covered);
     // thresholds from the previous level's exact top-k
     thresh_kernel<<<(B_pad + 127) / 128, 128, 0, stream>>>(ix->d_sample_d.p, ix->d_sample_cnt.p, k, ix->d_qn.p, d_misc,
-                                                           ix->store_metric, dim, B, B_pad, ix->d_thr.p);
+                                                           ix->store_metric, dim, B, B_pad, ix->d_thr.p,
+                                                           reinterpret_cast<__nv_bfloat16*>(ix->d_q16.p), kp, pitch);
     SDB_CUDA(cudaMemsetAsync(d_cnt, 0, size_t(B) * sizeof(uint32_t), stream));
     TcArgs ta{};
     ta.q16 = reinterpret_cast<const __nv_bfloat16*>(ix->d_q16.p);
     ta.x16 = reinterpret_cast<const __nv_bfloat16*>(ix->d_x16.p);
     ta.xn = ix->d_xn.p; ta.thr = ix->d_thr.p; ta.exists = ix->d_exists;
-    ta.kp = kp; ta.first_id = first_id; ta.end_id = lvl_end;
-    ta.l2 = ix->store_metric == SDB_METRIC_EUCLIDEAN;
+    ta.kp = kp; ta.pitch = pitch; ta.first_id = first_id; ta.end_id = lvl_end;
+    ta.l2 = l2;
     ta.cand = ix->d_cand.p; ta.cand_cnt = d_cnt; ta.B = B;
     const uint32_t ntiles = (lvl_end - first_id + TN - 1) / TN;
     // ~6 waves of CTAs (2 resident per SM) so the last wave's imbalance stays small
