@@ -233,10 +233,10 @@ def main():
     ncpu = os.cpu_count() or 1
     if args.graph == "auto":
         # C2 asks for the reference-built graph. Its CPU build needs ~28 s x 16 threads per 1M-point
-        # shard; when N ranks share the host cores and fewer than 4 threads are left per rank the
+        # shard; when N ranks share the host cores and fewer than 6 threads are left per rank the
         # shards are built by the CUDA batched insert (K8) instead — same search QPS within 1 %
         # (profiles/r01_ab_k1.txt), and stated in config.graph.
-        args.graph = "oracle" if ncpu // world >= 4 else "gpu"
+        args.graph = "oracle" if ncpu // world >= 6 else "gpu"
     if args.graph == "oracle":
         oix, _, tb = build_oracle_index(X, start, max(1, ncpu // world))
         log(f"[rank {rank}] reference-built graph: {tb:.1f}s on {max(1, ncpu // world)} threads")

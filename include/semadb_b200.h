@@ -227,6 +227,17 @@ int sdb_merge_topk(int32_t device, uint32_t S, uint32_t B, uint32_t k, const uin
 int sdb_merge_topk_device(int32_t device, uint32_t S, uint32_t B, uint32_t k, const uint64_t* d_in_ids,
                           const float* d_in_dists, const uint32_t* d_in_counts, uint64_t* d_out_ids,
                           float* d_out_dists, uint32_t* d_out_counts, void* stream);
+/* ---- hybrid-score merge: replaces the dedupe-and-add + sort of indexManager.searchParallel
+ * (shard/index/search.go:211-298) for B requests of S sub-searches each (an "_and" / "_or" query
+ * whose members are vector searches). in_*: S x B x k (sub-search-major), counts S x B;
+ * in_hybrid = HybridScore (-distance * weight, vamana.go:303), in_dists NaN = no distance.
+ * disjunction != 0: "_or" (union of the result-id sets), else "_and" (ids present in every
+ * sub-search). A node found again adds its HybridScore to its first occurrence. out_*: B x (S*k),
+ * sorted by HybridScore descending (ties: first-appearance order), padded with id 0 / -inf / +inf. */
+int sdb_hybrid_merge(int32_t device, uint32_t S, uint32_t B, uint32_t k, int32_t disjunction, const uint64_t* in_ids,
+                     const float* in_hybrid, const float* in_dists, const uint32_t* in_counts, uint64_t* out_ids,
+                     float* out_hybrid, float* out_dists, uint32_t* out_counts);
+
 /* ---- cross-shard exchange fused into the search kernel (replaces the fan-in of
  * ClusterNode.SearchPoints, cluster/actions.go:316-376, without a separate collective).
  * Every GPU owns a gather buffer ids[S][B][k] / dists[S][B][k] / counts[S][B] that its peers

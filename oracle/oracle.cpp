@@ -1239,6 +1239,50 @@ void orc_merge_topk(const uint64_t* in_ids, const float* in_dists, const uint32_
   }
 }
 
+// Hybrid-score merge (indexManager.searchParallel, shard/index/search.go:259-298) for B requests of
+// S sub-searches: the sets are the sub-searches' result ids (vamana.go:285-307 returns exactly
+// those); FastOr / FastAnd; walk results in sub-search order; first occurrence appended, later ones
+// add HybridScore (f32) and donate a distance if the first had none (NaN = nil); slices.SortFunc by
+// HybridScore descending — unstable in Go, stable (first-appearance order) here.
+// in_*: S x B x k, counts S x B; out_*: B x (S*k).
+void orc_hybrid_merge(const uint64_t* in_ids, const float* in_h, const float* in_d, const uint32_t* in_counts, int S,
+                      size_t B, int k, int disjunction, uint64_t* out_ids, float* out_h, float* out_d,
+                      uint32_t* out_counts) {
+  const size_t M = size_t(S) * k;
+  for (size_t b = 0; b < B; ++b) {
+    std::vector<std::vector<uint64_t>> sets(S);
+    for (int s = 0; s < S; ++s)
+      for (uint32_t r = 0; r < std::min<uint32_t>(in_counts[size_t(s) * B + b], k); ++r)
+        sets[s].push_back(in_ids[(size_t(s) * B + b) * k + r]);
+    auto in_final = [&](uint64_t id) {
+      if (disjunction) return true;
+      for (int s = 0; s < S; ++s)
+        if (std::find(sets[s].begin(), sets[s].end(), id) == sets[s].end()) return false;
+      return true;
+    };
+    struct Res { uint64_t id; float h; float d; };
+    std::vector<Res> fin;
+    for (int s = 0; s < S; ++s)
+      for (uint32_t r = 0; r < std::min<uint32_t>(in_counts[size_t(s) * B + b], k); ++r) {
+        const size_t o = (size_t(s) * B + b) * k + r;
+        if (!in_final(in_ids[o])) continue;
+        auto it = std::find_if(fin.begin(), fin.end(), [&](const Res& x) { return x.id == in_ids[o]; });
+        if (it == fin.end()) fin.push_back(Res{in_ids[o], in_h[o], in_d[o]});
+        else {
+          it->h += in_h[o];
+          if (std::isnan(it->d) && !std::isnan(in_d[o])) it->d = in_d[o];
+        }
+      }
+    std::stable_sort(fin.begin(), fin.end(), [](const Res& a, const Res& c) { return a.h > c.h; });
+    for (size_t j = 0; j < M; ++j) {
+      out_ids[b * M + j] = j < fin.size() ? fin[j].id : 0;
+      out_h[b * M + j] = j < fin.size() ? fin[j].h : -INFINITY;
+      out_d[b * M + j] = j < fin.size() ? fin[j].d : INFINITY;
+    }
+    out_counts[b] = uint32_t(fin.size());
+  }
+}
+
 // Per-shard request limit (cluster/actions.go:291-299).
 int orc_shard_limit(int limit, int nshards, int maxSearchLimit) {
   int target = int(float(limit) * (1 / float(nshards)) * 1.42f + 10.0f);

@@ -114,6 +114,8 @@ def lib():
     L.orc_flat_search.argtypes = [C.c_void_p, f32p, C.c_size_t, C.c_int, C.c_uint32, u32p, C.c_size_t, u32p, f32p,
                                   u32p, C.c_int]
     L.orc_merge_topk.argtypes = [u64p, f32p, u32p, C.c_int, C.c_size_t, C.c_int, u64p, f32p, u32p]
+    L.orc_hybrid_merge.argtypes = [u64p, f32p, f32p, u32p, C.c_int, C.c_size_t, C.c_int, C.c_int, u64p, f32p, f32p, u32p]
+    L.orc_hybrid_merge.restype = None
     L.orc_shard_limit.restype = C.c_int
     L.orc_shard_limit.argtypes = [C.c_int, C.c_int, C.c_int]
     L.orc_hw_threads.restype = C.c_int
@@ -406,6 +408,20 @@ def merge_topk(ids, dists, counts, k):
     lib().orc_merge_topk(_p(ids, u64p), _p(dists, f32p), _p(counts, u32p), S, B, k, _p(oi, u64p), _p(od, f32p),
                          _p(oc, u32p))
     return oi, od, oc
+
+
+def hybrid_merge(ids, hybrid, dists, counts, disjunction):
+    """shard/index/search.go:259-298. ids/hybrid/dists: [S,B,k]; counts: [S,B] -> [B,S*k] lists."""
+    ids = np.ascontiguousarray(ids, dtype=np.uint64)
+    hybrid, dists, counts = _f32(hybrid), _f32(dists), _u32(counts)
+    S, B, k = ids.shape
+    oi = np.zeros((B, S * k), dtype=np.uint64)
+    oh = np.zeros((B, S * k), dtype=np.float32)
+    od = np.zeros((B, S * k), dtype=np.float32)
+    oc = np.zeros(B, dtype=np.uint32)
+    lib().orc_hybrid_merge(_p(ids, u64p), _p(hybrid, f32p), _p(dists, f32p), _p(counts, u32p), S, B, k,
+                           1 if disjunction else 0, _p(oi, u64p), _p(oh, f32p), _p(od, f32p), _p(oc, u32p))
+    return oi, oh, od, oc
 
 
 def shard_limit(limit, nshards, max_search_limit=75):

@@ -105,6 +105,8 @@ _SIGS = {
     "sdb_merge_topk": (C.c_int, [C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, u64p, f32p, u32p, u64p, f32p, u32p]),
     "sdb_merge_topk_device": (C.c_int, [C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sdb_hybrid_merge": (C.c_int, [C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, u64p, f32p, f32p, u32p, u64p,
+                                   f32p, f32p, u32p]),
     "sdb_shard_limit": (C.c_uint32, [C.c_uint32, C.c_uint32, C.c_uint32]),
 }
 

@@ -159,6 +159,75 @@ __global__ void merge_topk_kernel(uint32_t S, uint32_t B, uint32_t k, const uint
   }
 }
 
+// Hybrid-score merge of S sub-searches per request (indexManager.searchParallel,
+// shard/index/search.go:211-298): final set = OR / AND of the sub-searches' result-id sets; results
+// are walked in sub-search order, rank order; a node seen again adds its HybridScore to the first
+// occurrence (f32, in that order) and donates its distance if the first had none (NaN = nil);
+// then sort by HybridScore descending. The reference's sort is unstable: ties keep first-appearance
+// order here (and in the oracle). One thread per request; lists are S*k <= 1200 entries.
+__global__ void hybrid_merge_kernel(uint32_t S, uint32_t B, uint32_t k, int disjunction, const uint64_t* in_ids,
+                                    const float* in_h, const float* in_d, const uint32_t* in_c, uint64_t* out_ids,
+                                    float* out_h, float* out_d, uint32_t* out_c) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const uint32_t M = S * k;
+  uint64_t* oi = out_ids + size_t(b) * M;
+  float* oh = out_h + size_t(b) * M;
+  float* od = out_d + size_t(b) * M;
+  uint32_t n = 0;
+  for (uint32_t s = 0; s < S; ++s) {
+    const uint32_t cs = min(in_c[size_t(s) * B + b], k);
+    for (uint32_t r = 0; r < cs; ++r) {
+      const size_t o = (size_t(s) * B + b) * k + r;
+      const uint64_t id = in_ids[o];
+      if (!disjunction) {  // finalSet.Contains(r.NodeId): present in every sub-search's set
+        bool everywhere = true;
+        for (uint32_t t = 0; t < S && everywhere; ++t) {
+          if (t == s) continue;
+          const uint32_t ct = min(in_c[size_t(t) * B + b], k);
+          bool found = false;
+          for (uint32_t j = 0; j < ct && !found; ++j) found = in_ids[(size_t(t) * B + b) * k + j] == id;
+          everywhere = found;
+        }
+        if (!everywhere) continue;
+      }
+      uint32_t idx = n;
+      for (uint32_t j = 0; j < n; ++j)
+        if (oi[j] == id) { idx = j; break; }
+      if (idx == n) {
+        oi[n] = id;
+        oh[n] = in_h[o];
+        od[n] = in_d[o];
+        ++n;
+      } else {
+        oh[idx] = __fadd_rn(oh[idx], in_h[o]);
+        if (isnan(od[idx]) && !isnan(in_d[o])) od[idx] = in_d[o];
+      }
+    }
+  }
+  // stable insertion sort, HybridScore descending
+  for (uint32_t i = 1; i < n; ++i) {
+    const uint64_t ci = oi[i];
+    const float ch = oh[i], cd = od[i];
+    uint32_t j = i;
+    while (j > 0 && oh[j - 1] < ch) {
+      oi[j] = oi[j - 1];
+      oh[j] = oh[j - 1];
+      od[j] = od[j - 1];
+      --j;
+    }
+    oi[j] = ci;
+    oh[j] = ch;
+    od[j] = cd;
+  }
+  out_c[b] = n;
+  for (uint32_t j = n; j < M; ++j) {
+    oi[j] = 0;
+    oh[j] = -__int_as_float(0x7f800000);
+    od[j] = __int_as_float(0x7f800000);
+  }
+}
+
 int set_device_checked(int device) {
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -436,6 +505,35 @@ int sdb_merge_topk(int32_t device, uint32_t S, uint32_t B, uint32_t k, const uin
   if (rc) return rc;
   SDB_CUDA(cudaMemcpy(out_ids, oi.p, size_t(B) * k * 8, cudaMemcpyDeviceToHost));
   SDB_CUDA(cudaMemcpy(out_dists, od.p, size_t(B) * k * 4, cudaMemcpyDeviceToHost));
+  SDB_CUDA(cudaMemcpy(out_counts, oc.p, size_t(B) * 4, cudaMemcpyDeviceToHost));
+  return SDB_OK;
+}
+
+int sdb_hybrid_merge(int32_t device, uint32_t S, uint32_t B, uint32_t k, int32_t disjunction, const uint64_t* in_ids,
+                     const float* in_hybrid, const float* in_dists, const uint32_t* in_counts, uint64_t* out_ids,
+                     float* out_hybrid, float* out_dists, uint32_t* out_counts) {
+  if (B == 0) return SDB_OK;
+  if (!in_ids || !in_hybrid || !in_dists || !in_counts || !out_ids || !out_hybrid || !out_dists || !out_counts)
+    return fail(SDB_ERR_INVALID, "null argument");
+  if (S < 1 || S > 16 || k < 1 || k > 75) return fail(SDB_ERR_INVALID, "hybrid merge supports 1..16 sub-searches of limit 1..75");
+  int rc = set_device_checked(device);
+  if (rc) return rc;
+  const size_t n = size_t(S) * B * k;
+  TmpDev di, dh, dd, dc, oi, oh, od, oc;
+  if ((rc = di.alloc(n * 8)) || (rc = dh.alloc(n * 4)) || (rc = dd.alloc(n * 4)) || (rc = dc.alloc(size_t(S) * B * 4)) ||
+      (rc = oi.alloc(n * 8)) || (rc = oh.alloc(n * 4)) || (rc = od.alloc(n * 4)) || (rc = oc.alloc(size_t(B) * 4)))
+    return rc;
+  SDB_CUDA(cudaMemcpy(di.p, in_ids, n * 8, cudaMemcpyHostToDevice));
+  SDB_CUDA(cudaMemcpy(dh.p, in_hybrid, n * 4, cudaMemcpyHostToDevice));
+  SDB_CUDA(cudaMemcpy(dd.p, in_dists, n * 4, cudaMemcpyHostToDevice));
+  SDB_CUDA(cudaMemcpy(dc.p, in_counts, size_t(S) * B * 4, cudaMemcpyHostToDevice));
+  hybrid_merge_kernel<<<(B + 63) / 64, 64>>>(S, B, k, disjunction, static_cast<uint64_t*>(di.p), static_cast<float*>(dh.p),
+                                             static_cast<float*>(dd.p), static_cast<uint32_t*>(dc.p), static_cast<uint64_t*>(oi.p),
+                                             static_cast<float*>(oh.p), static_cast<float*>(od.p), static_cast<uint32_t*>(oc.p));
+  SDB_CUDA(cudaGetLastError());
+  SDB_CUDA(cudaMemcpy(out_ids, oi.p, n * 8, cudaMemcpyDeviceToHost));
+  SDB_CUDA(cudaMemcpy(out_hybrid, oh.p, n * 4, cudaMemcpyDeviceToHost));
+  SDB_CUDA(cudaMemcpy(out_dists, od.p, n * 4, cudaMemcpyDeviceToHost));
   SDB_CUDA(cudaMemcpy(out_counts, oc.p, size_t(B) * 4, cudaMemcpyDeviceToHost));
   return SDB_OK;
 }

@@ -146,3 +146,33 @@ def test_merge_topk_matches_oracle():
                                            cnt.ctypes.data_as(u32p), gi.ctypes.data_as(u64p),
                                            gd.ctypes.data_as(f32p), gc.ctypes.data_as(u32p)))
     assert (gc == oc).all() and (gi == oi).all() and gd.tobytes() == od.tobytes()
+
+
+@pytest.mark.parametrize("disjunction", [True, False])
+def test_hybrid_merge_matches_oracle(disjunction):
+    """sdb_hybrid_merge vs the oracle's restatement of searchParallel (shard/index/search.go:259-298):
+    random overlapping sub-search lists, some without distances, ragged counts."""
+    rng = np.random.Generator(np.random.PCG64(77))
+    S, B, k = 3, 500, 10
+    ids = rng.integers(2, 40, size=(S, B, k)).astype(np.uint64)
+    for s in range(S):  # ids are unique inside one sub-search's list
+        for b in range(B):
+            ids[s, b] = rng.permutation(np.arange(2, 40, dtype=np.uint64))[:k]
+    d = np.sort(rng.integers(0, 30, size=(S, B, k)).astype(np.float32), axis=2)
+    w = np.array([0.5, 1.0, 2.0], np.float32).reshape(S, 1, 1)
+    h = (np.float32(-1) * d * w).astype(np.float32)
+    d[2] = np.nan  # a text sub-search: scores, no distances
+    h[2] = np.sort(rng.random((B, k)).astype(np.float32), axis=1)[:, ::-1]
+    cnt = rng.integers(0, k + 1, size=(S, B)).astype(np.uint32)
+    oi, oh, od, oc = O.hybrid_merge(ids, h, d, cnt, disjunction)
+    gi = np.zeros((B, S * k), np.uint64)
+    gh = np.zeros((B, S * k), np.float32)
+    gd = np.zeros((B, S * k), np.float32)
+    gc = np.zeros(B, np.uint32)
+    _capi.check(_capi.lib().sdb_hybrid_merge(0, S, B, k, 1 if disjunction else 0, ids.ctypes.data_as(u64p),
+                                             h.ctypes.data_as(f32p), d.ctypes.data_as(f32p), cnt.ctypes.data_as(u32p),
+                                             gi.ctypes.data_as(u64p), gh.ctypes.data_as(f32p), gd.ctypes.data_as(f32p),
+                                             gc.ctypes.data_as(u32p)))
+    assert (gc == oc).all() and (gi == oi).all()
+    assert gh.tobytes() == oh.tobytes() and gd.tobytes() == od.tobytes()
+    assert oc.max() > k and (oc.min() == 0 or not disjunction)

@@ -463,3 +463,41 @@ def test_delete_orphan_goes_to_start_overflow():
     ix.update_delete(np.array([2], np.uint32), np.zeros((1, 2), np.float32), np.zeros(1, np.uint8))
     assert ix.start_extra().tolist() == []
     _graph_invariants(ix, [3, 4, 5, 7, 8, 9, 10])
+
+
+def test_hybrid_merge_semantics():
+    """indexManager.searchParallel (shard/index/search.go:259-298), shaped after the reference's
+    TestSearch_Or / TestSearch_And / TestSearch_OrVector (shard/index/search_test.go:289-457):
+    union vs intersection of the result-id sets, duplicate hits add their HybridScore, the first
+    non-nil distance is kept, output sorted by HybridScore descending."""
+    nan = np.float32(np.nan)
+    # request 0: two sub-searches overlapping in ids 42 and 43
+    ids = np.zeros((2, 1, 4), np.uint64)
+    h = np.zeros((2, 1, 4), np.float32)
+    d = np.full((2, 1, 4), nan, np.float32)
+    ids[0, 0] = [42, 43, 44, 45]
+    h[0, 0] = [-0.0, -0.5, -1.0, -1.5]      # vector search, weight 0.5: HybridScore = -d * w
+    d[0, 0] = [0.0, 1.0, 2.0, 3.0]
+    ids[1, 0, :3] = [43, 42, 7]
+    h[1, 0, :3] = [2.0, 1.0, 0.5]           # text search: score * weight, no distance
+    c = np.array([[4], [3]], np.uint32)
+    oi, oh, od, oc = O.hybrid_merge(ids, h, d, c, disjunction=True)
+    assert oc[0] == 5
+    assert oi[0, :5].tolist() == [43, 42, 7, 44, 45]
+    assert oh[0, :5].tolist() == [1.5, 1.0, 0.5, -1.0, -1.5]
+    assert od[0, 0] == 1.0 and od[0, 1] == 0.0 and np.isnan(od[0, 2])
+    assert (np.diff(oh[0, :5]) <= 0).all()
+    oi, oh, od, oc = O.hybrid_merge(ids, h, d, c, disjunction=False)
+    assert oc[0] == 2 and oi[0, :2].tolist() == [43, 42] and oh[0, :2].tolist() == [1.5, 1.0]
+    # TestSearch_OrVector: the same five results from two searches with weight 0.5 each:
+    # HybridScore adds up to -distance
+    ids2 = np.tile(np.array([42, 43, 41, 44, 40], np.uint64), (2, 1, 1))
+    d2 = np.tile(np.array([0.0, 2.0, 2.0, 8.0, 8.0], np.float32), (2, 1, 1))
+    h2 = (np.float32(-1) * d2 * np.float32(0.5)).astype(np.float32)
+    c2 = np.full((2, 1), 5, np.uint32)
+    oi, oh, od, oc = O.hybrid_merge(ids2, h2, d2, c2, disjunction=True)
+    assert oc[0] == 5 and oi[0, 0] == 42 and (oh[0, :5] == -od[0, :5]).all()
+    assert oi[0, :5].tolist() == [42, 43, 41, 44, 40]  # ties keep first-appearance order
+    # a single sub-search is returned as is (search.go:246-249)
+    oi, oh, od, oc = O.hybrid_merge(ids[:1], h[:1], d[:1], c[:1], disjunction=False)
+    assert oc[0] == 4 and oi[0].tolist() == [42, 43, 44, 45]
