@@ -515,15 +515,35 @@ int sdb_search_batch(sdb_index* ix, uint32_t B, const float* queries, uint32_t k
   uint32_t n_seed = 0;
   const bool filtered = filter_ids != nullptr;
   if (filtered && (rc = stage_filter(ix, filter_ids, n_filter, search_size, &n_seed))) return rc;
-  if ((rc = ix->d_q.ensure(size_t(B) * ix->p.dim))) return rc;
+  // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister: what a cgo wrapper keeps for its
+  // request batches) are mapped into the device address space: the kernel then reads each query
+  // once straight from host memory (512 B per query, when a warp picks the query up) and stores
+  // the top-k straight back, so the copies disappear from the critical path instead of preceding
+  // and following the kernel. Pageable buffers go through the staging copies.
+  const bool zero_copy = getenv("SDB_NO_ZEROCOPY") == nullptr;
+  auto mapped = [&](const void* p) -> void* {
+    if (!zero_copy) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+  };
+  const float* q_dev = static_cast<const float*>(mapped(queries));
+  uint64_t* oid_dev = static_cast<uint64_t*>(mapped(out_ids));
+  float* od_dev = static_cast<float*>(mapped(out_dists));
+  uint32_t* oc_dev = static_cast<uint32_t*>(mapped(out_counts));
+  if (!q_dev) {
+    if ((rc = ix->d_q.ensure(size_t(B) * ix->p.dim))) return rc;
+    SDB_CUDA(cudaMemcpyAsync(ix->d_q.p, queries, size_t(B) * ix->p.dim * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+    q_dev = ix->d_q.p;
+  }
   if ((rc = ensure_out_scratch(ix, B, k))) return rc;
-  SDB_CUDA(cudaMemcpyAsync(ix->d_q.p, queries, size_t(B) * ix->p.dim * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
-  rc = launch_search(ix, B, ix->d_q.p, k, search_size, ix->d_oid.p, ix->d_od.p, ix->d_oc.p, nullptr, nullptr, nullptr, 0,
-                     filtered ? ix->d_filter_seed.p : nullptr, n_seed, filtered ? ix->d_filter_bits.p : nullptr, ix->stream);
+  rc = launch_search(ix, B, q_dev, k, search_size, oid_dev ? oid_dev : ix->d_oid.p, od_dev ? od_dev : ix->d_od.p,
+                     oc_dev ? oc_dev : ix->d_oc.p, nullptr, nullptr, nullptr, 0, filtered ? ix->d_filter_seed.p : nullptr, n_seed,
+                     filtered ? ix->d_filter_bits.p : nullptr, ix->stream);
   if (rc) return rc;
-  SDB_CUDA(cudaMemcpyAsync(out_ids, ix->d_oid.p, size_t(B) * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, ix->stream));
-  SDB_CUDA(cudaMemcpyAsync(out_dists, ix->d_od.p, size_t(B) * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
-  SDB_CUDA(cudaMemcpyAsync(out_counts, ix->d_oc.p, size_t(B) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ix->stream));
+  if (!oid_dev) SDB_CUDA(cudaMemcpyAsync(out_ids, ix->d_oid.p, size_t(B) * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, ix->stream));
+  if (!od_dev) SDB_CUDA(cudaMemcpyAsync(out_dists, ix->d_od.p, size_t(B) * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+  if (!oc_dev) SDB_CUDA(cudaMemcpyAsync(out_counts, ix->d_oc.p, size_t(B) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ix->stream));
   SDB_CUDA(cudaStreamSynchronize(ix->stream));
   return SDB_OK;
 }

@@ -142,3 +142,30 @@ def test_visited_list_matches_oracle():
         n = vn[b]
         assert (vi[b, :n] == ref["vis_ids"][b, :n]).all()
         assert vd[b, :n].tobytes() == ref["vis_dists"][b, :n].tobytes()
+
+
+def test_search_batch_pinned_buffers_zero_copy():
+    """sdb_search_batch with page-locked caller buffers (the kernel reads queries from and writes
+    results to mapped host memory) must return exactly what the staged-copy path returns for
+    pageable buffers, and what the oracle returns."""
+    import ctypes as C
+
+    import torch
+    from semadb_b200 import _capi
+    n, dim, B, k = 6000, 128, 500, 10
+    X = synth.sift_shaped(n, dim, 3)
+    Q = synth.sift_shaped(B, dim, 4, w_seed=3)
+    oix, ids, start = oracle_graph(X)
+    g = mirror_to_gpu(oix, X, ids, start)
+    ref = oix.search(Q, k=k, threads=8)
+    pi, pd, pc = g.search_batch(Q, k, 75)  # numpy (pageable) buffers: staging copies
+    h_q = torch.from_numpy(Q).pin_memory()
+    h_ids = torch.zeros((B, k), dtype=torch.int64).pin_memory()
+    h_d = torch.zeros((B, k), dtype=torch.float32).pin_memory()
+    h_c = torch.zeros((B,), dtype=torch.int32).pin_memory()
+    _capi.check(_capi.lib().sdb_search_batch(g._h, B, C.cast(h_q.data_ptr(), _capi.f32p), k, 75, None, 0,
+                                             C.cast(h_ids.data_ptr(), _capi.u64p), C.cast(h_d.data_ptr(), _capi.f32p),
+                                             C.cast(h_c.data_ptr(), _capi.u32p)))
+    assert (h_ids.numpy().astype(np.uint64) == pi).all() and h_d.numpy().tobytes() == pd.tobytes()
+    assert (h_c.numpy().astype(np.uint32) == pc).all()
+    assert (pi == ref["ids"].astype(np.uint64)).all() and pd.tobytes() == ref["dists"].tobytes()
