@@ -152,6 +152,7 @@ def test_search_batch_pinned_buffers_zero_copy():
 
     import torch
     from semadb_b200 import _capi
+    from tests.helpers import mirror_to_gpu, oracle_graph
     n, dim, B, k = 6000, 128, 500, 10
     X = synth.sift_shaped(n, dim, 3)
     Q = synth.sift_shaped(B, dim, 4, w_seed=3)
