@@ -162,6 +162,8 @@ def c5a():
     n = 1_000_000
     X = synth.sift_shaped(n, 128, 3)
     g = IndexVamana("c5a", IndexVectorVamanaParameters(128, "euclidean", L, R, ALPHA), start_vector=synth.start_vector(128, 99))
+    if os.environ.get("SDB_INSERT_CONFIG"):  # "min,max,growth_div" (A/B of the mini-batch schedule)
+        g.insert_config(*[int(x) for x in os.environ["SDB_INSERT_CONFIG"].split(",")])
     ids = np.arange(2, n + 2, dtype=np.uint64)
     torch.cuda.synchronize()
     t = time.time()
@@ -172,7 +174,8 @@ def c5a():
     deg, _ = g.get_edges(ids[:100000])
     print(json.dumps({"config": "c5a", "workload": "batched build from empty: 1M x 128 SIFT-shaped f32 L2 (host vectors, H2D inside)",
                       "build_s": dt, "points_per_s": n / dt, "recall_at_10_of_built_graph": recall(g, Q, got),
-                      "mean_out_degree": float(deg.mean()), "search_qps_on_built_graph": len(Q) / (ms * 1e-3)}), flush=True)
+                      "mean_out_degree": float(deg.mean()), "search_qps_on_built_graph": len(Q) / (ms * 1e-3),
+                      "insert_config": os.environ.get("SDB_INSERT_CONFIG", "default 1,4096,16")}), flush=True)
 
 
 def flat(n=1_000_000, B=10_000):
