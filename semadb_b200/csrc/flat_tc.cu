@@ -3,9 +3,9 @@
 //
 // bf16 products cannot be final distances (1e-5 tolerance, SURVEY.md §7.3-⑥), so the tensor
 // cores only *generate candidates*, with a guarantee:
-//   1. exact top-k of every query over the first 1024 points (the exact CUDA-core scan, flat.cu)
+//   1. exact top-k of every query over the first 128 points (the exact CUDA-core scan, flat.cu)
 //      gives tau_q >= the true k-th smallest distance; steps 2-3 then run over growing prefixes
-//      of the store (x32 per level: 32k points, 1M, ...), each level's exact top-k tightening
+//      of the store (x32 per level: 4k points, 131k, 4M, ...), each level's exact top-k tightening
 //      tau for the next, so every level keeps ~32 k candidates per query;
 //   2. a bf16 GEMM (fp32 accumulate) scores every (query, point) pair: a(q,x) = |x|^2 - 2 q~.x~
 //      (+|q|^2) for squared-L2, -q~.x~ for dot/cosine. |a - d| <= eps_q, a bound from the bf16
@@ -41,7 +41,8 @@ constexpr int TPAD = 8;                 // bf16 elements of row padding (16 B): 
 constexpr int TROW = TK + TPAD;         // 72 bf16 = 144 B per smem row
 constexpr int TC_THREADS = 256;
 constexpr uint32_t CAND_CAP = 4096;     // candidate ids kept per query
-constexpr uint32_t LEVEL0 = 1024;       // points scanned exactly to bound the k-th distance
+constexpr uint32_t LEVEL0 = 128;        // points scanned exactly to bound the k-th distance (SDB_FLAT_LEVEL0 overrides: A/B);
+                                        // 1M points: 128 -> 4k -> 131k -> all runs in 5.45 ms, 1024 -> 32k -> all in 5.85 ms
 constexpr uint32_t LEVEL_RATIO = 32;    // each tensor-core level covers 32x more points than the one before
 constexpr size_t TC_SMEM = size_t(2) * (TM + TN) * TROW * 2 + TN * 4;
 
@@ -627,7 +628,41 @@ __global__ void __launch_bounds__(128) rescore_kernel(const float* vec, uint32_t
   __syncthreads();
   constexpr bool L2 = (METRIC == METRIC_EUCLIDEAN);
   const int trips = dim >> 5;
-  for (uint32_t c0 = 0; c0 < n; c0 += 16) {
+  uint32_t c0 = 0;
+  if (trips <= 4) {
+    // rows of up to 4 trips: four candidates per 8-lane group per step, all 16 row loads of a
+    // lane in flight before the first is consumed (the gather is latency-bound otherwise)
+    for (; c0 < n; c0 += 64) {
+      float4 y[4][4];
+      uint32_t pid[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t c = c0 + u * 16 + grp;
+        pid[u] = cand[size_t(q) * CAND_CAP + (c < n ? c : 0)];
+        const float* row = vec + size_t(pid[u]) * vec_pitch + 4 * g;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) y[u][t] = t < trips ? ldg_f4_stream(row + 32 * t) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t c = c0 + u * 16 + grp;
+        const float* row = vec + size_t(pid[u]) * vec_pitch;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (t < trips) trip_accum<L2>(*reinterpret_cast<const float4*>(s_q + 32 * t + 4 * g), y[u][t], acc);
+        float tail = 0.0f;
+        if (g == 0)
+          for (uint32_t i = trips << 5; i < dim; ++i) tail = tail_accum<L2>(s_q[i], __ldg(row + i), tail);
+        const float r = group_reduce(acc, tail);
+        if (g == 0 && c < n) {
+          s_d[c] = metric_epilogue<METRIC>(r);
+          s_id[c] = pid[u];
+        }
+      }
+    }
+  }
+  for (; c0 < n; c0 += 16) {
     const uint32_t c = c0 + grp;
     const bool act = c < n;
     const uint32_t pid = cand[size_t(q) * CAND_CAP + (act ? c : 0)];
@@ -702,13 +737,21 @@ __global__ void scatter_results_kernel(const uint32_t* list, uint32_t n, uint32_
 
 }  // namespace
 
+static uint32_t level0_points() {
+  if (const char* e = getenv("SDB_FLAT_LEVEL0")) {
+    const int v = atoi(e);
+    if (v >= 32 && v <= 65536) return uint32_t(v);
+  }
+  return LEVEL0;
+}
+
 bool flat_tc_eligible(const sdb_index* ix, uint32_t k, bool filtered) {
   if (getenv("SDB_FLAT_EXACT")) return false;
   if (filtered || ix->quant_active()) return false;
   if (ix->store_metric != SDB_METRIC_EUCLIDEAN && ix->store_metric != SDB_METRIC_DOT && ix->store_metric != SDB_METRIC_COSINE)
     return false;
   const uint32_t end_id = std::max<uint32_t>(2, ix->max_node_id + 1);
-  return end_id - 2 >= LEVEL0 * LEVEL_RATIO && k <= 75;
+  return end_id - 2 >= LEVEL0 * LEVEL_RATIO && k <= 75;  // (with the default LEVEL0)
 }
 
 int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k, uint64_t* d_out_ids, float* d_out_dists,
@@ -754,13 +797,13 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
   }
   // ---- level 0: exact scan of the first LEVEL0 points bounds every query's k-th distance
   if ((rc = launch_flat_exact(ix, B, d_queries, k, nullptr, ix->d_sample_ids.p, ix->d_sample_d.p, ix->d_sample_cnt.p, stream,
-                              first_id, first_id + LEVEL0)))
+                              first_id, first_id + level0_points())))
     return rc;
   // ---- levels 1..: tensor-core pass over a 32x larger prefix, thresholds from the level before
   const uint32_t npts = end_id - first_id;
   const uint32_t qtiles = B_pad / TM;
   const size_t qsmem = size_t((dim + 3) & ~3u) * sizeof(float);
-  uint64_t covered = LEVEL0;
+  uint64_t covered = level0_points();
   while (covered < npts) {
     covered = std::min<uint64_t>(npts, covered * LEVEL_RATIO);
     const bool last = covered >= npts;
