@@ -8,7 +8,7 @@
 
 namespace sdb {
 
-constexpr int PRUNE_THREADS = 128;
+constexpr int PRUNE_THREADS = 256;
 constexpr int PRUNE_GROUPS = PRUNE_THREADS / 8;
 constexpr int MAX_CAND = 256;  // visited-list capacity handed to robustPrune
 
@@ -150,14 +150,15 @@ __device__ inline void robust_prune_cta(const StoreView& s, PruneShared& sh, con
   const int g = lane & 7;
   const int grp = threadIdx.x >> 3;  // 0..PRUNE_GROUPS-1
   for (int i = threadIdx.x; i < n; i += blockDim.x) sh.removed[i] = 0;
-  if (threadIdx.x == 0) *sh.cnt = 0;
   __syncthreads();
+  // every thread tracks the edge count in a register (the decisions below are block-uniform):
+  // one barrier per accepted candidate — after its removal marks — instead of three
+  int cnt = 0;
   for (int i = 0; i < n; ++i) {
     if (sh.removed[i] || sh.sid[i] == node) continue;  // block-uniform
-    __syncthreads();
-    if (threadIdx.x == 0) sh.edges[(*sh.cnt)++] = sh.sid[i];
-    __syncthreads();
-    if (*sh.cnt >= R) break;
+    if (threadIdx.x == 0) sh.edges[cnt] = sh.sid[i];
+    ++cnt;
+    if (cnt >= R) break;
     const unsigned char* xi = i < staged ? rows + size_t(i) * s.row_bytes : global_row(s, sh.sid[i]);
     for (int j0 = i + 1; j0 < n; j0 += PRUNE_GROUPS) {
       int j = j0 + grp;
@@ -169,8 +170,9 @@ __device__ inline void robust_prune_cta(const StoreView& s, PruneShared& sh, con
       float d = row_dist(s, xi, yj, g);
       if (act && g == 0 && __fmul_rn(alpha, d) < sh.sdist[j]) sh.removed[j] = 1;  // search.go:132
     }
-    __syncthreads();
+    __syncthreads();  // removal marks of this round are visible before the next candidate is read
   }
+  if (threadIdx.x == 0) *sh.cnt = cnt;
   __syncthreads();
 }
 
