@@ -308,8 +308,6 @@ def main():
     h_c = torch.zeros((B,), dtype=torch.int32).pin_memory()
     import ctypes as C
 
-    d_q2 = torch.empty_like(d_q)
-
     def e2e_step():
         if world == 1:
             _capi.check(lib.sdb_search_batch(gix._h, B, C.cast(h_q.data_ptr(), _capi.f32p), K, L, None, 0,
@@ -318,13 +316,9 @@ def main():
             return
         # N > 1: every rank receives the broadcast query batch in host memory (the Go cluster layer
         # fans requests out to shards, cluster/actions.go:316-351), copies it in, runs the sharded
-        # search (K1 with the fused peer gather, barrier, K6) and reads the merged lists back.
-        d_q2.copy_(h_q, non_blocking=True)
-        r_ids, r_d, r_c = searcher.search_batch_device(d_q2, K, L)
-        h_ids.copy_(r_ids, non_blocking=True)
-        h_d.copy_(r_d, non_blocking=True)
-        h_c.copy_(r_c, non_blocking=True)
-        torch.cuda.synchronize()
+        # search (K1 with the fused peer gather, barrier, K6) and receives the merged lists.
+        # The buffers are page-locked: the kernels read / write them in place (mapped host memory).
+        searcher.search_batch_pinned(h_q, K, L, h_ids, h_d, h_c, dev)
 
     for _ in range(2):
         e2e_step()

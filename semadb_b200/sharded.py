@@ -150,6 +150,43 @@ class ShardedSearcher:
                       torch.zeros((B, k), dtype=torch.float32, device=device),
                       torch.zeros((B,), dtype=torch.int32, device=device))
 
+    def search_batch_pinned(self, h_queries, k: int, search_size: int, h_ids, h_dists, h_counts, device,
+                            max_search_limit: int = 75):
+        """Host-facing twin of search_batch_device for page-locked (pinned) torch CPU tensors:
+        pinned memory is mapped into the device address space, so K1 reads the broadcast query
+        batch straight from host memory and K6 stores the merged lists straight back — no
+        staging copies around the kernels. Falls back to explicit copies when the fused
+        exchange is not active. Synchronises before returning."""
+        import torch
+        B = int(h_queries.shape[0])
+        stream = torch.cuda.current_stream(device).cuda_stream
+        fused = self.world > 1 and self.exchange != "nccl" and self._peer is not None and \
+            (self._peer.B, self._peer.k) == (B, k) and h_queries.is_pinned() and h_ids.is_pinned() and \
+            h_dists.is_pinned() and h_counts.is_pinned()
+        if not fused:
+            r_ids, r_d, r_c = self.search_batch_device(h_queries.to(device, non_blocking=True), k, search_size,
+                                                       max_search_limit)
+            h_ids.copy_(r_ids, non_blocking=True)
+            h_dists.copy_(r_d, non_blocking=True)
+            h_counts.copy_(r_c, non_blocking=True)
+            torch.cuda.synchronize(device)
+            return
+        l_ids, l_d, l_c = self._bufs[0], self._bufs[1], self._bufs[2]
+        pb = self._peer
+        pb.epoch += 1
+        par = pb.epoch & 1
+        pg = pb._pg[par]
+        pg.per_shard_limit = shard_limit(k, self.world, max_search_limit)
+        lib = _capi.lib()
+        di = device.index or 0
+        _capi.check(lib.sdb_search_batch_gather_device(self.index._h, B, h_queries.data_ptr(), k, search_size,
+                                                       l_ids.data_ptr(), l_d.data_ptr(), l_c.data_ptr(), C.byref(pg), stream))
+        _capi.check(lib.sdb_peer_barrier_device(di, self.world, self.rank, pb._flags, pb.epoch, stream))
+        g_i, g_dd, g_cc = pb.local(par)
+        _capi.check(lib.sdb_merge_topk_device(di, self.world, B, k, g_i, g_dd, g_cc, h_ids.data_ptr(), h_dists.data_ptr(),
+                                              h_counts.data_ptr(), stream))
+        torch.cuda.synchronize(device)
+
     def search_batch_device(self, d_queries, k: int, search_size: int, max_search_limit: int = 75):
         """d_queries: [B, dim] f32 CUDA tensor, identical on every rank (broadcast by the
         caller). Returns merged (global ids [B,k] int64, dists [B,k], counts [B]) on every rank."""

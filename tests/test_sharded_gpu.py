@@ -150,6 +150,15 @@ def _p2p_worker(rank, world, port, out_dir):
         got = b.search_batch_device(d_q, k, 75)
         torch.cuda.synchronize()
         same = same and all(bool((x == y).all().item()) for x, y in zip(got, ref))
+    # host-facing twin: pinned buffers read / written in place by the kernels
+    h_q = torch.from_numpy(Q).pin_memory()
+    h_i = torch.zeros((B, k), dtype=torch.int64).pin_memory()
+    h_d = torch.zeros((B, k), dtype=torch.float32).pin_memory()
+    h_c = torch.zeros((B,), dtype=torch.int32).pin_memory()
+    for _ in range(2):
+        b.search_batch_pinned(h_q, k, 75, h_i, h_d, h_c, dev)
+        same = same and bool((h_i == ref[0].cpu()).all()) and bool((h_d == ref[1].cpu()).all()) and \
+            bool((h_c == ref[2].cpu()).all())
     failed = b._peer.barrier_failed()
     np.savez(os.path.join(out_dir, f"p2p{rank}.npz"), same=same, failed=failed, ids=ref[0].cpu().numpy())
     dist.barrier()
