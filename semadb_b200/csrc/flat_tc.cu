@@ -362,31 +362,44 @@ __device__ __forceinline__ void t5_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ void t5_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void t5_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-constexpr int T5_HITS = 16;  // survivors parked per epilogue thread between flushes
+constexpr int T5_HITS = 8;    // survivors parked per epilogue thread between flushes
+constexpr int T5_ESTAGES = 2;  // ring of extension blocks
+constexpr uint32_t T5_QEXT_BYTES = T5_M * 32;   // extension block of the query tile: 16 bf16 = 32 B per row
+constexpr uint32_t T5_XEXT_BYTES = T5_N * 32;   // extension block of a point tile
 struct T5Smem {  // offsets from the 1024-byte aligned base
-  uint32_t q, x, xn, hits, bars, tmem_slot, total;
+  uint32_t q, qe, x, xe, hits, bars, tmem_slot, total;
   int stages;
 };
+// nkb = data K blocks (64 wide); the extension travels as a 16-wide block of 32-byte rows
+// (SWIZZLE_32B) in its own small ring: a quarter of the bytes a 64-wide block would move
 __host__ __device__ inline T5Smem t5_layout(uint32_t nkb, int stages) {
   T5Smem L;
   L.stages = stages;
   L.q = 0;
-  L.x = T5_QT * nkb * T5_QBLK_BYTES;
-  L.xn = L.x + uint32_t(stages) * T5_XBLK_BYTES;
-  L.hits = L.xn;
+  L.qe = T5_QT * nkb * T5_QBLK_BYTES;
+  L.x = L.qe + ((T5_QT * T5_QEXT_BYTES + 1023u) & ~1023u);
+  L.xe = L.x + uint32_t(stages) * T5_XBLK_BYTES;
+  L.hits = L.xe + T5_ESTAGES * T5_XEXT_BYTES;
   L.bars = L.hits + T5_EPI_THREADS * T5_HITS * 4;
-  L.tmem_slot = L.bars + (2 * uint32_t(stages) + 5) * 8;
+  L.tmem_slot = L.bars + (2 * uint32_t(stages) + 2 * T5_ESTAGES + 5) * 8;
   L.total = L.tmem_slot + 16;
   return L;
 }
 
+// K-major operand with 32-byte rows (one K16 step wide), 32-byte swizzle: 8-row groups 256 B apart
+__device__ __forceinline__ uint64_t t5_smem_desc_sw32(uint32_t addr) {
+  return uint64_t((addr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t(256 >> 4) << 32) | (uint64_t(1) << 46) |
+         (uint64_t(6) << 61);
+}
+
 __global__ void __launch_bounds__(T5_THREADS, 1)
-tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, TcArgs a, int stages) {
+tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
+                  const __grid_constant__ CUtensorMap map_qe, const __grid_constant__ CUtensorMap map_xe, TcArgs a, int stages) {
   extern __shared__ unsigned char t5_raw[];
   const uint32_t raw = smem_u32(t5_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   unsigned char* gbase = t5_raw + (base - raw);
-  const uint32_t nkb = a.pitch / T5_KB;  // data K blocks + the extension block (bias, threshold)
+  const uint32_t nkb = a.kp / T5_KB;  // data K blocks; the extension block (bias, threshold) has its own ring
   const T5Smem L = t5_layout(nkb, stages);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // barriers: full[s], empty[s], q_full, tmem_full[2], tmem_empty[2]
@@ -395,6 +408,8 @@ tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   const uint32_t bar_q = base + L.bars + uint32_t(2 * stages) * 8;
   auto bar_tfull = [&](int i) { return base + L.bars + uint32_t(2 * stages + 1 + i) * 8; };
   auto bar_tempty = [&](int i) { return base + L.bars + uint32_t(2 * stages + 3 + i) * 8; };
+  auto bar_efull = [&](int i) { return base + L.bars + uint32_t(2 * stages + 5 + i) * 8; };
+  auto bar_eempty = [&](int i) { return base + L.bars + uint32_t(2 * stages + 5 + T5_ESTAGES + i) * 8; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + L.tmem_slot);
 
   const uint32_t q0 = blockIdx.x * (T5_M * T5_QT);
@@ -412,6 +427,10 @@ tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       t5_mbar_init(bar_tfull(i), 1);
       t5_mbar_init(bar_tempty(i), T5_EPI_THREADS / 32);
     }
+    for (int i = 0; i < T5_ESTAGES; ++i) {
+      t5_mbar_init(bar_efull(i), 1);
+      t5_mbar_init(bar_eempty(i), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: all 512 columns (two 256-column accumulators)
@@ -426,12 +445,14 @@ tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      t5_mbar_expect_tx(bar_q, T5_QT * nkb * T5_QBLK_BYTES);
-      for (uint32_t qt = 0; qt < T5_QT; ++qt)
+      t5_mbar_expect_tx(bar_q, T5_QT * (nkb * T5_QBLK_BYTES + T5_QEXT_BYTES));
+      for (uint32_t qt = 0; qt < T5_QT; ++qt) {
         for (uint32_t kb = 0; kb < nkb; ++kb)
           t5_tma_load_2d(base + L.q + (qt * nkb + kb) * T5_QBLK_BYTES, &map_q, int32_t(kb * T5_KB), int32_t(q0 + qt * T5_M), bar_q);
-      int s = 0;
-      uint32_t ph = 0;
+        t5_tma_load_2d(base + L.qe + qt * T5_QEXT_BYTES, &map_qe, int32_t(a.kp), int32_t(q0 + qt * T5_M), bar_q);
+      }
+      int s = 0, es = 0;
+      uint32_t ph = 0, eph = 0;
       for (uint32_t t = tile_begin; t < tile_end; ++t) {
         const int32_t p0 = int32_t(a.first_id + t * T5_N);
         for (uint32_t kb = 0; kb < nkb; ++kb) {
@@ -440,6 +461,10 @@ tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           t5_tma_load_2d(base + L.x + uint32_t(s) * T5_XBLK_BYTES, &map_x, int32_t(kb * T5_KB), p0, bar_full(s));
           if (++s == stages) { s = 0; ph ^= 1u; }
         }
+        t5_mbar_wait(bar_eempty(es), eph ^ 1u);
+        t5_mbar_expect_tx(bar_efull(es), T5_XEXT_BYTES);
+        t5_tma_load_2d(base + L.xe + uint32_t(es) * T5_XEXT_BYTES, &map_xe, int32_t(a.kp), p0, bar_efull(es));
+        if (++es == T5_ESTAGES) { es = 0; eph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -447,8 +472,8 @@ tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     if (lane == 0) {
       t5_mbar_wait(bar_q, 0);
       t5_fence_after();
-      int s = 0;
-      uint32_t ph = 0;
+      int s = 0, es = 0;
+      uint32_t ph = 0, eph = 0;
       uint32_t it = 0;
       for (uint32_t t = tile_begin; t < tile_end; ++t, ++it) {
         const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
@@ -459,15 +484,23 @@ tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           t5_mbar_wait(bar_full(s), ph);
           t5_fence_after();
           const uint64_t bdesc = t5_smem_desc(base + L.x + uint32_t(s) * T5_XBLK_BYTES);
-          const uint32_t ksteps = kb + 1 == nkb ? 1u : uint32_t(T5_KB / 16);  // the extension is one K16 step
           for (uint32_t qt = 0; qt < T5_QT; ++qt) {
             const uint64_t adesc = t5_smem_desc(base + L.q + (qt * nkb + kb) * T5_QBLK_BYTES);
-            for (uint32_t k = 0; k < ksteps; ++k)  // +32 B per K step inside the swizzle row
+#pragma unroll
+            for (uint32_t k = 0; k < T5_KB / 16; ++k)  // +32 B per K step inside the swizzle row
               t5_mma(d_tmem + qt * T5_N, adesc + 2 * k, bdesc + 2 * k, (kb | k) != 0 ? 1u : 0u);
           }
           t5_commit(bar_empty(s));  // stage free once these MMAs have read it
           if (++s == stages) { s = 0; ph ^= 1u; }
         }
+        // the K extension (bias, threshold): one K16 step from the 32-byte-row ring
+        t5_mbar_wait(bar_efull(es), eph);
+        t5_fence_after();
+        for (uint32_t qt = 0; qt < T5_QT; ++qt)
+          t5_mma(d_tmem + qt * T5_N, t5_smem_desc_sw32(base + L.qe + qt * T5_QEXT_BYTES),
+                 t5_smem_desc_sw32(base + L.xe + uint32_t(es) * T5_XEXT_BYTES), 1u);
+        t5_commit(bar_eempty(es));
+        if (++es == T5_ESTAGES) { es = 0; eph ^= 1u; }
         t5_commit(bar_tfull(acc));  // accumulator complete
       }
     }
@@ -545,17 +578,18 @@ PFN_cuTensorMapEncodeTiled_v12000 t5_encode_fn() {
   return fn;
 }
 
-// [rows][kp] bf16 row-major -> boxes of box_rows x 64 elements, 128-byte swizzle
-int t5_make_map(CUtensorMap* map, const void* ptr, uint32_t rows, uint32_t kp, uint32_t box_rows) {
+// [rows][pitch] bf16 row-major -> boxes of box_rows x box_cols elements: 64 columns with the
+// 128-byte swizzle (data K blocks), 16 columns with the 32-byte swizzle (the K extension)
+int t5_make_map(CUtensorMap* map, const void* ptr, uint32_t rows, uint32_t pitch, uint32_t box_rows, uint32_t box_cols) {
   auto fn = t5_encode_fn();
   if (!fn) return fail(SDB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-  cuuint64_t gdim[2] = {kp, rows};
-  cuuint64_t gstride[1] = {cuuint64_t(kp) * 2};
-  cuuint32_t box[2] = {T5_KB, box_rows};
+  cuuint64_t gdim[2] = {pitch, rows};
+  cuuint64_t gstride[1] = {cuuint64_t(pitch) * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SDB_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string(int(r)));
   return SDB_OK;
 }
@@ -564,14 +598,17 @@ int t5_make_map(CUtensorMap* map, const void* ptr, uint32_t rows, uint32_t kp, u
 bool t5_eligible(uint32_t kp) { return kp <= 384 && !getenv("SDB_FLAT_MMA_SYNC"); }
 
 int launch_tc5_filter(sdb_index* ix, TcArgs ta, uint32_t B_pad, cudaStream_t stream) {
-  const uint32_t nkb = ta.pitch / T5_KB;
-  int stages = int((206u * 1024u - T5_QT * nkb * T5_QBLK_BYTES) / T5_XBLK_BYTES);
+  const uint32_t nkb = ta.kp / T5_KB;
+  const uint32_t fixed = t5_layout(nkb, 0).total + 1024;
+  int stages = int((227u * 1024u - fixed) / T5_XBLK_BYTES);
   if (stages > 8) stages = 8;
   const T5Smem L = t5_layout(nkb, stages);
   const size_t smem = size_t(L.total) + 1024;
-  CUtensorMap mq, mx;
+  CUtensorMap mq, mx, mqe, mxe;
   int rc;
-  if ((rc = t5_make_map(&mq, ta.q16, B_pad, ta.pitch, T5_M)) || (rc = t5_make_map(&mx, ta.x16, ta.rows_alloc, ta.pitch, T5_N))) return rc;
+  if ((rc = t5_make_map(&mq, ta.q16, B_pad, ta.pitch, T5_M, T5_KB)) || (rc = t5_make_map(&mx, ta.x16, ta.rows_alloc, ta.pitch, T5_N, T5_KB)) ||
+      (rc = t5_make_map(&mqe, ta.q16, B_pad, ta.pitch, T5_M, 16)) || (rc = t5_make_map(&mxe, ta.x16, ta.rows_alloc, ta.pitch, T5_N, 16)))
+    return rc;
   static size_t attr_smem = 0;
   if (attr_smem < smem) {
     SDB_CUDA(cudaFuncSetAttribute(tc5_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -595,7 +632,7 @@ int launch_tc5_filter(sdb_index* ix, TcArgs ta, uint32_t B_pad, cudaStream_t str
   }
   ta.tiles_per_cta = (ntiles + ysplit - 1) / ysplit;
   ysplit = (ntiles + ta.tiles_per_cta - 1) / ta.tiles_per_cta;
-  tc5_filter_kernel<<<dim3(qtiles, ysplit), T5_THREADS, smem, stream>>>(mq, mx, ta, stages);
+  tc5_filter_kernel<<<dim3(qtiles, ysplit), T5_THREADS, smem, stream>>>(mq, mx, mqe, mxe, ta, stages);
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;
 }
