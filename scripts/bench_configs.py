@@ -48,8 +48,9 @@ def time_search(g, Q, steps=10, warmup=3):
     d = torch.zeros((B, K), dtype=torch.float32, device=dev)
     c = torch.zeros((B,), dtype=torch.int32, device=dev)
     st = torch.cuda.current_stream()
-    for _ in range(warmup):
+    for _ in range(warmup + 2):
         g.search_batch_device(d_q, K, L, ids, d, c, st.cuda_stream)
+        torch.cuda.synchronize()  # the visited-table size adapts between searches that find the stream idle
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)

@@ -609,7 +609,8 @@ int launch_tc5_filter(sdb_index* ix, TcArgs ta, uint32_t B_pad, cudaStream_t str
   if ((rc = t5_make_map(&mq, ta.q16, B_pad, ta.pitch, T5_M, T5_KB)) || (rc = t5_make_map(&mx, ta.x16, ta.rows_alloc, ta.pitch, T5_N, T5_KB)) ||
       (rc = t5_make_map(&mqe, ta.q16, B_pad, ta.pitch, T5_M, 16)) || (rc = t5_make_map(&mxe, ta.x16, ta.rows_alloc, ta.pitch, T5_N, 16)))
     return rc;
-  static size_t attr_smem = 0;
+  static size_t attr_smem_dev[64] = {};  // cudaFuncSetAttribute is per device
+  size_t& attr_smem = attr_smem_dev[ix->device & 63];
   if (attr_smem < smem) {
     SDB_CUDA(cudaFuncSetAttribute(tc5_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     attr_smem = smem;
@@ -637,12 +638,24 @@ int launch_tc5_filter(sdb_index* ix, TcArgs ta, uint32_t B_pad, cudaStream_t str
   return SDB_OK;
 }
 
+// Levels cover disjoint point ranges: a level's candidate list starts with the exact top-k of
+// everything before it, so its re-score yields the exact top-k of the whole prefix.
+__global__ void seed_cand_kernel(const uint64_t* prev_ids, const uint32_t* prev_cnt, uint32_t k, uint32_t B, uint32_t* cand,
+                                 uint32_t* cand_cnt) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= B) return;
+  const uint32_t c = min(prev_cnt[q], k);
+  for (uint32_t i = 0; i < c; ++i) cand[size_t(q) * CAND_CAP + i] = uint32_t(prev_ids[size_t(q) * k + i]);
+  cand_cnt[q] = c;
+}
+
 // Exact re-score of one query's candidates + top-k by (distance asc, id asc). One CTA per query.
 template <int METRIC>
 __global__ void __launch_bounds__(128) rescore_kernel(const float* vec, uint32_t vec_pitch, uint32_t dim, const float* queries,
                                                       const uint32_t* cand, const uint32_t* cand_cnt, uint32_t k,
                                                       uint64_t* out_ids, float* out_d, uint32_t* out_cnt,
-                                                      uint32_t* overflow_list, uint32_t* overflow_cnt, int last_level) {
+                                                      uint32_t* overflow_list, uint32_t* overflow_cnt, uint32_t* overflow_flag,
+                                                      int last_level) {
   __shared__ float s_d[CAND_CAP];
   __shared__ uint32_t s_id[CAND_CAP];
   __shared__ float s_bd[4];
@@ -652,12 +665,12 @@ __global__ void __launch_bounds__(128) rescore_kernel(const float* vec, uint32_t
   const int tid = threadIdx.x, lane = tid & 31, g = lane & 7, grp = tid >> 3;  // 16 groups
   const uint32_t n = cand_cnt[q];
   if (n > CAND_CAP) {
-    // last level: the query goes to the exact scan. Earlier levels only produce a bound for the
-    // next one: keep the previous bound by reporting "fewer than k results" (threshold = +inf
-    // would let everything pass), i.e. leave the level's outputs as they were.
-    if (tid == 0 && last_level) {
-      overflow_list[atomicAdd(overflow_cnt, 1u)] = q;
-      out_cnt[q] = 0;
+    // Levels cover disjoint point ranges, so a list that overflowed at any level has lost
+    // candidates for good: the query goes to the exact scan after the last level (once: the
+    // per-query flag). Its outputs of this level stay as they were (the previous bound).
+    if (tid == 0) {
+      if (atomicExch(&overflow_flag[q], 1u) == 0u) overflow_list[atomicAdd(overflow_cnt, 1u)] = q;
+      if (last_level) out_cnt[q] = 0;
     }
     return;
   }
@@ -814,20 +827,22 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
     ix->tc_epoch = ix->vec_epoch;
   }
   if ((rc = ix->d_q16.ensure(size_t(B_pad) * pitch)) || (rc = ix->d_qn.ensure(B_pad)) || (rc = ix->d_thr.ensure(B_pad)) ||
-      (rc = ix->d_cand.ensure(size_t(B) * CAND_CAP)) || (rc = ix->d_candcnt.ensure(size_t(B) * 2 + 8)) ||
+      (rc = ix->d_cand.ensure(size_t(B) * CAND_CAP)) || (rc = ix->d_candcnt.ensure(size_t(B) * 3 + 8)) ||
       (rc = ix->d_sample_ids.ensure(size_t(B) * k)) || (rc = ix->d_sample_d.ensure(size_t(B) * k)) ||
       (rc = ix->d_sample_cnt.ensure(B)))
     return rc;
   uint32_t* d_cnt = ix->d_candcnt.p;            // [B] candidate counts
   uint32_t* d_ovf_list = ix->d_candcnt.p + B;   // [B] overflowed queries
   uint32_t* d_misc = ix->d_candcnt.p + 2 * size_t(B);  // [0] xmax bits, [1] overflow count
-  SDB_CUDA(cudaMemsetAsync(d_misc, 0, 8 * sizeof(uint32_t), stream));
+  uint32_t* d_ovf_flag = d_misc + 8;                   // [B] query already on the overflow list
+  SDB_CUDA(cudaMemsetAsync(d_misc, 0, (8 + size_t(B)) * sizeof(uint32_t), stream));
   to_bf16_kernel<<<(B_pad + 7) / 8, 256, 0, stream>>>(d_queries, dim, dim, B, B_pad, reinterpret_cast<__nv_bfloat16*>(ix->d_q16.p),
                                                      kp, pitch, l2 ? -2.0f : -1.0f, ix->d_qn.p);
   xmax_kernel<<<(end_id - first_id + 255) / 256, 256, 0, stream>>>(ix->d_xn.p, ix->d_exists, first_id, end_id, d_misc);
   ix->launches += 2;
   SDB_CUDA(cudaGetLastError());
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};  // cudaFuncSetAttribute is per device
+  bool& attr_set = attr_set_dev[ix->device & 63];
   if (!attr_set) {
     SDB_CUDA(cudaFuncSetAttribute(tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TC_SMEM)));
     attr_set = true;
@@ -841,23 +856,27 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
   const uint32_t qtiles = B_pad / TM;
   const size_t qsmem = size_t((dim + 3) & ~3u) * sizeof(float);
   uint64_t covered = level0_points();
+  uint32_t lvl_begin = first_id + uint32_t(covered);  // levels cover disjoint ranges [lvl_begin, lvl_end)
   while (covered < npts) {
     covered = std::min<uint64_t>(npts, covered * LEVEL_RATIO);
-    const bool last = covered >= npts;
-    const uint32_t lvl_end = last ? end_id : first_id + uint32_t(covered);
+    // whole 256-point tiles: what a level scans past its nominal end is not scanned again
+    uint64_t span = (first_id + covered - lvl_begin + 255) / 256 * 256;
+    const bool last = lvl_begin + span >= end_id;
+    const uint32_t lvl_end = last ? end_id : lvl_begin + uint32_t(span);
+    covered = lvl_end - first_id;
     // thresholds from the previous level's exact top-k
     thresh_kernel<<<(B_pad + 127) / 128, 128, 0, stream>>>(ix->d_sample_d.p, ix->d_sample_cnt.p, k, ix->d_qn.p, d_misc,
                                                            ix->store_metric, dim, B, B_pad, ix->d_thr.p,
                                                            reinterpret_cast<__nv_bfloat16*>(ix->d_q16.p), kp, pitch);
-    SDB_CUDA(cudaMemsetAsync(d_cnt, 0, size_t(B) * sizeof(uint32_t), stream));
+    seed_cand_kernel<<<(B + 127) / 128, 128, 0, stream>>>(ix->d_sample_ids.p, ix->d_sample_cnt.p, k, B, ix->d_cand.p, d_cnt);
     TcArgs ta{};
     ta.q16 = reinterpret_cast<const __nv_bfloat16*>(ix->d_q16.p);
     ta.x16 = reinterpret_cast<const __nv_bfloat16*>(ix->d_x16.p);
     ta.xn = ix->d_xn.p; ta.thr = ix->d_thr.p; ta.exists = ix->d_exists;
-    ta.kp = kp; ta.pitch = pitch; ta.first_id = first_id; ta.end_id = lvl_end;
+    ta.kp = kp; ta.pitch = pitch; ta.first_id = lvl_begin; ta.end_id = lvl_end;
     ta.l2 = l2;
     ta.cand = ix->d_cand.p; ta.cand_cnt = d_cnt; ta.B = B;
-    const uint32_t ntiles = (lvl_end - first_id + TN - 1) / TN;
+    const uint32_t ntiles = (lvl_end - lvl_begin + TN - 1) / TN;
     // ~6 waves of CTAs (2 resident per SM) so the last wave's imbalance stays small
     uint32_t ysplit = std::max<uint32_t>(1, (uint32_t(ix->sm_count) * 12 + qtiles - 1) / qtiles);
     ysplit = std::min(ysplit, ntiles);
@@ -878,15 +897,15 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
     switch (ix->store_metric) {
       case SDB_METRIC_EUCLIDEAN:
         rescore_kernel<METRIC_EUCLIDEAN><<<B, 128, qsmem, stream>>>(ix->d_vec, ix->vec_pitch, dim, d_queries, ix->d_cand.p, d_cnt, k,
-                                                                    o_ids, o_d, o_c, d_ovf_list, d_misc + 1, last ? 1 : 0);
+                                                                    o_ids, o_d, o_c, d_ovf_list, d_misc + 1, d_ovf_flag, last ? 1 : 0);
         break;
       case SDB_METRIC_DOT:
         rescore_kernel<METRIC_DOT><<<B, 128, qsmem, stream>>>(ix->d_vec, ix->vec_pitch, dim, d_queries, ix->d_cand.p, d_cnt, k, o_ids,
-                                                              o_d, o_c, d_ovf_list, d_misc + 1, last ? 1 : 0);
+                                                              o_d, o_c, d_ovf_list, d_misc + 1, d_ovf_flag, last ? 1 : 0);
         break;
       default:
         rescore_kernel<METRIC_COSINE><<<B, 128, qsmem, stream>>>(ix->d_vec, ix->vec_pitch, dim, d_queries, ix->d_cand.p, d_cnt, k,
-                                                                 o_ids, o_d, o_c, d_ovf_list, d_misc + 1, last ? 1 : 0);
+                                                                 o_ids, o_d, o_c, d_ovf_list, d_misc + 1, d_ovf_flag, last ? 1 : 0);
         break;
     }
     ix->launches += 3;
@@ -899,10 +918,11 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
       uint32_t mx = 0;
       for (uint32_t v : h) { tot += v; mx = std::max(mx, v); }
       fprintf(stderr, "[sdb] flat tc level over %u points: %u queries, %.1f candidates/query (max %u, cap %u)\n",
-              lvl_end - first_id, B, double(tot) / B, mx, CAND_CAP);
+              lvl_end - lvl_begin, B, double(tot) / B, mx, CAND_CAP);
     }
+    lvl_begin = lvl_end;
   }
-  // ---- queries whose candidate list overflowed on the last level: exact scan
+  // ---- queries whose candidate list overflowed at some level: exact scan
   uint32_t h_ovf = 0;
   SDB_CUDA(cudaMemcpyAsync(&h_ovf, d_misc + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
   {

@@ -323,6 +323,11 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
     size_t budget = std::min<size_t>(ix->smem_optin, size_t(100) << 10);
     size_t dyn_budget = budget > static_smem ? budget - static_smem : 0;
     int staged_max = int(std::min<size_t>(MAX_CAND, dyn_budget / view.row_bytes));
+    // ... but no more than 32 KB of rows (at least 32 rows if they fit): a back-edge prune has 65
+    // candidates, and residency beats staging the long tail of a visited list — 1M x 128 builds in
+    // 1.12 s with 64 staged rows, 1.19 s with 96, 1.26 s with 128, 1.35 s with 186 (profiles/r01_ab_insert.txt)
+    staged_max = std::min(staged_max, std::max(int((size_t(32) << 10) / view.row_bytes), std::min(32, staged_max)));
+    if (const char* e = getenv("SDB_STAGED_MAX")) staged_max = std::max(1, std::min(staged_max, atoi(e)));  // A/B knob
     size_t dyn_smem = PruneShared::bytes(MAX_CAND + 1) + size_t(staged_max) * view.row_bytes;
     INS_CUDA(cudaFuncSetAttribute(prune_new_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn_smem)));
     INS_CUDA(cudaFuncSetAttribute(backedge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn_smem)));

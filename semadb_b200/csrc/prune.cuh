@@ -10,7 +10,7 @@ namespace sdb {
 
 constexpr int PRUNE_THREADS = 256;
 constexpr int PRUNE_GROUPS = PRUNE_THREADS / 8;
-constexpr int MAX_CAND = 256;  // visited-list capacity handed to robustPrune
+constexpr int MAX_CAND = 512;  // visited-list capacity handed to robustPrune (hamming shards of 6M points expand > 256 nodes for some inserts)
 
 struct StoreView {
   int mode;  // 0 float rows, 1 bit rows, 2 PQ codes (SDC)

@@ -74,15 +74,19 @@ int launch_with_retry(sdb_index* ix, SearchArgs a, cudaStream_t stream) {
   if (rc) return rc;
   // second pass over queries whose visited set overflowed (normally none): u32 table, 32768 slots
   a.work_counter = a.work_counter + 2;
-  constexpr int RK = (KIND == EVAL_FLOAT_FIXED) ? EVAL_FLOAT_GENERIC : (KIND == EVAL_ADC_SMEM) ? EVAL_ADC : KIND;
-  constexpr int RT = (KIND == EVAL_BITS) ? TRIPS : 1;  // bit rows: chunks per row must still cover the row
+  // same evaluator as the first pass (a re-run query walks ~80 hops alone on its SM: the
+  // pipelined row gather is what keeps that under a millisecond); the ADC table goes back to
+  // global memory because the u32 visited table takes the shared memory
+  constexpr int RK = (KIND == EVAL_ADC_SMEM) ? EVAL_ADC : KIND;
+  constexpr int RT = (KIND == EVAL_BITS || KIND == EVAL_FLOAT_FIXED) ? TRIPS : 1;  // rows must still be covered
+  constexpr int RS = (KIND == EVAL_BITS || KIND == EVAL_FLOAT_FIXED) ? SETS : 1;
   if (getenv("SDB_DEBUG_RETRY")) {
     uint32_t h[2] = {0, 0};
     cudaStreamSynchronize(stream);
     cudaMemcpy(h, a.work_counter - 2, sizeof(h), cudaMemcpyDeviceToHost);
     fprintf(stderr, "[sdb] beam search: %u of %u queries overflowed the compact visited table -> retry launch\n", h[1], a.B);
   }
-  return launch_variant<RK, METRIC, RT, 1, false, 0, VisitedTable<15>, FILTER, true, 1>(ix, a, stream);
+  return launch_variant<RK, METRIC, RT, RS, false, 0, VisitedTable<15>, FILTER, true, 1>(ix, a, stream);
 }
 
 // Tuning knob for A/B runs on the GPU (not part of the ABI): SDB_K1_VARIANT picks the
@@ -121,12 +125,15 @@ int launch_search(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k,
                   uint32_t* d_vis_len, uint32_t vis_cap, const uint32_t* d_filter_seed, uint32_t n_filter_seed,
                   const uint32_t* d_filter_bits, cudaStream_t stream) {
   // Visited-table size for this launch: start at 5888 slots; if the previous search on this
-  // handle sent more than 1 % of its queries to the RETRY launch (they visited more nodes than
+  // handle sent more than 0.1 % of its queries to the RETRY launch (they visited more nodes than
   // 87.5 % of the table), step up. Read only when the stream is idle: never adds a sync.
   if (ix->retry_check_pending && cudaStreamQuery(ix->last_search_stream) == cudaSuccess) {
     uint32_t h_retry = 0;
     SDB_CUDA(cudaMemcpy(&h_retry, ix->d_work.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    if (uint64_t(h_retry) * 100 > ix->last_B && ix->vt_level < 2) ix->vt_level++;
+    // A re-run query costs about as much as a whole first-pass wave (it walks its ~80 hops
+    // alone on an SM), so a handful per batch already outweighs the ~5-10 % the bigger table
+    // costs everybody: step up above 0.1 % of the batch (or any at all in a small batch).
+    if ((uint64_t(h_retry) * 1000 > ix->last_B || (h_retry > 0 && ix->last_B <= 2000)) && ix->vt_level < 2) ix->vt_level++;
     ix->retry_check_pending = false;
   }
   int rc;

@@ -604,11 +604,12 @@ struct FloatEvalFixed {
   }
   __device__ __forceinline__ void issue(const SearchArgs& a, const uint32_t* cid, int n, int s, int g, int grp,
                                         float4 (&v)[TRIPS]) {
-    // groups past the end read the start node's row instead (cache-hot, no branch, result
-    // discarded) so every load is unconditional — not the query's own row, which may live in
-    // mapped host memory
+    // groups past the end re-read the hop's first candidate row (this warp's own, cache-hot;
+    // no branch, result discarded) so every load is unconditional. Not the query's own row,
+    // which may live in mapped host memory, and not one fixed row for everybody: a single
+    // line hammered by every warp of the GPU cost C1 (L2-resident) two thirds of its QPS.
     const int ci = s * 4 + grp;
-    const float* row = a.vec + size_t(ci < n ? cid[ci] : START_ID) * a.vec_pitch + 4 * g;
+    const float* row = a.vec + size_t(cid[ci < n ? ci : 0]) * a.vec_pitch + 4 * g;
 #pragma unroll
     for (int t = 0; t < TRIPS; ++t) v[t] = ldg_f4_stream(row + 32 * t);
   }
