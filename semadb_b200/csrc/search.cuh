@@ -14,6 +14,10 @@
 //     slot, bubble while strictly smaller).
 // Algorithmic bytes per query = n_dist*row_bytes + n_hops*R*4; the
 // kernel reports n_hops and n_dist per query.
+// Evaluators: f32 rows (fixed dims pipelined, any dim generic), bit rows (hamming / jaccard),
+// PQ codes against the query's ADC table in global or in shared memory (bulk async copy).
+// Epilogue: the top-k goes to the caller's buffers (device, or mapped host memory) and, for a
+// sharded search, straight into every peer GPU's gather buffer (PeerGather).
 #pragma once
 #include "common.cuh"
 
@@ -593,10 +597,8 @@ struct FloatEvalFixed {
   static constexpr bool QREG = (TRIPS <= 4);
   float4 q[QREG ? TRIPS : 1];
   const float* qs;
-  const float* qglobal;
   __device__ __forceinline__ void load_query(const float* qsmem, const float* qg, int lane) {
     qs = qsmem;
-    qglobal = qg;
     if (QREG) {
 #pragma unroll
       for (int t = 0; t < TRIPS; ++t) q[t] = ldg_f4(qg + 32 * t + 4 * (lane & 7));
