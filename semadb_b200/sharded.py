@@ -154,8 +154,8 @@ class ShardedSearcher:
                             max_search_limit: int = 75):
         """Host-facing twin of search_batch_device for page-locked (pinned) torch CPU tensors:
         pinned memory is mapped into the device address space, so K1 reads the broadcast query
-        batch straight from host memory and K6 stores the merged lists straight back — no
-        staging copies around the kernels. Falls back to explicit copies when the fused
+        batch straight from host memory (no staging copy in front of the kernel); the merged
+        lists come back with one small copy. Falls back to explicit copies when the fused
         exchange is not active. Synchronises before returning."""
         import torch
         B = int(h_queries.shape[0])
@@ -183,8 +183,15 @@ class ShardedSearcher:
                                                        l_ids.data_ptr(), l_d.data_ptr(), l_c.data_ptr(), C.byref(pg), stream))
         _capi.check(lib.sdb_peer_barrier_device(di, self.world, self.rank, pb._flags, pb.epoch, stream))
         g_i, g_dd, g_cc = pb.local(par)
-        _capi.check(lib.sdb_merge_topk_device(di, self.world, B, k, g_i, g_dd, g_cc, h_ids.data_ptr(), h_dists.data_ptr(),
-                                              h_counts.data_ptr(), stream))
+        # The merge is a short kernel: its 300 k small stores would sit exposed on PCIe if they went
+        # to mapped host memory (measured: +0.3 ms per step at B = 10 k), so it writes device buffers
+        # and one 1.24 MB copy brings the lists back. K1's query reads stay zero-copy.
+        m_ids, m_d, m_c = self._bufs[3], self._bufs[4], self._bufs[5]
+        _capi.check(lib.sdb_merge_topk_device(di, self.world, B, k, g_i, g_dd, g_cc, m_ids.data_ptr(), m_d.data_ptr(),
+                                              m_c.data_ptr(), stream))
+        h_ids.copy_(m_ids, non_blocking=True)
+        h_dists.copy_(m_d, non_blocking=True)
+        h_counts.copy_(m_c, non_blocking=True)
         torch.cuda.synchronize(device)
 
     def search_batch_device(self, d_queries, k: int, search_size: int, max_search_limit: int = 75):
