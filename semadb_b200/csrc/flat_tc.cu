@@ -566,6 +566,237 @@ tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   }
 }
 
+
+// ================================================================================================
+// Two-SM form of the same pass (tcgen05 cta_group::2): a cluster of two CTAs on neighbouring SMs
+// works on 256 queries x 256 points per step. Each CTA keeps its own 128-query tile (its half of
+// M = 256) and loads only ITS HALF of every point tile (128 rows) — the pair's MMA reads both
+// halves, so the L2->SM bytes per SM and tile halve (36 KB instead of 72 KB), which is what
+// bounds the one-SM kernel. The leader CTA (cluster rank 0) issues the M256 x N256 x K16 MMAs;
+// both CTAs' TMA loads report to the leader's full barriers (cta_group::2 loads, peer bit of the
+// barrier address cleared); tcgen05.commit multicasts to both CTAs' empty / accumulator-full
+// barriers; both CTAs' epilogue warps arrive on the leader's accumulator-empty barrier.
+constexpr uint32_t T2_XBLK_BYTES = 128 * 128;  // this CTA's half of a point tile, one 64-wide K block
+constexpr uint32_t T2_XEXT_BYTES = 128 * 32;
+constexpr uint32_t T2_PEER_MASK = 0xFEFFFFFFu;  // clears the peer bit of a shared::cluster address: the even CTA's copy
+constexpr uint32_t T2_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(256 >> 3) << 17) | (uint32_t(256 >> 4) << 24);
+
+__host__ __device__ inline T5Smem t2_layout(uint32_t nkb, int stages) {
+  T5Smem L;
+  L.stages = stages;
+  L.q = 0;
+  L.qe = nkb * T5_QBLK_BYTES;
+  L.x = L.qe + ((T5_QEXT_BYTES + 1023u) & ~1023u);
+  L.xe = L.x + uint32_t(stages) * T2_XBLK_BYTES;
+  L.hits = L.xe + T5_ESTAGES * T2_XEXT_BYTES;
+  L.bars = L.hits + T5_EPI_THREADS * T5_HITS * 4;
+  L.tmem_slot = L.bars + (2 * uint32_t(stages) + 2 * T5_ESTAGES + 5) * 8;
+  L.total = L.tmem_slot + 16;
+  return L;
+}
+
+__device__ __forceinline__ uint32_t t2_cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void t2_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load into this CTA's shared memory, completion bytes reported to the LEADER CTA's barrier
+__device__ __forceinline__ void t2_tma_load_2d(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar & T2_PEER_MASK)
+      : "memory");
+}
+__device__ __forceinline__ void t2_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(T2_IDESC), "r"(accumulate), "r"(z)
+      : "memory");
+}
+// arrive once on the barrier at this offset in BOTH CTAs when the MMAs issued so far have completed
+__device__ __forceinline__ void t2_commit_both(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void t2_arrive_leader(uint32_t bar) {
+  // unqualified form (as CUTLASS's ClusterBarrier::arrive): the .release.cluster variant sat in the MIO
+  // queue for 42 % of all samples; what is ordered here are TMEM reads, fenced by tcgen05.fence before it
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & T2_PEER_MASK) : "memory");
+}
+
+__global__ void __launch_bounds__(T5_THREADS, 1)
+tc5x2_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
+                    const __grid_constant__ CUtensorMap map_qe, const __grid_constant__ CUtensorMap map_xe, TcArgs a, int stages) {
+  extern __shared__ unsigned char t5_raw[];
+  const uint32_t raw = smem_u32(t5_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  unsigned char* gbase = t5_raw + (base - raw);
+  const uint32_t nkb = a.kp / T5_KB;
+  const T5Smem L = t2_layout(nkb, stages);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = t2_cta_rank();
+  const bool leader = rank == 0;
+  auto bar_full = [&](int s) { return base + L.bars + uint32_t(s) * 8; };
+  auto bar_empty = [&](int s) { return base + L.bars + uint32_t(stages + s) * 8; };
+  const uint32_t bar_q = base + L.bars + uint32_t(2 * stages) * 8;
+  auto bar_tfull = [&](int i) { return base + L.bars + uint32_t(2 * stages + 1 + i) * 8; };
+  auto bar_tempty = [&](int i) { return base + L.bars + uint32_t(2 * stages + 3 + i) * 8; };
+  auto bar_efull = [&](int i) { return base + L.bars + uint32_t(2 * stages + 5 + i) * 8; };
+  auto bar_eempty = [&](int i) { return base + L.bars + uint32_t(2 * stages + 5 + T5_ESTAGES + i) * 8; };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + L.tmem_slot);
+
+  const uint32_t q0 = blockIdx.x * T5_M;  // this CTA's query tile; blockIdx.x = 2c, 2c+1 form a cluster
+  const uint32_t tile_begin = blockIdx.y * a.tiles_per_cta;
+  const uint32_t ntiles_total = (a.end_id - a.first_id + 255) / 256;
+  const uint32_t tile_end = min(tile_begin + a.tiles_per_cta, ntiles_total);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      t5_mbar_init(bar_full(s), 1);
+      t5_mbar_init(bar_empty(s), 1);
+    }
+    t5_mbar_init(bar_q, 1);
+    for (int i = 0; i < 2; ++i) {
+      t5_mbar_init(bar_tfull(i), 1);
+      t5_mbar_init(bar_tempty(i), 2 * (T5_EPI_THREADS / 32));  // both CTAs' epilogue warps
+    }
+    for (int i = 0; i < T5_ESTAGES; ++i) {
+      t5_mbar_init(bar_efull(i), 1);
+      t5_mbar_init(bar_eempty(i), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // both CTAs: the pair's TMEM (512 columns in each SM)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + L.tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  t5_fence_before();
+  __syncthreads();
+  t2_cluster_sync();  // the peer's barriers are initialised before anything signals them
+  t5_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own query tile, own half of every point tile =====
+    if (lane == 0) {
+      if (leader) t5_mbar_expect_tx(bar_q, 2 * (nkb * T5_QBLK_BYTES + T5_QEXT_BYTES));
+      for (uint32_t kb = 0; kb < nkb; ++kb)
+        t2_tma_load_2d(base + L.q + kb * T5_QBLK_BYTES, &map_q, int32_t(kb * T5_KB), int32_t(q0), bar_q);
+      t2_tma_load_2d(base + L.qe, &map_qe, int32_t(a.kp), int32_t(q0), bar_q);
+      int s = 0, es = 0;
+      uint32_t ph = 0, eph = 0;
+      for (uint32_t t = tile_begin; t < tile_end; ++t) {
+        const int32_t p0 = int32_t(a.first_id + t * 256 + rank * 128);
+        for (uint32_t kb = 0; kb < nkb; ++kb) {
+          t5_mbar_wait(bar_empty(s), ph ^ 1u);
+          if (leader) t5_mbar_expect_tx(bar_full(s), 2 * T2_XBLK_BYTES);
+          t2_tma_load_2d(base + L.x + uint32_t(s) * T2_XBLK_BYTES, &map_x, int32_t(kb * T5_KB), p0, bar_full(s));
+          if (++s == stages) { s = 0; ph ^= 1u; }
+        }
+        t5_mbar_wait(bar_eempty(es), eph ^ 1u);
+        if (leader) t5_mbar_expect_tx(bar_efull(es), 2 * T2_XEXT_BYTES);
+        t2_tma_load_2d(base + L.xe + uint32_t(es) * T2_XEXT_BYTES, &map_xe, int32_t(a.kp), p0, bar_efull(es));
+        if (++es == T5_ESTAGES) { es = 0; eph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: the leader CTA's elected lane drives both SMs' tensor cores =====
+    if (leader && lane == 0) {
+      t5_mbar_wait(bar_q, 0);
+      t5_fence_after();
+      int s = 0, es = 0;
+      uint32_t ph = 0, eph = 0;
+      uint32_t it = 0;
+      for (uint32_t t = tile_begin; t < tile_end; ++t, ++it) {
+        const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
+        t5_mbar_wait(bar_tempty(acc), aph ^ 1u);  // both epilogues have drained this accumulator
+        t5_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (uint32_t kb = 0; kb < nkb; ++kb) {
+          t5_mbar_wait(bar_full(s), ph);
+          t5_fence_after();
+          const uint64_t adesc = t5_smem_desc(base + L.q + kb * T5_QBLK_BYTES);
+          const uint64_t bdesc = t5_smem_desc(base + L.x + uint32_t(s) * T2_XBLK_BYTES);
+#pragma unroll
+          for (uint32_t k = 0; k < T5_KB / 16; ++k) t2_mma(d_tmem, adesc + 2 * k, bdesc + 2 * k, (kb | k) != 0 ? 1u : 0u);
+          t2_commit_both(bar_empty(s));
+          if (++s == stages) { s = 0; ph ^= 1u; }
+        }
+        t5_mbar_wait(bar_efull(es), eph);
+        t5_fence_after();
+        t2_mma(d_tmem, t5_smem_desc_sw32(base + L.qe), t5_smem_desc_sw32(base + L.xe + uint32_t(es) * T2_XEXT_BYTES), 1u);
+        t2_commit_both(bar_eempty(es));
+        if (++es == T5_ESTAGES) { es = 0; eph ^= 1u; }
+        t2_commit_both(bar_tfull(acc));
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): sign filter over this CTA's 128 queries x the tile's 256 points =====
+    const int e = warp - 2;
+    const int quad = warp & 3;
+    const int col0 = (e >> 2) * 128;
+    const int etid = threadIdx.x - 64;
+    const uint32_t q = q0 + uint32_t(quad) * 32 + lane;
+    const bool q_ok = q < a.B;
+    uint32_t* my_hits = reinterpret_cast<uint32_t*>(gbase + L.hits) + etid * T5_HITS;
+    int nh = 0;
+    auto flush_hits = [&]() {
+      if (nh && q_ok) {
+        uint32_t slot = atomicAdd(&a.cand_cnt[q], uint32_t(nh));
+        for (int i = 0; i < nh; ++i, ++slot)
+          if (slot < CAND_CAP) a.cand[size_t(q) * CAND_CAP + slot] = my_hits[i];
+      }
+      nh = 0;
+    };
+    uint32_t it = 0;
+    for (uint32_t t = tile_begin; t < tile_end; ++t, ++it) {
+      const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
+      const uint32_t p0 = a.first_id + t * 256;
+      t5_mbar_wait(bar_tfull(acc), aph);
+      t5_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * 256 + uint32_t(col0);
+      uint32_t v[2][32];
+      t5_ld32(taddr, v[0]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        t5_wait_ld();
+        if (c + 1 < 4) t5_ld32(taddr + uint32_t(c + 1) * 32, v[(c + 1) & 1]);
+        uint32_t mask = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mask = __funnelshift_l(v[c & 1][j], mask, 1);
+        while (mask) {
+          const int j = __clz(mask);
+          mask &= ~(0x80000000u >> j);
+          my_hits[nh++] = p0 + uint32_t(col0) + uint32_t(c) * 32 + uint32_t(j);
+          if (nh == T5_HITS) flush_hits();
+        }
+      }
+      t5_fence_before();
+      __syncwarp();
+      if (lane == 0) t2_arrive_leader(bar_tempty(acc));
+    }
+    flush_hits();
+  }
+  t5_fence_before();
+  __syncthreads();
+  t2_cluster_sync();  // nobody leaves while the peer may still read this CTA's shared memory or signal its barriers
+  if (warp == 1) {
+    t5_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 t5_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (!fn) {
@@ -633,6 +864,36 @@ int launch_tc5_filter(sdb_index* ix, TcArgs ta, uint32_t B_pad, cudaStream_t str
   }
   ta.tiles_per_cta = (ntiles + ysplit - 1) / ysplit;
   ysplit = (ntiles + ta.tiles_per_cta - 1) / ta.tiles_per_cta;
+  if (getenv("SDB_FLAT_2CTA") && qtiles % 2 == 0) {
+    // two-SM variant: X maps with 128-row boxes (each CTA loads its half of a point tile)
+    const uint32_t fixed2 = t2_layout(nkb, 0).total + 1024;
+    int st2 = int((227u * 1024u - fixed2) / T2_XBLK_BYTES);
+    if (st2 > 8) st2 = 8;
+    const size_t smem2 = size_t(t2_layout(nkb, st2).total) + 1024;
+    CUtensorMap mx2, mxe2;
+    if ((rc = t5_make_map(&mx2, ta.x16, ta.rows_alloc, ta.pitch, 128, T5_KB)) || (rc = t5_make_map(&mxe2, ta.x16, ta.rows_alloc, ta.pitch, 128, 16)))
+      return rc;
+    static size_t attr2_dev[64] = {};
+    if (attr2_dev[ix->device & 63] < smem2) {
+      SDB_CUDA(cudaFuncSetAttribute(tc5x2_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem2)));
+      attr2_dev[ix->device & 63] = smem2;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(qtiles, ysplit);
+    cfg.blockDim = dim3(T5_THREADS);
+    cfg.dynamicSmemBytes = smem2;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SDB_CUDA(cudaLaunchKernelEx(&cfg, tc5x2_filter_kernel, mq, mx2, mqe, mxe2, ta, st2));
+    SDB_CUDA(cudaGetLastError());
+    return SDB_OK;
+  }
   tc5_filter_kernel<<<dim3(qtiles, ysplit), T5_THREADS, smem, stream>>>(mq, mx, mqe, mxe, ta, stages);
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;
