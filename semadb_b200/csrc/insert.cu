@@ -117,14 +117,26 @@ __global__ void __launch_bounds__(PRUNE_THREADS) backedge_kernel(BackArgs a) {
   const int g = lane & 7;
   const int grp = threadIdx.x >> 3;
   const uint32_t nseg = *a.seg_count;
+  // The per-target chain seg_start -> keys -> deg / adj is three dependent global loads (~2 us) in
+  // front of what is often a plain append: the next target's head of the chain is fetched while
+  // this one is processed.
+  uint32_t nx_p0 = 0, nx_B = 0;
+  if (blockIdx.x < nseg) {
+    nx_p0 = a.seg_start[blockIdx.x];
+    nx_B = a.keys[nx_p0];
+  }
   for (uint32_t seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
-    const uint32_t p0 = a.seg_start[seg];
-    const uint32_t B = a.keys[p0];
+    const uint32_t p0 = nx_p0;
+    const uint32_t B = nx_B;
     __syncthreads();
     // every thread tracks the degree in a register (a shared counter bumped by one thread
     // would race with the other warps' branch on it)
     int cur_n = int(a.deg[B]);
     for (uint32_t t = threadIdx.x; t < a.R; t += blockDim.x) cur[t] = a.adj[size_t(B) * a.R + t];
+    if (seg + gridDim.x < nseg) {
+      nx_p0 = a.seg_start[seg + gridDim.x];
+      nx_B = a.keys[nx_p0];
+    }
     __syncthreads();
     const unsigned char* xb = global_row(a.s, B);
     uint32_t p_end = p0;
@@ -132,9 +144,11 @@ __global__ void __launch_bounds__(PRUNE_THREADS) backedge_kernel(BackArgs a) {
     uint32_t p = p0;
     while (p < p_end) {
       if (cur_n + 1 <= int(a.R)) {
-        if (threadIdx.x == 0) cur[cur_n] = a.new_ids[a.vals[p] / a.R];  // nodeB.AddNeighbour(vecA) (insert.go:62)
-        ++cur_n;
-        ++p;
+        // nodeB.AddNeighbour(vecA) (insert.go:62) for as many in-edges as fit, one barrier
+        const uint32_t take = min(uint32_t(int(a.R) - cur_n), p_end - p);
+        for (uint32_t t = threadIdx.x; t < take; t += blockDim.x) cur[cur_n + t] = a.new_ids[a.vals[p + t] / a.R];
+        cur_n += int(take);
+        p += take;
         __syncthreads();
         continue;
       }
