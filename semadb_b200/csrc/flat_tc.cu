@@ -362,7 +362,7 @@ __device__ __forceinline__ void t5_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ void t5_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void t5_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-constexpr int T5_HITS = 8;    // survivors parked per epilogue thread between flushes
+constexpr int T5_HITS = 6;    // survivors per half-buffer (two halves per epilogue thread)
 constexpr int T5_ESTAGES = 2;  // ring of extension blocks
 constexpr uint32_t T5_QEXT_BYTES = T5_M * 32;   // extension block of the query tile: 16 bf16 = 32 B per row
 constexpr uint32_t T5_XEXT_BYTES = T5_N * 32;   // extension block of a point tile
@@ -380,7 +380,7 @@ __host__ __device__ inline T5Smem t5_layout(uint32_t nkb, int stages) {
   L.x = L.qe + ((T5_QT * T5_QEXT_BYTES + 1023u) & ~1023u);
   L.xe = L.x + uint32_t(stages) * T5_XBLK_BYTES;
   L.hits = L.xe + T5_ESTAGES * T5_XEXT_BYTES;
-  L.bars = L.hits + T5_EPI_THREADS * T5_HITS * 4;
+  L.bars = L.hits + T5_EPI_THREADS * 2 * T5_HITS * 4;
   L.tmem_slot = L.bars + (2 * uint32_t(stages) + 2 * T5_ESTAGES + 5) * 8;
   L.total = L.tmem_slot + 16;
   return L;
@@ -517,14 +517,29 @@ tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const int etid = threadIdx.x - 64;      // 0..255
     const uint32_t q = q0 + uint32_t(qt) * T5_M + uint32_t(quad) * 32 + lane;
     const bool q_ok = q < a.B;
-    uint32_t* my_hits = reinterpret_cast<uint32_t*>(gbase + L.hits) + etid * T5_HITS;
-    int nh = 0;
+    // Two half-buffers per thread. A full half reserves its slots with an atomicAdd whose return
+    // value is NOT consumed yet: the thread goes on filtering into the other half, and copies the
+    // reserved half out at the next flush, when the round trip (~1 us) has long completed. (Waiting
+    // for every atomicAdd was 40 % of the samples of a candidate-dense level.)
+    uint32_t* hit_buf = reinterpret_cast<uint32_t*>(gbase + L.hits) + etid * (2 * T5_HITS);
+    uint32_t* my_hits = hit_buf;
+    int nh = 0, cur_half = 0, pend_n = 0;
+    uint32_t pend_slot = 0;
+    auto drain_pending = [&]() {  // copy out the half reserved by the previous flush
+      const uint32_t* src = hit_buf + (cur_half ^ 1) * T5_HITS;
+      uint32_t slot = pend_slot;
+      for (int i = 0; i < pend_n; ++i, ++slot)
+        if (slot < CAND_CAP) a.cand[size_t(q) * CAND_CAP + slot] = src[i];
+      pend_n = 0;
+    };
     auto flush_hits = [&]() {
+      drain_pending();
       if (nh && q_ok) {
-        uint32_t slot = atomicAdd(&a.cand_cnt[q], uint32_t(nh));
-        for (int i = 0; i < nh; ++i, ++slot)
-          if (slot < CAND_CAP) a.cand[size_t(q) * CAND_CAP + slot] = my_hits[i];
+        pend_slot = atomicAdd(&a.cand_cnt[q], uint32_t(nh));
+        pend_n = nh;
       }
+      cur_half ^= 1;
+      my_hits = hit_buf + cur_half * T5_HITS;
       nh = 0;
     };
     uint32_t it = 0;
@@ -557,6 +572,7 @@ tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       if (lane == 0) t5_mbar_arrive(bar_tempty(acc));
     }
     flush_hits();
+    drain_pending();
   }
   t5_fence_before();
   __syncthreads();
@@ -589,7 +605,7 @@ __host__ __device__ inline T5Smem t2_layout(uint32_t nkb, int stages) {
   L.x = L.qe + ((T5_QEXT_BYTES + 1023u) & ~1023u);
   L.xe = L.x + uint32_t(stages) * T2_XBLK_BYTES;
   L.hits = L.xe + T5_ESTAGES * T2_XEXT_BYTES;
-  L.bars = L.hits + T5_EPI_THREADS * T5_HITS * 4;
+  L.bars = L.hits + T5_EPI_THREADS * 2 * T5_HITS * 4;
   L.tmem_slot = L.bars + (2 * uint32_t(stages) + 2 * T5_ESTAGES + 5) * 8;
   L.total = L.tmem_slot + 16;
   return L;
@@ -749,14 +765,29 @@ tc5x2_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     const int etid = threadIdx.x - 64;
     const uint32_t q = q0 + uint32_t(quad) * 32 + lane;
     const bool q_ok = q < a.B;
-    uint32_t* my_hits = reinterpret_cast<uint32_t*>(gbase + L.hits) + etid * T5_HITS;
-    int nh = 0;
+    // Two half-buffers per thread. A full half reserves its slots with an atomicAdd whose return
+    // value is NOT consumed yet: the thread goes on filtering into the other half, and copies the
+    // reserved half out at the next flush, when the round trip (~1 us) has long completed. (Waiting
+    // for every atomicAdd was 40 % of the samples of a candidate-dense level.)
+    uint32_t* hit_buf = reinterpret_cast<uint32_t*>(gbase + L.hits) + etid * (2 * T5_HITS);
+    uint32_t* my_hits = hit_buf;
+    int nh = 0, cur_half = 0, pend_n = 0;
+    uint32_t pend_slot = 0;
+    auto drain_pending = [&]() {  // copy out the half reserved by the previous flush
+      const uint32_t* src = hit_buf + (cur_half ^ 1) * T5_HITS;
+      uint32_t slot = pend_slot;
+      for (int i = 0; i < pend_n; ++i, ++slot)
+        if (slot < CAND_CAP) a.cand[size_t(q) * CAND_CAP + slot] = src[i];
+      pend_n = 0;
+    };
     auto flush_hits = [&]() {
+      drain_pending();
       if (nh && q_ok) {
-        uint32_t slot = atomicAdd(&a.cand_cnt[q], uint32_t(nh));
-        for (int i = 0; i < nh; ++i, ++slot)
-          if (slot < CAND_CAP) a.cand[size_t(q) * CAND_CAP + slot] = my_hits[i];
+        pend_slot = atomicAdd(&a.cand_cnt[q], uint32_t(nh));
+        pend_n = nh;
       }
+      cur_half ^= 1;
+      my_hits = hit_buf + cur_half * T5_HITS;
       nh = 0;
     };
     uint32_t it = 0;
@@ -787,6 +818,7 @@ tc5x2_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       if (lane == 0) t2_arrive_leader(bar_tempty(acc));
     }
     flush_hits();
+    drain_pending();
   }
   t5_fence_before();
   __syncthreads();
