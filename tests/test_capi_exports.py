@@ -58,3 +58,12 @@ def test_parameter_validation_mirrors_reference():
         assert ei.value.code == _capi.ERR_INVALID, p
     with pytest.raises(_capi.SdbError):
         IndexVamana("x", IndexVectorVamanaParameters(8, "manhattan"), start_seed=1)
+
+
+def test_search_parallel_merge_single_member_passthrough():
+    """search.go:246-249: one member query is returned as is — no device call involved."""
+    from semadb_b200.search import search_parallel_merge
+    from semadb_b200.vamana import SearchResult
+    res = [SearchResult(7, 1.5, -1.5), SearchResult(9, 2.0, -2.0)]
+    s, out = search_parallel_merge([res], is_disjunction=True)
+    assert s == {7, 9} and out == res
