@@ -4,22 +4,29 @@
 // bf16 products cannot be final distances (1e-5 tolerance, SURVEY.md §7.3-⑥), so the tensor
 // cores only *generate candidates*, with a guarantee:
 //   1. exact top-k of every query over the first 128 points (the exact CUDA-core scan, flat.cu)
-//      gives tau_q >= the true k-th smallest distance; steps 2-3 then run over growing prefixes
-//      of the store (x32 per level: 4k points, 131k, 4M, ...), each level's exact top-k tightening
-//      tau for the next, so every level keeps ~32 k candidates per query;
+//      gives tau_q >= the true k-th smallest distance; steps 2-3 then run level by level over
+//      disjoint point ranges (each ending x32 further: 4k points, 131k, 4M, ...). A level's
+//      candidate list is seeded with the exact top-k of everything before it, so its re-score is
+//      the exact top-k of the whole prefix and tau tightens from level to level (~32 k
+//      candidates per query and level);
 //   2. a bf16 GEMM (fp32 accumulate) scores every (query, point) pair: a(q,x) = |x|^2 - 2 q~.x~
 //      (+|q|^2) for squared-L2, -q~.x~ for dot/cosine. |a - d| <= eps_q, a bound from the bf16
 //      unit roundoff 2^-8 and the largest point norm: eps_q = c1 |q| xmax + c2 (|q|^2 + xmax^2).
-//      Every pair with a <= tau_q + eps_q is appended to the query's candidate list — a superset
+//      Every pair with a < tau_q + eps_q is appended to the query's candidate list — a superset
 //      of the true top-k, because a true top-k member has d <= tau_q;
 //   3. candidates are re-scored with the reference's exact summation order (common.cuh) and the
 //      top-k taken by (distance asc, id asc) — flat.go:99,117 with ascending-id iteration.
-// A query whose candidate list overflows falls back to the exact scan. The result is therefore
-// bit-identical to flat.cu's, and tests compare the two.
+// A query whose candidate list overflows at any level falls back to the exact scan. The result is
+// therefore bit-identical to flat.cu's, and tests compare the two.
 //
-// GEMM: mma.sync.m16n8k16 bf16 (CTA tile 128 queries x 128 points, 8 warps of 64x32, K chunks
-// of 64 double-buffered with cp.async, ldmatrix fragments). The accumulators stay in registers,
-// which is what the threshold filter wants: it looks at every score once and keeps ~0.05 %.
+// Three forms of the GEMM + filter, same candidates:
+//   * tc5_filter_kernel (default, dim <= 384): tcgen05.mma M128xN256xK16 from TMA-fed (SWIZZLE_128B)
+//     shared memory into TMEM, warp-specialised, bias and threshold folded into the GEMM as a K
+//     extension so the epilogue is a sign test — see the comment above the kernel;
+//   * tc5x2_filter_kernel (SDB_FLAT_2CTA=1): the cta_group::2 form, two SMs per 256 x 256 step;
+//   * tc_filter_kernel (dim > 384, SDB_FLAT_MMA_SYNC=1): mma.sync.m16n8k16 bf16, CTA tile 128 x 128,
+//     8 warps of 64x32, K chunks of 64 double-buffered with cp.async, ldmatrix fragments,
+//     accumulators in registers.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
