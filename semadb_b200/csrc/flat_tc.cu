@@ -888,11 +888,11 @@ int launch_tc5_filter(sdb_index* ix, TcArgs ta, uint32_t B_pad, cudaStream_t str
   const uint32_t qtiles = B_pad / (T5_M * T5_QT);
   const uint32_t ntiles = (ta.end_id - ta.first_id + T5_N - 1) / T5_N;
   // one CTA per SM: split the point range so that the CTAs fill whole waves of sm_count (the
-  // fewest waves >= 3 whose last wave is at least 97 % full; each CTA keeps >= 16 tiles)
+  // fewest waves >= 3 whose last wave is at least 97 % full; each CTA keeps >= 4 tiles)
   uint32_t ysplit = 1;
   {
     const uint32_t sms = uint32_t(ix->sm_count);
-    const uint32_t ymax = std::max<uint32_t>(1, std::min<uint32_t>(64, ntiles / 16));
+    const uint32_t ymax = std::max<uint32_t>(1, std::min<uint32_t>(64, ntiles / 4));  // >= 4 tiles per CTA
     double best = -1.0;
     for (uint32_t y = 1; y <= ymax; ++y) {
       const uint32_t ctas = qtiles * y, waves = (ctas + sms - 1) / sms;
