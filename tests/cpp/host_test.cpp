@@ -20,6 +20,7 @@
 
 #include "../../semadb_b200/host/coalescer.hpp"
 #include "../../semadb_b200/host/gpuvamana.hpp"
+#include "../../semadb_b200/host/search.hpp"
 
 using namespace semadb;
 using vamana::IndexVamana;
@@ -337,6 +338,43 @@ static void test_coalescer() {
                (unsigned long long)co.batches());
 }
 
+// TestSearch_OrVector / TestSearch_And (shard/index/search_test.go:289-457) over the GPU path: two
+// vector searches of the same neighbourhood with weight 0.5 each merge into results whose
+// HybridScore is -distance; `_and` keeps the common ids only.
+static void test_search_parallel_merge() {
+  diskstore::MemBucket bucket;
+  std::unique_ptr<IndexVamana> inv;
+  REQUIRE_OK(IndexVamana::New("test", vamanaParams(2), &bucket, &inv, 0, 7));
+  std::vector<IndexVectorChange> pts;
+  for (uint64_t i = 0; i < 100; ++i) pts.push_back(IndexVectorChange{i + 2, {float(i), float(i + 1)}});
+  REQUIRE_OK(inv->InsertUpdateDelete(pts));
+  const float w = 0.5f;
+  models::SearchVectorVamanaOptions o;
+  o.Vector = {42.0f, 43.0f};
+  o.Limit = 5;
+  o.Weight = w;
+  std::vector<uint64_t> s1, s2, fs;
+  std::vector<models::SearchResult> r1, r2, fr;
+  REQUIRE_OK(inv->Search(o, nullptr, &s1, &r1));
+  REQUIRE_OK(inv->Search(o, nullptr, &s2, &r2));
+  CHECK(r1.size() == 5);
+  REQUIRE_OK(index::SearchParallelMerge({r1, r2}, true, 0, &fs, &fr));
+  CHECK(fr.size() == 5 && fs.size() == 5);
+  CHECK(!fr.empty() && fr[0].NodeId == 44);  // point 42 has node id 44
+  for (size_t i = 0; i < fr.size(); ++i) {
+    CHECK(fr[i].HybridScore == -fr[i].Distance);  // two weights of 0.5 add up
+    if (i + 1 < fr.size()) CHECK(fr[i].HybridScore >= fr[i + 1].HybridScore);
+  }
+  o.Limit = 3;
+  std::vector<uint64_t> s3;
+  std::vector<models::SearchResult> r3;
+  REQUIRE_OK(inv->Search(o, nullptr, &s3, &r3));
+  REQUIRE_OK(index::SearchParallelMerge({r1, r3}, false, 0, &fs, &fr));
+  CHECK(fr.size() == 3 && fs == std::vector<uint64_t>({43, 44, 45}));
+  REQUIRE_OK(index::SearchParallelMerge({r3}, false, 0, &fs, &fr));  // single member: passed through
+  CHECK(fr.size() == r3.size());
+}
+
 int main(int argc, char** argv) {
   const std::string mode = argc > 1 ? argv[1] : "codec";
   test_codec();
@@ -349,6 +387,7 @@ int main(int argc, char** argv) {
     test_cud_and_persistence();
     test_quantized_persistence();
     test_coalescer();
+    test_search_parallel_merge();
   }
   if (g_fail) {
     std::fprintf(stderr, "%d check(s) failed\n", g_fail);
