@@ -122,19 +122,38 @@ int sdb_index_delete(sdb_index* ix, uint64_t n, const uint64_t* ids);
 
 /* ---- search: replaces IndexVamana.Search (vamana.go:278-310) for a batch of B queries.
  * queries: B x dim. k = Limit, search_size = SearchSize (error if < k).
- * filter_ids: optional ascending node ids shared by the batch (search.go:33-51,93-95).
+ * filter_ids: optional ascending node ids shared by the batch (search.go:33-51,93-95);
+ * filter_ids != NULL means "filtered" even when n_filter == 0 (see sdb_search_batch_filters).
  * out_ids/out_dists: B x k, row b holds out_counts[b] results (start node removed,
  * vamana.go:294-296), remaining slots id 0 / +inf. HybridScore = -dist*weight is left
  * to the caller (vamana.go:303). */
 int sdb_search_batch(sdb_index* ix, uint32_t B, const float* queries, uint32_t k, uint32_t search_size,
                      const uint64_t* filter_ids, uint64_t n_filter, uint64_t* out_ids, float* out_dists,
                      uint32_t* out_counts);
+/* Per-request filters in one batch (the reference hands every request its own bitmap:
+ * shard/index/search.go:59-85 -> vamana/search.go:33-51,93-95). filter f is the ascending id
+ * list filter_ids[filter_offsets[f] .. filter_offsets[f+1]); request b uses filter
+ * query_filter[b], or none if query_filter[b] < 0 (query_filter == NULL: every request uses
+ * filter 0). An EMPTY list is a filter like any other — a non-nil empty bitmap seeds nothing and
+ * the request returns no result — so callers whose empty container has a NULL data pointer use
+ * this entry point (n_filters >= 1) instead of sdb_search_batch's `filter_ids != NULL` rule.
+ * n_filters == 0 = nobody is filtered. Unfiltered requests of a mixed batch run through the
+ * same kernels as an unfiltered batch. */
+int sdb_search_batch_filters(sdb_index* ix, uint32_t B, const float* queries, uint32_t k, uint32_t search_size,
+                             uint32_t n_filters, const uint64_t* filter_ids, const uint64_t* filter_offsets,
+                             const int32_t* query_filter, uint64_t* out_ids, float* out_dists, uint32_t* out_counts);
 /* Same with device-resident queries/outputs; enqueues on `stream` (cudaStream_t). */
 int sdb_search_batch_device(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k, uint32_t search_size,
                             uint64_t* d_out_ids, float* d_out_dists, uint32_t* d_out_counts, void* stream);
 /* Per-query counters of the most recent search on this handle (nodes expanded, distances
  * evaluated): the terms of the algorithmic-bytes formula, SURVEY.md §8d. Synchronises. */
 int sdb_last_search_stats(sdb_index* ix, uint32_t B, uint32_t* hops_out, uint32_t* ndist_out);
+/* Kernel timing for the roofline figure: while enabled, every search on the handle brackets its
+ * first-pass beam-search kernel with CUDA events on the launching stream (up to 256 searches per
+ * enabling; no synchronisation is added). _read waits for the recorded events and returns the
+ * per-search kernel durations in ms: *n_out = searches recorded, min(*n_out, cap) values copied. */
+int sdb_search_profile(sdb_index* ix, int32_t enable);
+int sdb_search_profile_read(sdb_index* ix, uint32_t cap, float* ms_out, uint32_t* n_out);
 /* Total kernel launches issued by this handle so far (bench.py's gpu_launches). */
 uint64_t sdb_launch_count(const sdb_index* ix);
 /* Diagnostic twin of greedySearch's second return value (search.go:100): the visited
@@ -156,6 +175,18 @@ int sdb_flat_last_stats(sdb_index* ix, int32_t* path, uint64_t* candidates, uint
 /* ---- insert: replaces IndexVamana.InsertUpdateDelete's insert branch (vamana.go:136-201,
  * insert.go:16-68): greedySearch + robustPrune + back-edges for n new points, batched. */
 int sdb_insert_batch(sdb_index* ix, uint64_t n, const uint64_t* ids, const float* vectors);
+/* Same with the n x dim vectors already resident on the index's GPU (bulk loads whose vectors are
+ * produced on the device); ids stay on the host. Orders itself after all prior device work. */
+int sdb_insert_batch_device(sdb_index* ix, uint64_t n, const uint64_t* ids, const float* d_vectors);
+/* Inserts (since creation) whose visited list exceeded the robustPrune candidate capacity (512) and
+ * was cut to its first 512 expansions; the reference's list is unbounded. Not an error: the graph
+ * stays valid and the call's state is committed. */
+uint64_t sdb_insert_truncated(const sdb_index* ix);
+/* Running totals of the batched insert since creation (or the last reset), the terms of the build's
+ * algorithmic-bytes figure: out8 = {points inserted, nodes expanded by their
+ * searches, distances evaluated by their searches, out-edges written by robustPrune(new), back-edge
+ * targets updated, robustPrune(B) runs on saturated targets, candidates of those runs, 0}. */
+int sdb_insert_stats(sdb_index* ix, uint64_t* out8, int32_t reset);
 /* The whole of IndexVamana.InsertUpdateDelete (vamana.go:136-263) except the trailing Fit and
  * flush: has_vector[i] == 0 stands for a nil vector (IndexVectorChange.Vector == nil,
  * vamana.go:122-125; NULL = all have vectors). Each change is classified against the store
@@ -265,6 +296,13 @@ int sdb_search_batch_gather_device(sdb_index* ix, uint32_t B, const float* d_que
                                    const sdb_peer_gather* peers, void* stream);
 int sdb_peer_barrier_device(int32_t device, uint32_t n_peers, uint32_t me, uint32_t* const* peer_flags, uint32_t epoch,
                             void* stream);
+/* A peer that never arrives is given ~20 s; the barrier kernel then records the timeout in a
+ * page-locked status word of its device. From then on sdb_peer_barrier_device,
+ * sdb_search_batch_gather_device and sdb_merge_topk_device on that device fail with SDB_ERR_STATE
+ * (the step whose barrier timed out merged stale slots). sdb_peer_barrier_check reads the word
+ * (no synchronisation: call it after synchronising the step's stream to validate that step) and
+ * returns SDB_OK or SDB_ERR_STATE; clear != 0 resets it once the caller has recovered. */
+int sdb_peer_barrier_check(int32_t device, int32_t clear);
 /* Per-shard request limit (cluster/actions.go:291-299). Pure host arithmetic. */
 uint32_t sdb_shard_limit(uint32_t limit, uint32_t n_shards, uint32_t max_search_limit);
 

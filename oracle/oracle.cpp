@@ -313,6 +313,7 @@ struct Index {
   // storage, dense by node id (0 invalid, 1 = start node, users from 2:
   // vamana.go:28,150-157; idcounter.go:52-54)
   size_t cap = 0;
+  bool codes_only = false;  // hydrated from n<id>q payloads alone: raw vectors are not loaded (binary.go:275-296, product.go:349-371)
   std::vector<float> vec;
   std::vector<uint64_t> bits;
   std::vector<uint8_t> codes;
@@ -336,7 +337,7 @@ struct Index {
   void reserve(size_t n) {
     if (n <= cap) return;
     size_t nc = std::max(n, cap * 2);
-    vec.resize(nc * dim);
+    if (!codes_only) vec.resize(nc * dim);
     if (quant == Q_BINARY) bits.resize(nc * words);
     if (quant == Q_PRODUCT) codes.resize(nc * pqM);
     exists.resize(nc, 0);
@@ -1072,6 +1073,30 @@ int orc_index_get_codes(void* h, const uint32_t* ids, size_t n, uint8_t* out) {
   if (ix->quant == Q_PRODUCT) for (size_t i = 0; i < n; ++i) std::memcpy(out + i * ix->pqM, ix->C(ids[i]), ix->pqM);
   else if (ix->quant == Q_BINARY) for (size_t i = 0; i < n; ++i) std::memcpy(out + i * ix->words * 8, ix->B(ids[i]), ix->words * 8);
   else return -1;
+  return 0;
+}
+// Hydrate quantised points from their codes alone, like loading the n<id>q keys of a fitted
+// store (binary.go:275-296, product.go:349-371: a point with codes does not load its raw vector).
+// Only valid on an empty index or one already in this mode; searches then use the codes only.
+int orc_index_set_codes(void* h, const uint32_t* ids, const uint8_t* codes, size_t n) {
+  auto* ix = static_cast<Index*>(h);
+  const bool bq = ix->quant == Q_BINARY && ix->bq_fitted, pq = ix->quant == Q_PRODUCT && ix->pq_fitted();
+  if (!bq && !pq) return -1;
+  if (ix->count != 0 && !ix->codes_only) return -2;
+  if (!ix->codes_only) {
+    ix->codes_only = true;
+    std::vector<float>().swap(ix->vec);
+  }
+  uint32_t mx = 0;
+  for (size_t i = 0; i < n; ++i) mx = std::max(mx, ids[i]);
+  ix->reserve(size_t(mx) + 1);
+  for (size_t i = 0; i < n; ++i) {
+    const uint32_t id = ids[i];
+    if (bq) std::memcpy(&ix->bits[size_t(id) * ix->words], codes + i * size_t(ix->words) * 8, size_t(ix->words) * 8);
+    else std::memcpy(&ix->codes[size_t(id) * ix->pqM], codes + i * size_t(ix->pqM), ix->pqM);
+    if (!ix->exists[id]) { ix->exists[id] = 1; ix->count++; }
+    if (id != 1 && id > ix->maxNodeId) ix->maxNodeId = id;
+  }
   return 0;
 }
 int orc_index_get_vectors(void* h, const uint32_t* ids, size_t n, float* out) {

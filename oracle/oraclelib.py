@@ -90,6 +90,8 @@ def lib():
     L.orc_index_get_bq_threshold.argtypes = [C.c_void_p, f32p]
     L.orc_index_get_codes.restype = C.c_int
     L.orc_index_get_codes.argtypes = [C.c_void_p, u32p, C.c_size_t, u8p]
+    L.orc_index_set_codes.restype = C.c_int
+    L.orc_index_set_codes.argtypes = [C.c_void_p, u32p, u8p, C.c_size_t]
     L.orc_index_get_vectors.restype = C.c_int
     L.orc_index_get_vectors.argtypes = [C.c_void_p, u32p, C.c_size_t, f32p]
     L.orc_index_capacity.restype = C.c_uint64
@@ -296,6 +298,14 @@ class OracleIndex:
         rc = lib().orc_index_get_codes(self._h, _p(ids, u32p), len(ids), _p(out, u8p))
         assert rc == 0
         return out
+
+    def set_codes(self, ids, codes):
+        """Hydrate from quantised codes alone (binary.go:275-296, product.go:349-371)."""
+        ids = _u32(ids)
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        rc = lib().orc_index_set_codes(self._h, _p(ids, u32p), _p(codes, u8p), len(ids))
+        if rc:
+            raise RuntimeError(f"oracle set_codes failed rc={rc}")
 
     def get_vectors(self, ids):
         ids = _u32(ids)

@@ -71,18 +71,26 @@ _SIGS = {
     "sdb_index_get_vectors": (C.c_int, [H, C.c_uint64, u64p, f32p]),
     "sdb_index_delete": (C.c_int, [H, C.c_uint64, u64p]),
     "sdb_search_batch": (C.c_int, [H, C.c_uint32, f32p, C.c_uint32, C.c_uint32, u64p, C.c_uint64, u64p, f32p, u32p]),
+    "sdb_search_batch_filters": (C.c_int, [H, C.c_uint32, f32p, C.c_uint32, C.c_uint32, C.c_uint32, u64p, u64p, i32p, u64p, f32p,
+                                           u32p]),
     "sdb_search_batch_device": (C.c_int, [H, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p]),
     "sdb_search_batch_gather_device": (C.c_int, [H, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                                  C.c_void_p, C.POINTER(SdbPeerGather), C.c_void_p]),
     "sdb_peer_barrier_device": (C.c_int, [C.c_int32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.c_uint32,
                                           C.c_void_p]),
+    "sdb_peer_barrier_check": (C.c_int, [C.c_int32, C.c_int32]),
     "sdb_last_search_stats": (C.c_int, [H, C.c_uint32, u32p, u32p]),
+    "sdb_search_profile": (C.c_int, [H, C.c_int32]),
+    "sdb_search_profile_read": (C.c_int, [H, C.c_uint32, f32p, u32p]),
     "sdb_launch_count": (C.c_uint64, [H]),
     "sdb_search_visited": (C.c_int, [H, C.c_uint32, f32p, C.c_uint32, C.c_uint32, u64p, f32p, u32p]),
     "sdb_flat_search_batch": (C.c_int, [H, C.c_uint32, f32p, C.c_uint32, u64p, C.c_uint64, u64p, f32p, u32p]),
     "sdb_flat_last_stats": (C.c_int, [H, i32p, u64p, u32p]),
     "sdb_insert_batch": (C.c_int, [H, C.c_uint64, u64p, f32p]),
+    "sdb_insert_batch_device": (C.c_int, [H, C.c_uint64, u64p, C.c_void_p]),
+    "sdb_insert_truncated": (C.c_uint64, [H]),
+    "sdb_insert_stats": (C.c_int, [H, u64p, C.c_int32]),
     "sdb_insert_config": (C.c_int, [H, C.c_uint32, C.c_uint32, C.c_uint32]),
     "sdb_insert_update_delete": (C.c_int, [H, C.c_uint64, u64p, f32p, u8p]),
     "sdb_edge_scan": (C.c_int, [H, C.c_uint64, u64p, u64p, u64p, u64p, u64p]),

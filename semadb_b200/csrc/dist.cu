@@ -3,6 +3,9 @@
 // (shard/vectorstore/plain.go:76-97, binary.go:187-234, product.go:238-305), the binary
 // encoder (binary.go:103-129), the PQ encoder (product.go:136-159), the ADC table builder
 // (product.go:255-263, K4) and the cross-shard top-k merge (cluster/actions.go:357-376, K6).
+#include <mutex>
+#include <string>
+
 #include "common.cuh"
 #include "index.cuh"
 
@@ -303,9 +306,12 @@ int launch_merge(uint32_t S, uint32_t B, uint32_t k, const uint64_t* in_ids, con
 // p's flags[me] with a system-scope release (the peer stores of the kernels before it on this
 // stream are ordered first), then waits until peer p's epoch has arrived in flags_me[p].
 // Epochs only grow, so the words are never reset. A peer that never arrives (a crashed rank)
-// is given ~20 s, then the kernel records the failure in flags_me[SDB_MAX_PEERS + p] and returns.
+// is given ~20 s; then the kernel records the failure in flags_me[SDB_MAX_PEERS + p] AND in the
+// library's page-locked status word of this device, which every later exchange call on the
+// device (and sdb_peer_barrier_check) reads on the host without a synchronisation and turns
+// into SDB_ERR_STATE: the merge that follows a timed-out barrier read stale slots.
 struct PeerFlags { uint32_t* f[SDB_MAX_PEERS]; };
-__global__ void peer_barrier_kernel(PeerFlags pf, uint32_t n, uint32_t me, uint32_t epoch) {
+__global__ void peer_barrier_kernel(PeerFlags pf, uint32_t n, uint32_t me, uint32_t epoch, uint32_t* host_status) {
   const uint32_t p = threadIdx.x;
   if (p >= n) return;
   __threadfence_system();
@@ -318,10 +324,42 @@ __global__ void peer_barrier_kernel(PeerFlags pf, uint32_t n, uint32_t me, uint3
     if (int32_t(v - epoch) >= 0) break;
     if (clock64() - t0 > 40000000000LL) {
       pf.f[me][SDB_MAX_PEERS + p] = epoch;
+      if (host_status) {
+        host_status[1] = p;
+        __threadfence_system();
+        host_status[0] = epoch;  // non-zero = a barrier of this device timed out at that epoch
+        __threadfence_system();
+      }
       break;
     }
     __nanosleep(200);
   }
+}
+
+// one {epoch, peer} pair of page-locked, device-mapped words per device, allocated on first use
+constexpr int kMaxDevices = 64;
+static volatile uint32_t* g_barrier_status[kMaxDevices] = {};
+static std::mutex g_barrier_mu;
+static int barrier_status_word(int device, volatile uint32_t** out) {
+  if (device < 0 || device >= kMaxDevices) return fail(SDB_ERR_INVALID, "device ordinal out of range");
+  std::lock_guard<std::mutex> g(g_barrier_mu);
+  if (!g_barrier_status[device]) {
+    void* p = nullptr;
+    SDB_CUDA(cudaHostAlloc(&p, 2 * sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable));
+    static_cast<uint32_t*>(p)[0] = 0;
+    static_cast<uint32_t*>(p)[1] = 0;
+    g_barrier_status[device] = static_cast<volatile uint32_t*>(p);
+  }
+  *out = g_barrier_status[device];
+  return SDB_OK;
+}
+// SDB_ERR_STATE if a peer barrier on this device has timed out (sticky until cleared)
+int peer_barrier_poisoned(int device) {
+  if (device < 0 || device >= kMaxDevices) return SDB_OK;
+  volatile uint32_t* w = g_barrier_status[device];
+  if (!w || w[0] == 0) return SDB_OK;
+  return fail(SDB_ERR_STATE, "cross-GPU barrier timed out at epoch " + std::to_string(w[0]) + " waiting for peer " +
+                                 std::to_string(w[1]) + ": the merged lists of that step are invalid");
 }
 
 }  // namespace sdb
@@ -483,6 +521,7 @@ int sdb_merge_topk_device(int32_t device, uint32_t S, uint32_t B, uint32_t k, co
   if (k < 1 || k > 75) return fail(SDB_ERR_INVALID, "invalid limit");
   int rc = set_device_checked(device);
   if (rc) return rc;
+  if ((rc = peer_barrier_poisoned(device))) return rc;  // an earlier cross-GPU barrier on this device timed out
   return launch_merge(S, B, k, d_in_ids, d_in_dists, d_in_counts, d_out_ids, d_out_dists, d_out_counts, static_cast<cudaStream_t>(stream));
 }
 
@@ -549,9 +588,23 @@ int sdb_peer_barrier_device(int32_t device, uint32_t n_peers, uint32_t me, uint3
     if (!peer_flags[p]) return fail(SDB_ERR_INVALID, "peer barrier: null flag pointer");
     pf.f[p] = peer_flags[p];
   }
-  peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pf, n_peers, me, epoch);
+  if ((rc = peer_barrier_poisoned(device))) return rc;
+  volatile uint32_t* status = nullptr;
+  if ((rc = barrier_status_word(device, &status))) return rc;
+  uint32_t* d_status = nullptr;
+  SDB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_status), const_cast<uint32_t*>(status), 0));
+  peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pf, n_peers, me, epoch, d_status);
   SDB_CUDA(cudaGetLastError());
   return SDB_OK;
+}
+
+int sdb_peer_barrier_check(int32_t device, int32_t clear) {
+  int rc = peer_barrier_poisoned(device);
+  if (rc && clear && device >= 0 && device < kMaxDevices && g_barrier_status[device]) {
+    g_barrier_status[device][0] = 0;
+    g_barrier_status[device][1] = 0;
+  }
+  return rc;
 }
 
 }  // extern "C"

@@ -54,6 +54,23 @@ __global__ void gather_edges_kernel(const uint32_t* adj, const uint32_t* deg, ui
   for (uint32_t i = threadIdx.x; i < R; i += blockDim.x) rows[size_t(r) * R + i] = adj[size_t(id) * R + i];
   if (threadIdx.x == 0) degs[r] = deg[id];
 }
+// code rows (PQ bytes / bit words) <-> a dense staging buffer: one thread per byte
+__global__ void scatter_codes_kernel(uint8_t* base, uint32_t pitch, uint32_t width, uint8_t* exists, const uint32_t* ids,
+                                     const uint8_t* src, uint64_t n) {
+  const uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n * width) return;
+  const uint64_t r = t / width;
+  const uint32_t c = uint32_t(t % width);
+  const uint32_t id = ids[r];
+  base[size_t(id) * pitch + c] = src[t];
+  if (c == 0) exists[id] = 1;
+}
+__global__ void gather_codes_kernel(const uint8_t* base, uint32_t pitch, uint32_t width, const uint32_t* ids, uint8_t* dst,
+                                    uint64_t n) {
+  const uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n * width) return;
+  dst[t] = base[size_t(ids[t / width]) * pitch + uint32_t(t % width)];
+}
 __global__ void fill_u32_kernel(uint32_t* p, uint32_t v, size_t n) {
   size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   size_t stride = size_t(gridDim.x) * blockDim.x;
@@ -265,10 +282,13 @@ void sdb_index_destroy(sdb_index* ix) {
   cudaFree(ix->d_bq_thr);
   cudaFree(ix->d_pq_centroids);
   cudaFree(ix->d_pq_cdist);
+  cudaFree(ix->d_ins_stats);
   ix->d_q.release(); ix->d_oid.release(); ix->d_od.release(); ix->d_oc.release(); ix->d_hops.release();
-  ix->d_ndist.release(); ix->d_work.release(); ix->d_adc.release(); ix->d_filter_seed.release();
-  ix->d_filter_bits.release(); ix->d_vis_ids.release(); ix->d_vis_len.release(); ix->d_vis_d.release();
+  ix->d_ndist.release(); ix->d_work.release(); ix->d_adc.release(); ix->d_filter_ids.release(); ix->d_filter_off.release();
+  ix->d_filter_bits.release(); ix->d_qmap.release(); ix->d_query_filter.release(); ix->d_retry_bitmap.release(); ix->d_vis_ids.release(); ix->d_vis_len.release(); ix->d_vis_d.release();
   ix->d_ids64.release(); ix->d_tmp32.release(); ix->d_tmpf.release(); ix->d_tmp8.release(); ix->h_stage.release();
+  for (auto& e : ix->prof_ev)
+    if (e) cudaEventDestroy(e);
   if (ix->stream) cudaStreamDestroy(ix->stream);
   cudaGetLastError();
   delete ix;
@@ -378,6 +398,8 @@ int sdb_index_set_edges(sdb_index* ix, uint64_t n, const uint64_t* ids, const ui
   std::vector<uint32_t> h32, rows, degs;
   for (uint64_t s = 0; s < n; s += chunk) {
     uint64_t m = std::min(chunk, n - s);
+    int rc = stage_ids(ix, m, ids + s, false, true, h32);
+    if (rc) return rc;
     rows.assign(size_t(m) * R, INVALID_ID);
     degs.resize(m);
     for (uint64_t i = 0; i < m; ++i) {
@@ -386,13 +408,16 @@ int sdb_index_set_edges(sdb_index* ix, uint64_t n, const uint64_t* ids, const ui
       for (uint32_t j = 0; j < d; ++j) {
         uint64_t e = edges[off + j];
         if (e == 0 || e >= (uint64_t(1) << 31) - 1) return fail(SDB_ERR_INVALID, "edge target out of range");
+        // a dangling edge (target never stored, or deleted) would send the search kernel to a row
+        // that does not exist; the reference fails with "failed to get node for neighbours"
+        // (search.go:77-80). Points are hydrated before edges (sdb_index_set_vectors / set_codes).
+        if (e >= ix->rows || !ix->h_exists[e])
+          return fail(SDB_ERR_NOTFOUND, "edge of node " + std::to_string(ids[s + i]) + " points at a node that does not exist: " + std::to_string(e));
         rows[size_t(i) * R + j] = uint32_t(e);
       }
       off += d;
       degs[i] = d;
     }
-    int rc = stage_ids(ix, m, ids + s, false, true, h32);
-    if (rc) return rc;
     if ((rc = ix->d_ids64.ensure((size_t(m) * R + m + 1) / 2 + 1))) return rc;
     uint32_t* d_rows = reinterpret_cast<uint32_t*>(ix->d_ids64.p);
     uint32_t* d_degs = d_rows + size_t(m) * R;
@@ -477,44 +502,82 @@ static int ensure_out_scratch(sdb_index* ix, uint32_t B, uint32_t k) {
   return SDB_OK;
 }
 
-// roaring filter -> first-L seed ids + dense bitmask over rows (search.go:40-44,93)
-static int stage_filter(sdb_index* ix, const uint64_t* filter_ids, uint64_t n_filter, uint32_t L, uint32_t* n_seed) {
-  std::vector<uint32_t> seed;
-  std::vector<uint32_t> bits((size_t(ix->rows) + 31) / 32, 0);
-  uint64_t prev = 0;
-  for (uint64_t i = 0; i < n_filter; ++i) {
-    uint64_t id = filter_ids[i];
-    if (i && id <= prev) return fail(SDB_ERR_INVALID, "filter ids must be strictly ascending");
-    prev = id;
-    if (id < ix->rows) bits[id >> 5] |= 1u << (id & 31);
-    if (seed.size() < L) {
-      if (id == 0 || id >= ix->rows || !ix->h_exists[id]) return fail(SDB_ERR_NOTFOUND, "failed to get filter points");  // search.go:45-48
-      seed.push_back(uint32_t(id));
+// Host staging of a batch's filters (search.go:33-51,93-95; one roaring bitmap per request,
+// shard/index/search.go:59-85) into the device form of SearchFilters: concatenated ascending u32
+// id lists + offsets, the per-query filter index, the batch positions of the filtered and of the
+// unfiltered requests, and — for a single shared filter — a dense bitmask over rows.
+// filter f = filter_ids[filter_offsets[f] .. filter_offsets[f+1]); query_filter[b] < 0 = request b
+// is not filtered (nullptr: every request uses filter 0). An EMPTY list is still a filter: the
+// reference then seeds nothing and returns no result (search.go:33-51 with an empty bitmap).
+static int stage_filters(sdb_index* ix, uint32_t B, uint32_t n_filters, const uint64_t* filter_ids,
+                         const uint64_t* filter_offsets, const int32_t* query_filter, uint32_t L, bool want_bits,
+                         SearchFilters* out) {
+  if (n_filters == 0 || !filter_offsets) return fail(SDB_ERR_INVALID, "filters: need at least one filter and its offsets");
+  std::vector<uint32_t> ids, off(size_t(n_filters) + 1, 0), qf_plain, qf_filtered;
+  std::vector<int32_t> qfil;
+  ids.reserve(size_t(filter_offsets[n_filters] - filter_offsets[0]));
+  for (uint32_t f = 0; f < n_filters; ++f) {
+    const uint64_t b0 = filter_offsets[f], b1 = filter_offsets[f + 1];
+    if (b1 < b0 || (b1 > b0 && !filter_ids)) return fail(SDB_ERR_INVALID, "filters: offsets must ascend");
+    off[f] = uint32_t(ids.size());
+    uint64_t prev = 0;
+    for (uint64_t i = b0; i < b1; ++i) {
+      const uint64_t id = filter_ids[i];
+      if (i > b0 && id <= prev) return fail(SDB_ERR_INVALID, "filter ids must be strictly ascending");
+      prev = id;
+      if (i - b0 < L && (id == 0 || id >= ix->rows || !ix->h_exists[id]))
+        return fail(SDB_ERR_NOTFOUND, "failed to get filter points");  // GetMany of the seeds, search.go:45-48
+      if (id < ix->rows) ids.push_back(uint32_t(id));  // ids beyond the store can never be expanded
+    }
+  }
+  off[n_filters] = uint32_t(ids.size());
+  if (ids.size() >= (size_t(1) << 32)) return fail(SDB_ERR_INVALID, "filters: too many ids in one batch");
+  if (query_filter) {
+    qfil.assign(query_filter, query_filter + B);
+    for (uint32_t b = 0; b < B; ++b) {
+      if (qfil[b] >= int32_t(n_filters)) return fail(SDB_ERR_INVALID, "filters: query_filter index out of range");
+      if (qfil[b] < 0) { qf_plain.push_back(b); qfil[b] = 0; }
+      else qf_filtered.push_back(b);
     }
   }
   int rc;
-  if ((rc = ix->d_filter_seed.ensure(seed.size() + 1))) return rc;
-  if ((rc = ix->d_filter_bits.ensure(bits.size() + 1))) return rc;
-  SDB_CUDA(cudaMemcpyAsync(ix->d_filter_seed.p, seed.data(), seed.size() * 4, cudaMemcpyHostToDevice, ix->stream));
-  SDB_CUDA(cudaMemcpyAsync(ix->d_filter_bits.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+  if ((rc = ix->d_filter_ids.ensure(ids.size() + 1))) return rc;
+  if ((rc = ix->d_filter_off.ensure(off.size()))) return rc;
+  SDB_CUDA(cudaMemcpyAsync(ix->d_filter_ids.p, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+  SDB_CUDA(cudaMemcpyAsync(ix->d_filter_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+  *out = SearchFilters{};
+  out->ids = ix->d_filter_ids.p;
+  out->off = ix->d_filter_off.p;
+  out->n_filtered = B;
+  std::vector<uint32_t> bits;
+  if (want_bits && n_filters == 1 && !query_filter) {
+    bits.assign((size_t(ix->rows) + 31) / 32, 0);
+    for (uint32_t id : ids) bits[id >> 5] |= 1u << (id & 31);
+    if ((rc = ix->d_filter_bits.ensure(bits.size() + 1))) return rc;
+    SDB_CUDA(cudaMemcpyAsync(ix->d_filter_bits.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+    out->bits = ix->d_filter_bits.p;
+  }
+  if (query_filter) {
+    if ((rc = ix->d_query_filter.ensure(B))) return rc;
+    if ((rc = ix->d_qmap.ensure(size_t(B) + 1))) return rc;
+    SDB_CUDA(cudaMemcpyAsync(ix->d_query_filter.p, qfil.data(), size_t(B) * 4, cudaMemcpyHostToDevice, ix->stream));
+    if (!qf_filtered.empty())
+      SDB_CUDA(cudaMemcpyAsync(ix->d_qmap.p, qf_filtered.data(), qf_filtered.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+    if (!qf_plain.empty())
+      SDB_CUDA(cudaMemcpyAsync(ix->d_qmap.p + qf_filtered.size(), qf_plain.data(), qf_plain.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+    out->query_filter = ix->d_query_filter.p;
+    out->qmap_filtered = ix->d_qmap.p;
+    out->n_filtered = uint32_t(qf_filtered.size());
+    out->qmap_plain = ix->d_qmap.p + qf_filtered.size();
+    out->n_plain = uint32_t(qf_plain.size());
+  }
   SDB_CUDA(cudaStreamSynchronize(ix->stream));  // host vectors go out of scope
-  *n_seed = uint32_t(seed.size());
   return SDB_OK;
 }
 
-int sdb_search_batch(sdb_index* ix, uint32_t B, const float* queries, uint32_t k, uint32_t search_size,
-                     const uint64_t* filter_ids, uint64_t n_filter, uint64_t* out_ids, float* out_dists,
-                     uint32_t* out_counts) {
-  if (!ix) return fail(SDB_ERR_INVALID, "null index");
-  if (B == 0) return SDB_OK;
-  if (!queries || !out_ids || !out_dists || !out_counts) return fail(SDB_ERR_INVALID, "null argument");
-  std::lock_guard<std::mutex> g(ix->mu);
-  SDB_CUDA(cudaSetDevice(ix->device));
-  int rc = check_search_args(ix, k, search_size);
-  if (rc) return rc;
-  uint32_t n_seed = 0;
-  const bool filtered = filter_ids != nullptr;
-  if (filtered && (rc = stage_filter(ix, filter_ids, n_filter, search_size, &n_seed))) return rc;
+static int search_batch_locked(sdb_index* ix, uint32_t B, const float* queries, uint32_t k, uint32_t search_size,
+                               const SearchFilters* filters, uint64_t* out_ids, float* out_dists, uint32_t* out_counts) {
+  int rc;
   // Page-locked caller buffers (cudaHostAlloc / cudaHostRegister: what a cgo wrapper keeps for its
   // request batches) are mapped into the device address space: the kernel then reads each query
   // once straight from host memory (512 B per query, when a warp picks the query up) and stores
@@ -538,14 +601,50 @@ int sdb_search_batch(sdb_index* ix, uint32_t B, const float* queries, uint32_t k
   }
   if ((rc = ensure_out_scratch(ix, B, k))) return rc;
   rc = launch_search(ix, B, q_dev, k, search_size, oid_dev ? oid_dev : ix->d_oid.p, od_dev ? od_dev : ix->d_od.p,
-                     oc_dev ? oc_dev : ix->d_oc.p, nullptr, nullptr, nullptr, 0, filtered ? ix->d_filter_seed.p : nullptr, n_seed,
-                     filtered ? ix->d_filter_bits.p : nullptr, ix->stream);
+                     oc_dev ? oc_dev : ix->d_oc.p, nullptr, nullptr, nullptr, 0, filters, ix->stream);
   if (rc) return rc;
   if (!oid_dev) SDB_CUDA(cudaMemcpyAsync(out_ids, ix->d_oid.p, size_t(B) * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, ix->stream));
   if (!od_dev) SDB_CUDA(cudaMemcpyAsync(out_dists, ix->d_od.p, size_t(B) * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
   if (!oc_dev) SDB_CUDA(cudaMemcpyAsync(out_counts, ix->d_oc.p, size_t(B) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ix->stream));
   SDB_CUDA(cudaStreamSynchronize(ix->stream));
   return SDB_OK;
+}
+
+int sdb_search_batch(sdb_index* ix, uint32_t B, const float* queries, uint32_t k, uint32_t search_size,
+                     const uint64_t* filter_ids, uint64_t n_filter, uint64_t* out_ids, float* out_dists,
+                     uint32_t* out_counts) {
+  if (!ix) return fail(SDB_ERR_INVALID, "null index");
+  if (B == 0) return SDB_OK;
+  if (!queries || !out_ids || !out_dists || !out_counts) return fail(SDB_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(ix->mu);
+  SDB_CUDA(cudaSetDevice(ix->device));
+  int rc = check_search_args(ix, k, search_size);
+  if (rc) return rc;
+  // filter_ids != NULL = filtered, even with n_filter == 0 (an empty bitmap filters everything out);
+  // callers whose empty container has a NULL data pointer use sdb_search_batch_filters
+  SearchFilters sf;
+  const bool filtered = filter_ids != nullptr;
+  if (filtered) {
+    const uint64_t offs[2] = {0, n_filter};
+    if ((rc = stage_filters(ix, B, 1, filter_ids, offs, nullptr, search_size, true, &sf))) return rc;
+  }
+  return search_batch_locked(ix, B, queries, k, search_size, filtered ? &sf : nullptr, out_ids, out_dists, out_counts);
+}
+
+int sdb_search_batch_filters(sdb_index* ix, uint32_t B, const float* queries, uint32_t k, uint32_t search_size,
+                             uint32_t n_filters, const uint64_t* filter_ids, const uint64_t* filter_offsets,
+                             const int32_t* query_filter, uint64_t* out_ids, float* out_dists, uint32_t* out_counts) {
+  if (!ix) return fail(SDB_ERR_INVALID, "null index");
+  if (B == 0) return SDB_OK;
+  if (!queries || !out_ids || !out_dists || !out_counts) return fail(SDB_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(ix->mu);
+  SDB_CUDA(cudaSetDevice(ix->device));
+  int rc = check_search_args(ix, k, search_size);
+  if (rc) return rc;
+  if (n_filters == 0) return search_batch_locked(ix, B, queries, k, search_size, nullptr, out_ids, out_dists, out_counts);
+  SearchFilters sf;
+  if ((rc = stage_filters(ix, B, n_filters, filter_ids, filter_offsets, query_filter, search_size, true, &sf))) return rc;
+  return search_batch_locked(ix, B, queries, k, search_size, &sf, out_ids, out_dists, out_counts);
 }
 
 int sdb_search_batch_device(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k, uint32_t search_size,
@@ -558,7 +657,7 @@ int sdb_search_batch_device(sdb_index* ix, uint32_t B, const float* d_queries, u
   int rc = check_search_args(ix, k, search_size);
   if (rc) return rc;
   return launch_search(ix, B, d_queries, k, search_size, d_out_ids, d_out_dists, d_out_counts, nullptr, nullptr, nullptr, 0,
-                       nullptr, 0, nullptr, static_cast<cudaStream_t>(stream));
+                       nullptr, static_cast<cudaStream_t>(stream));
 }
 
 int sdb_last_search_stats(sdb_index* ix, uint32_t B, uint32_t* hops_out, uint32_t* ndist_out) {
@@ -569,6 +668,31 @@ int sdb_last_search_stats(sdb_index* ix, uint32_t B, uint32_t* hops_out, uint32_
   SDB_CUDA(cudaDeviceSynchronize());
   SDB_CUDA(cudaMemcpy(hops_out, ix->d_hops.p, size_t(B) * 4, cudaMemcpyDeviceToHost));
   SDB_CUDA(cudaMemcpy(ndist_out, ix->d_ndist.p, size_t(B) * 4, cudaMemcpyDeviceToHost));
+  return SDB_OK;
+}
+
+int sdb_search_profile(sdb_index* ix, int32_t enable) {
+  if (!ix) return fail(SDB_ERR_INVALID, "null index");
+  std::lock_guard<std::mutex> g(ix->mu);
+  SDB_CUDA(cudaSetDevice(ix->device));
+  if (enable && ix->prof_ev.empty()) {
+    ix->prof_ev.resize(2 * sdb_index::PROF_RING, nullptr);
+    for (auto& e : ix->prof_ev) SDB_CUDA(cudaEventCreate(&e));
+  }
+  ix->prof_on = enable != 0;
+  ix->prof_n = 0;
+  return SDB_OK;
+}
+
+int sdb_search_profile_read(sdb_index* ix, uint32_t cap, float* ms_out, uint32_t* n_out) {
+  if (!ix || !n_out || (cap && !ms_out)) return fail(SDB_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(ix->mu);
+  SDB_CUDA(cudaSetDevice(ix->device));
+  *n_out = ix->prof_n;
+  for (uint32_t i = 0; i < ix->prof_n && i < cap; ++i) {
+    SDB_CUDA(cudaEventSynchronize(ix->prof_ev[2 * i + 1]));
+    SDB_CUDA(cudaEventElapsedTime(ms_out + i, ix->prof_ev[2 * i], ix->prof_ev[2 * i + 1]));
+  }
   return SDB_OK;
 }
 
@@ -588,7 +712,7 @@ int sdb_search_visited(sdb_index* ix, uint32_t B, const float* queries, uint32_t
   if ((rc = ix->d_vis_len.ensure(B))) return rc;
   SDB_CUDA(cudaMemcpyAsync(ix->d_q.p, queries, size_t(B) * ix->p.dim * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
   rc = launch_search(ix, B, ix->d_q.p, 1, search_size, ix->d_oid.p, ix->d_od.p, ix->d_oc.p, ix->d_vis_ids.p, ix->d_vis_d.p,
-                     ix->d_vis_len.p, vis_cap, nullptr, 0, nullptr, ix->stream);
+                     ix->d_vis_len.p, vis_cap, nullptr, ix->stream);
   if (rc) return rc;
   std::vector<uint32_t> ids(size_t(B) * vis_cap);
   std::vector<float> d(size_t(B) * vis_cap);
@@ -651,6 +775,35 @@ int sdb_insert_batch(sdb_index* ix, uint64_t n, const uint64_t* ids, const float
   std::lock_guard<std::mutex> g(ix->mu);
   SDB_CUDA(cudaSetDevice(ix->device));
   return insert_batch_locked(ix, n, ids, vectors);
+}
+
+int sdb_insert_batch_device(sdb_index* ix, uint64_t n, const uint64_t* ids, const float* d_vectors) {
+  if (!ix) return fail(SDB_ERR_INVALID, "null index");
+  if (n == 0) return SDB_OK;
+  if (!ids || !d_vectors) return fail(SDB_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(ix->mu);
+  SDB_CUDA(cudaSetDevice(ix->device));
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, d_vectors) != cudaSuccess || at.type != cudaMemoryTypeDevice || at.device != ix->device) {
+    cudaGetLastError();
+    return fail(SDB_ERR_INVALID, "sdb_insert_batch_device: vectors must be device memory of the index's GPU");
+  }
+  SDB_CUDA(cudaDeviceSynchronize());  // the caller's producer stream is unknown: order after everything
+  return insert_batch_locked(ix, n, ids, d_vectors, false, true);
+}
+
+uint64_t sdb_insert_truncated(const sdb_index* ix) { return ix ? ix->insert_truncated : 0; }
+
+int sdb_insert_stats(sdb_index* ix, uint64_t* out8, int32_t reset) {
+  if (!ix || !out8) return fail(SDB_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(ix->mu);
+  SDB_CUDA(cudaSetDevice(ix->device));
+  for (int i = 0; i < 8; ++i) out8[i] = 0;
+  if (!ix->d_ins_stats) return SDB_OK;
+  SDB_CUDA(cudaStreamSynchronize(ix->stream));
+  SDB_CUDA(cudaMemcpy(out8, ix->d_ins_stats, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if (reset) SDB_CUDA(cudaMemset(ix->d_ins_stats, 0, 8 * sizeof(uint64_t)));
+  return SDB_OK;
 }
 
 int sdb_insert_update_delete(sdb_index* ix, uint64_t n, const uint64_t* ids, const float* vectors,
@@ -780,14 +933,23 @@ int sdb_index_get_codes(sdb_index* ix, uint64_t n, const uint64_t* ids, uint8_t*
   std::lock_guard<std::mutex> g(ix->mu);
   SDB_CUDA(cudaSetDevice(ix->device));
   if (!ix->quant_active()) return fail(SDB_ERR_STATE, "quantizer is not fitted");
-  size_t width = ix->p.quantizer == SDB_QUANT_PRODUCT ? ix->pqM : size_t(ix->words) * 8;
-  size_t pitch = ix->p.quantizer == SDB_QUANT_PRODUCT ? ix->codes_pitch : size_t(ix->bits_pitch) * 8;
+  const uint32_t width = ix->p.quantizer == SDB_QUANT_PRODUCT ? ix->pqM : ix->words * 8;
+  const uint32_t pitch = ix->p.quantizer == SDB_QUANT_PRODUCT ? ix->codes_pitch : ix->bits_pitch * 8;
   const uint8_t* base = ix->p.quantizer == SDB_QUANT_PRODUCT ? ix->d_codes : reinterpret_cast<const uint8_t*>(ix->d_bits);
-  for (uint64_t i = 0; i < n; ++i) {
-    if (ids[i] >= ix->rows || !ix->h_exists[ids[i]]) return fail(SDB_ERR_NOTFOUND, "node id does not exist: " + std::to_string(ids[i]));
-    SDB_CUDA(cudaMemcpyAsync(out + i * width, base + size_t(ids[i]) * pitch, width, cudaMemcpyDeviceToHost, ix->stream));
+  // one gather kernel + one copy per chunk (a 1M-point flush used to issue 1M small copies)
+  const uint64_t chunk = std::max<uint64_t>(1, (uint64_t(256) << 20) / width);
+  std::vector<uint32_t> h32;
+  for (uint64_t s0 = 0; s0 < n; s0 += chunk) {
+    const uint64_t m = std::min(chunk, n - s0);
+    int rc = stage_ids(ix, m, ids + s0, true, false, h32);
+    if (rc) return rc;
+    if ((rc = ix->d_tmp8.ensure(size_t(m) * width))) return rc;
+    gather_codes_kernel<<<uint32_t((m * width + 255) / 256), 256, 0, ix->stream>>>(base, pitch, width, ix->d_tmp32.p, ix->d_tmp8.p, m);
+    ix->launches++;
+    SDB_CUDA(cudaGetLastError());
+    SDB_CUDA(cudaMemcpyAsync(out + s0 * width, ix->d_tmp8.p, size_t(m) * width, cudaMemcpyDeviceToHost, ix->stream));
+    SDB_CUDA(cudaStreamSynchronize(ix->stream));
   }
-  SDB_CUDA(cudaStreamSynchronize(ix->stream));
   return SDB_OK;
 }
 
@@ -797,29 +959,32 @@ int sdb_index_set_codes(sdb_index* ix, uint64_t n, const uint64_t* ids, const ui
   std::lock_guard<std::mutex> g(ix->mu);
   SDB_CUDA(cudaSetDevice(ix->device));
   if (!ix->quant_active()) return fail(SDB_ERR_STATE, "quantizer is not fitted");
-  uint64_t mx = 0;
-  for (uint64_t i = 0; i < n; ++i) {
+  for (uint64_t i = 0; i < n; ++i)
     if (ids[i] == 0) return fail(SDB_ERR_RESERVED_ID, "invalid point id: 0");
-    mx = std::max(mx, ids[i]);
-  }
-  int rc = index_reserve_locked(ix, mx);
-  if (rc) return rc;
-  size_t width = ix->p.quantizer == SDB_QUANT_PRODUCT ? ix->pqM : size_t(ix->words) * 8;
-  size_t pitch = ix->p.quantizer == SDB_QUANT_PRODUCT ? ix->codes_pitch : size_t(ix->bits_pitch) * 8;
-  uint8_t* base = ix->p.quantizer == SDB_QUANT_PRODUCT ? ix->d_codes : reinterpret_cast<uint8_t*>(ix->d_bits);
-  const uint8_t one = 1;
-  for (uint64_t i = 0; i < n; ++i) {
-    SDB_CUDA(cudaMemcpyAsync(base + size_t(ids[i]) * pitch, codes + i * width, width, cudaMemcpyHostToDevice, ix->stream));
-    SDB_CUDA(cudaMemcpyAsync(ix->d_exists + ids[i], &one, 1, cudaMemcpyHostToDevice, ix->stream));
-  }
-  SDB_CUDA(cudaStreamSynchronize(ix->stream));
-  for (uint64_t i = 0; i < n; ++i) {
-    if (!ix->h_exists[ids[i]]) {
-      ix->h_exists[ids[i]] = 1;
-      ix->count++;
+  const uint32_t width = ix->p.quantizer == SDB_QUANT_PRODUCT ? ix->pqM : ix->words * 8;
+  const uint32_t pitch = ix->p.quantizer == SDB_QUANT_PRODUCT ? ix->codes_pitch : ix->bits_pitch * 8;
+  const uint64_t chunk = std::max<uint64_t>(1, (uint64_t(256) << 20) / width);
+  std::vector<uint32_t> h32;
+  for (uint64_t s0 = 0; s0 < n; s0 += chunk) {
+    const uint64_t m = std::min(chunk, n - s0);
+    int rc = stage_ids(ix, m, ids + s0, false, true, h32);  // grows the row arrays
+    if (rc) return rc;
+    uint8_t* base = ix->p.quantizer == SDB_QUANT_PRODUCT ? ix->d_codes : reinterpret_cast<uint8_t*>(ix->d_bits);
+    if ((rc = ix->d_tmp8.ensure(size_t(m) * width))) return rc;
+    SDB_CUDA(cudaMemcpyAsync(ix->d_tmp8.p, codes + s0 * width, size_t(m) * width, cudaMemcpyHostToDevice, ix->stream));
+    scatter_codes_kernel<<<uint32_t((m * width + 255) / 256), 256, 0, ix->stream>>>(base, pitch, width, ix->d_exists, ix->d_tmp32.p, ix->d_tmp8.p, m);
+    ix->launches++;
+    SDB_CUDA(cudaGetLastError());
+    SDB_CUDA(cudaStreamSynchronize(ix->stream));
+    for (uint64_t i = 0; i < m; ++i) {
+      if (!ix->h_exists[h32[i]]) {
+        ix->h_exists[h32[i]] = 1;
+        ix->count++;
+      }
+      if (h32[i] != START_ID && h32[i] > ix->max_node_id) ix->max_node_id = h32[i];
     }
-    if (ids[i] > ix->max_node_id) ix->max_node_id = uint32_t(ids[i]);
   }
+  ix->vec_epoch++;
   return SDB_OK;
 }
 

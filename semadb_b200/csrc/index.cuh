@@ -121,8 +121,11 @@ struct sdb_index {
   sdb::DevBuf<float> d_od;
   sdb::DevBuf<uint32_t> d_oc, d_hops, d_ndist;
   sdb::DevBuf<uint32_t> d_work;
+  sdb::DevBuf<uint32_t> d_retry_bitmap;  // RETRY launch: [retry_slots][rows/32] exact visited bitmaps
+  uint32_t retry_slots = 1;
   sdb::DevBuf<float> d_adc;
-  sdb::DevBuf<uint32_t> d_filter_seed, d_filter_bits;
+  sdb::DevBuf<uint32_t> d_filter_ids, d_filter_off, d_filter_bits, d_qmap;
+  sdb::DevBuf<int32_t> d_query_filter;
   sdb::DevBuf<uint32_t> d_vis_ids, d_vis_len;
   sdb::DevBuf<float> d_vis_d;
   sdb::DevBuf<uint64_t> d_ids64;
@@ -145,6 +148,13 @@ struct sdb_index {
   bool retry_check_pending = false;  // d_work holds the retry count of the last search
   cudaStream_t last_search_stream = nullptr;
   uint64_t launches = 0;
+  // sdb_search_profile: CUDA events around the first-pass beam-search kernel of each search
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;  // [2 * PROF_RING]: start, stop pairs
+  uint32_t prof_n = 0;               // searches recorded since enabling
+  static constexpr uint32_t PROF_RING = 256;
+  unsigned long long* d_ins_stats = nullptr;  // [8] running totals of the batched insert (insert.cu)
+  uint64_t insert_truncated = 0;  // inserts whose visited list was cut to MAX_CAND candidates (insert.cu)
 
   // insert schedule
   uint32_t ins_min_batch = 1, ins_max_batch = 16384, ins_growth_div = 16;  // 4096 -> 16384: 1M x 128 builds in 1.87 s instead of 2.39 s, same recall (profiles/r01_ab_insert.txt)
@@ -156,10 +166,23 @@ struct sdb_index {
 
 namespace sdb {
 int index_reserve_locked(sdb_index* ix, uint64_t max_node_id);
+int peer_barrier_poisoned(int device);  // dist.cu: SDB_ERR_STATE once a cross-GPU barrier on the device has timed out
+// Device-side description of a batch's filters (search.cuh SearchArgs): nullptr = no request is
+// filtered. qmap_*: the batch positions of the filtered / unfiltered requests (either may be
+// nullptr when its count is 0 or B).
+struct SearchFilters {
+  const uint32_t* ids = nullptr;          // concatenated ascending ids
+  const uint32_t* off = nullptr;          // [n_filters + 1]
+  const int32_t* query_filter = nullptr;  // [B], nullptr = every filtered query uses filter 0
+  const uint32_t* bits = nullptr;         // optional bitmask over rows of filter 0
+  const uint32_t* qmap_filtered = nullptr;
+  uint32_t n_filtered = 0;
+  const uint32_t* qmap_plain = nullptr;
+  uint32_t n_plain = 0;
+};
 int launch_search(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k, uint32_t L, uint64_t* d_out_ids,
                   float* d_out_dists, uint32_t* d_out_counts, uint32_t* d_vis_ids, float* d_vis_dists,
-                  uint32_t* d_vis_len, uint32_t vis_cap, const uint32_t* d_filter_seed, uint32_t n_filter_seed,
-                  const uint32_t* d_filter_bits, cudaStream_t stream);
+                  uint32_t* d_vis_len, uint32_t vis_cap, const SearchFilters* filters, cudaStream_t stream);
 int launch_flat(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k, const uint32_t* d_filter_bits,
                 uint64_t* d_out_ids, float* d_out_dists, uint32_t* d_out_counts, cudaStream_t stream);
 int launch_flat_exact(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k, const uint32_t* d_filter_bits,
@@ -173,7 +196,8 @@ int launch_adc_tables(sdb_index* ix, uint32_t B, const float* d_queries, float* 
 int launch_merge(uint32_t S, uint32_t B, uint32_t k, const uint64_t* in_ids, const float* in_d, const uint32_t* in_c,
                  uint64_t* out_ids, float* out_d, uint32_t* out_c, cudaStream_t stream);
 // reinsert: ids already exist (update path, vamana.go:249-253): rows are overwritten, one point per mini-batch
-int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const float* vectors, bool reinsert = false);
+int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const float* vectors, bool reinsert = false,
+                        bool vectors_on_device = false);
 // VectorStore.Set on device-resident ids/vectors: scatter rows, mark exists, encode if fitted
 int set_rows_device(sdb_index* ix, uint32_t n, const uint32_t* d_ids, const float* d_vecs, cudaStream_t stream);
 int fit_locked(sdb_index* ix, uint64_t pq_first_row, int32_t* fitted);

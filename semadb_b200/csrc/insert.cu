@@ -30,6 +30,9 @@ namespace sdb {
 
 namespace {
 
+// running totals behind sdb_insert_stats (the terms of the build's algorithmic-bytes figure)
+enum : int { INS_POINTS = 0, INS_HOPS, INS_NDIST, INS_EDGES, INS_TARGETS, INS_PRUNES, INS_PRUNE_CAND, INS_NSTATS = 8 };
+
 struct InsertArgs {
   StoreView s;
   uint32_t* adj; uint32_t* deg; uint8_t* dirty; uint32_t R; float alpha;
@@ -43,6 +46,8 @@ struct InsertArgs {
   uint32_t* pair_val;        // [m*R] pair index (batch order)
   int staged_max;            // rows that fit in shared memory
   uint32_t* error_flag;
+  const uint32_t* ndist;     // [m] distance evaluations of each point's search
+  unsigned long long* stats; // running totals for sdb_insert_stats
 };
 
 __global__ void __launch_bounds__(PRUNE_THREADS) prune_new_kernel(InsertArgs a) {
@@ -53,7 +58,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS) prune_new_kernel(InsertArgs a) 
   const uint32_t A = a.new_ids[b];
   uint32_t n = a.vis_len[b];
   if (n > a.vis_cap || n > MAX_CAND) {
-    if (threadIdx.x == 0) atomicExch(a.error_flag, 1u);
+    if (threadIdx.x == 0) atomicAdd(a.error_flag, 1u);
     n = min(min(n, a.vis_cap), uint32_t(MAX_CAND));
   }
   sh.n = int(n);
@@ -76,6 +81,10 @@ __global__ void __launch_bounds__(PRUNE_THREADS) prune_new_kernel(InsertArgs a) 
   if (threadIdx.x == 0) {
     a.deg[A] = uint32_t(cnt);
     a.dirty[A] = 1;
+    atomicAdd(a.stats + INS_POINTS, 1ull);
+    atomicAdd(a.stats + INS_HOPS, (unsigned long long)a.vis_len[b]);
+    atomicAdd(a.stats + INS_NDIST, (unsigned long long)a.ndist[b]);
+    atomicAdd(a.stats + INS_EDGES, (unsigned long long)cnt);
   }
 }
 
@@ -106,6 +115,7 @@ struct BackArgs {
   const uint32_t* seg_start;
   const uint32_t* seg_count;
   int staged_max;
+  unsigned long long* stats;
 };
 
 __global__ void __launch_bounds__(PRUNE_THREADS) backedge_kernel(BackArgs a) {
@@ -172,6 +182,10 @@ __global__ void __launch_bounds__(PRUNE_THREADS) backedge_kernel(BackArgs a) {
         if (act && g == 0) sh.dist[j] = d;
       }
       __syncthreads();
+      if (threadIdx.x == 0) {
+        atomicAdd(a.stats + INS_PRUNES, 1ull);
+        atomicAdd(a.stats + INS_PRUNE_CAND, (unsigned long long)n);
+      }
       stable_sort_by_dist(sh);  // candidateSet.Sort() (insert.go:58)
       int staged = min(n, a.staged_max);
       stage_rows(a.s, sh, dyn, staged);
@@ -186,6 +200,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS) backedge_kernel(BackArgs a) {
     if (threadIdx.x == 0) {
       a.deg[B] = uint32_t(cur_n);
       a.dirty[B] = 1;
+      atomicAdd(a.stats + INS_TARGETS, 1ull);
     }
   }
 }
@@ -235,7 +250,8 @@ __global__ void check_rows_kernel(const uint32_t* adj, const uint32_t* deg, cons
 
 }  // namespace
 
-int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const float* vectors, bool reinsert) {
+int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const float* vectors, bool reinsert,
+                        bool vectors_on_device) {
   // classify like insertUpdateDelete (vamana.go:149-185): only fresh inserts are handled here
   std::vector<uint32_t> h32(n);
   uint64_t mx = 0;
@@ -251,6 +267,10 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
   int rc = index_reserve_locked(ix, mx);
   if (rc) return rc;
   cudaStream_t st = ix->stream;
+  if (!ix->d_ins_stats) {
+    SDB_CUDA(cudaMalloc(reinterpret_cast<void**>(&ix->d_ins_stats), INS_NSTATS * sizeof(unsigned long long)));
+    SDB_CUDA(cudaMemsetAsync(ix->d_ins_stats, 0, INS_NSTATS * sizeof(unsigned long long), st));
+  }
   const uint32_t R = ix->p.degree_bound, L = ix->p.search_size, dim = ix->p.dim;
   const uint32_t vis_cap = MAX_CAND;
   // updated points are re-inserted one by one (vamana.go:249-253) unless the index is relaxed
@@ -327,11 +347,15 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
   for (uint64_t c0 = 0; c0 < n; c0 += chunk_pts) {
     const uint64_t cn = std::min(chunk_pts, n - c0);
     INS_CHECK(d_ids.ensure(cn));
-    INS_CHECK(d_vecs.ensure(size_t(cn) * dim));
     INS_CUDA(cudaMemcpyAsync(d_ids.p, h32.data() + c0, cn * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    INS_CUDA(cudaMemcpyAsync(d_vecs.p, vectors + c0 * dim, size_t(cn) * dim * sizeof(float), cudaMemcpyHostToDevice, st));
+    const float* chunk_vecs = vectors + c0 * dim;  // device-resident input is used where it lies
+    if (!vectors_on_device) {
+      INS_CHECK(d_vecs.ensure(size_t(cn) * dim));
+      INS_CUDA(cudaMemcpyAsync(d_vecs.p, vectors + c0 * dim, size_t(cn) * dim * sizeof(float), cudaMemcpyHostToDevice, st));
+      chunk_vecs = d_vecs.p;
+    }
     // vecStore.Set for the chunk (insert.go:17): rows become visible, nothing points at them yet
-    INS_CHECK(set_rows_device(ix, uint32_t(cn), d_ids.p, d_vecs.p, st));
+    INS_CHECK(set_rows_device(ix, uint32_t(cn), d_ids.p, chunk_vecs, st));
     StoreView view = make_view(ix);
     // rows staged per CTA: aim for >= 2 CTAs/SM
     size_t budget = std::min<size_t>(ix->smem_optin, size_t(100) << 10);
@@ -362,7 +386,7 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
       if (timing) cudaStreamSynchronize(st);
       // 1. greedySearch(vec, 1, L) with the visited list
       INS_CHECK(launch_search(ix, m, b_vecs, 1, L, ix->d_oid.p, ix->d_od.p, ix->d_oc.p, ix->d_vis_ids.p, ix->d_vis_d.p,
-                              ix->d_vis_len.p, vis_cap, nullptr, 0, nullptr, st));
+                              ix->d_vis_len.p, vis_cap, nullptr, st));
       tick(0, t0);
       // 2. robustPrune(A) + emit back-edge pairs
       InsertArgs ia{};
@@ -370,6 +394,7 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
       ia.new_ids = b_ids; ia.vis_ids = ix->d_vis_ids.p; ia.vis_dists = ix->d_vis_d.p; ia.vis_len = ix->d_vis_len.p;
       ia.vis_cap = vis_cap; ia.m = m; ia.pair_key = d_pair_key.p; ia.pair_val = d_pair_val.p;
       ia.staged_max = staged_max; ia.error_flag = d_err;
+      ia.ndist = ix->d_ndist.p; ia.stats = ix->d_ins_stats;
       prune_new_kernel<<<m, PRUNE_THREADS, dyn_smem, st>>>(ia);
       ix->launches++;
       INS_CUDA(cudaGetLastError());
@@ -396,7 +421,7 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
       BackArgs ba{};
       ba.s = view; ba.adj = ix->d_adj; ba.deg = ix->d_deg; ba.dirty = ix->d_dirty; ba.R = R; ba.alpha = ix->p.alpha;
       ba.new_ids = b_ids; ba.keys = skeys; ba.vals = svals; ba.n_pairs = np; ba.seg_start = d_seg.p;
-      ba.seg_count = d_segcount; ba.staged_max = staged_max;
+      ba.seg_count = d_segcount; ba.staged_max = staged_max; ba.stats = ix->d_ins_stats;
       if (m == 1) {
         // a single new point: every target is its own segment, in edge order — no sort needed
         iota_segments_kernel<<<1, 64, 0, st>>>(skeys, np, d_seg.p, d_segcount);
@@ -442,7 +467,7 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
       uint32_t m = uint32_t(std::min<uint64_t>(std::min<uint64_t>(want, max_batch), cn - done));
       if (m == 0) m = 1;
       const uint32_t* b_ids = d_ids.p + done;
-      const float* b_vecs = d_vecs.p + done * dim;
+      const float* b_vecs = chunk_vecs + done * dim;
       INS_CHECK(run_batch(b_ids, b_vecs, m, c0 + done));
       if (repair && m > 1) {
         // Re-insert the points nobody points at, in quarter-size mini-batches: mutually close
@@ -490,7 +515,11 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
     }
     if (h32[i] > ix->max_node_id) ix->max_node_id = h32[i];
   }
-  if (h_misc[1]) return fail(SDB_ERR_INTERNAL, "visited list exceeded the robustPrune candidate capacity");
+  // A visited list longer than MAX_CAND was cut to its first MAX_CAND expansions before robustPrune
+  // (the reference's list is unbounded; never observed below 6M-point hamming shards at 512). The
+  // graph is valid and the index state is committed, so this is counted, not an error: failing
+  // here would leave host and device state apart (the points exist on the device).
+  ix->insert_truncated += h_misc[1];
   return SDB_OK;
 }
 

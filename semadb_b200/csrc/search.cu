@@ -1,6 +1,8 @@
 // search.cu — dispatch of the beam-search kernel variants (search.cuh).
 #include "search_launch.cuh"
 
+#include <algorithm>
+
 namespace sdb {
 
 namespace launch {
@@ -11,10 +13,11 @@ extern template int launch_float<METRIC_COSINE>(sdb_index*, const SearchArgs&, b
 }  // namespace launch
 using namespace launch;
 
+static int dispatch_search(sdb_index* ix, const SearchArgs& a, bool filtered, cudaStream_t stream);
+
 int launch_search(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k, uint32_t L, uint64_t* d_out_ids,
                   float* d_out_dists, uint32_t* d_out_counts, uint32_t* d_vis_ids, float* d_vis_dists,
-                  uint32_t* d_vis_len, uint32_t vis_cap, const uint32_t* d_filter_seed, uint32_t n_filter_seed,
-                  const uint32_t* d_filter_bits, cudaStream_t stream) {
+                  uint32_t* d_vis_len, uint32_t vis_cap, const SearchFilters* filters, cudaStream_t stream) {
   // Visited-table size for this launch: start at 5888 slots; if the previous search on this
   // handle sent more than 0.1 % of its queries to the RETRY launch (they visited more nodes than
   // 87.5 % of the table), step up. Read only when the stream is idle: never adds a sync.
@@ -66,9 +69,16 @@ int launch_search(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k,
   a.vis_dists = d_vis_dists;
   a.vis_len = d_vis_len;
   a.vis_cap = vis_cap;
-  a.filter_seed = d_filter_seed;
-  a.n_filter_seed = n_filter_seed;
-  a.filter_bits = d_filter_bits;
+  a.n_work = B;
+  // RETRY launch: one visited bitmap over all rows per resident CTA (at most 512 MB in total)
+  {
+    const uint32_t words = ((ix->rows + 31) / 32 + 3) / 4 * 4;
+    uint32_t slots = uint32_t(std::min<uint64_t>(uint64_t(ix->sm_count), std::max<uint64_t>(1, (uint64_t(512) << 20) / (uint64_t(words) * 4))));
+    if ((rc = ix->d_retry_bitmap.ensure(size_t(words) * slots))) return rc;
+    a.retry_bitmap = ix->d_retry_bitmap.p;
+    a.bitmap_words = words;
+    ix->retry_slots = slots;
+  }
   {
     const char* e = getenv("SDB_K1_FLAGS");
     a.flags = e ? uint32_t(atoi(e)) : 0u;
@@ -80,8 +90,34 @@ int launch_search(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k,
   ix->last_B = B;
   ix->retry_check_pending = true;
   ix->last_search_stream = stream;
-  const bool filtered = d_filter_bits != nullptr;
+  if (ix->p.quantizer == SDB_QUANT_PRODUCT && ix->pq_fitted) {
+    if ((rc = ix->d_adc.ensure(size_t(B) * ix->pqM * ix->pqK))) return rc;
+    if ((rc = launch_adc_tables(ix, B, d_queries, ix->d_adc.p, stream))) return rc;
+    a.adc = ix->d_adc.p;
+  }
+  if (filters == nullptr) return dispatch_search(ix, a, false, stream);
+  // per-request filters: the unfiltered requests of the batch run through the fast kernels, the
+  // filtered ones through the FILTER variant, each over its own subset of the batch
+  if (filters->n_plain > 0) {
+    SearchArgs u = a;
+    u.qmap = filters->n_plain == B ? nullptr : filters->qmap_plain;
+    u.n_work = filters->n_plain;
+    if ((rc = dispatch_search(ix, u, false, stream))) return rc;
+    if (filters->n_filtered > 0) SDB_CUDA(cudaMemsetAsync(ix->d_work.p, 0, 4 * sizeof(uint32_t), stream));
+  }
+  if (filters->n_filtered > 0) {
+    a.filter_ids = filters->ids;
+    a.filter_off = filters->off;
+    a.query_filter = filters->query_filter;
+    a.filter_bits = filters->bits;
+    a.qmap = filters->n_filtered == B ? nullptr : filters->qmap_filtered;
+    a.n_work = filters->n_filtered;
+    return dispatch_search(ix, a, true, stream);
+  }
+  return SDB_OK;
+}
 
+static int dispatch_search(sdb_index* ix, const SearchArgs& a, bool filtered, cudaStream_t stream) {
   if (ix->p.quantizer == SDB_QUANT_BINARY && ix->bq_fitted) {
     // KIND = bits: METRIC = hamming / jaccard, TRIPS = 128-byte chunks per row, SETS = pipeline depth
     const bool jac = ix->bq_metric == SDB_METRIC_JACCARD;
@@ -99,20 +135,18 @@ int launch_search(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k,
     return launch_with_retry<EVAL_BITS, METRIC_HAMMING, 4, 2, false, 2, false, 12>(ix, a, stream);
   }
   if (ix->p.quantizer == SDB_QUANT_PRODUCT && ix->pq_fitted) {
-    if ((rc = ix->d_adc.ensure(size_t(B) * ix->pqM * ix->pqK))) return rc;
-    if ((rc = launch_adc_tables(ix, B, d_queries, ix->d_adc.p, stream))) return rc;
-    a.adc = ix->d_adc.p;
     // ADC table in shared memory when at least two query-warps per SM can hold theirs (C4:
     // 96 x 256 x 4 B = 96 KB => exactly two); otherwise the table is read through L1/L2
     const size_t fixed = warp_smem_bytes<VisitedCompactN, false>(0, 0, 0, ix->pqM * ix->pqK) + 1024;
     const size_t room = ix->smem_per_sm / 2 > fixed ? (ix->smem_per_sm / 2 - fixed) / 2 : 0;  // 16-bit visited slots
     if (!filtered && room >= 4096 && !getenv("SDB_ADC_GLOBAL")) {
-      if (a.vt_slots > room) a.vt_slots = uint32_t(room) / 8 * 8;
+      SearchArgs t = a;
+      if (t.vt_slots > room) t.vt_slots = uint32_t(room) / 8 * 8;
       const uint32_t nch = (ix->pqM + 15) / 16;
-      if (nch <= 2) return launch_with_retry<EVAL_ADC_SMEM, 0, 2, 1, false, 2, false, 12>(ix, a, stream);
-      if (nch <= 4) return launch_with_retry<EVAL_ADC_SMEM, 0, 4, 1, false, 2, false, 12>(ix, a, stream);
-      if (nch <= 6) return launch_with_retry<EVAL_ADC_SMEM, 0, 6, 1, false, 2, false, 12>(ix, a, stream);
-      return launch_with_retry<EVAL_ADC_SMEM, 0, 8, 1, false, 2, false, 12>(ix, a, stream);
+      if (nch <= 2) return launch_with_retry<EVAL_ADC_SMEM, 0, 2, 1, false, 2, false, 12>(ix, t, stream);
+      if (nch <= 4) return launch_with_retry<EVAL_ADC_SMEM, 0, 4, 1, false, 2, false, 12>(ix, t, stream);
+      if (nch <= 6) return launch_with_retry<EVAL_ADC_SMEM, 0, 6, 1, false, 2, false, 12>(ix, t, stream);
+      return launch_with_retry<EVAL_ADC_SMEM, 0, 8, 1, false, 2, false, 12>(ix, t, stream);
     }
     return filtered ? launch_with_retry<EVAL_ADC, 0, 1, 1, false, 0, true, 1>(ix, a, stream)
                     : launch_with_retry<EVAL_ADC, 0, 1, 1, false, 2, false, 12>(ix, a, stream);
@@ -151,9 +185,10 @@ extern "C" int sdb_search_batch_gather_device(sdb_index* ix, uint32_t B, const f
   }
   std::lock_guard<std::mutex> lk(ix->mu);
   SDB_CUDA(cudaSetDevice(ix->device));
+  if (int prc = peer_barrier_poisoned(ix->device)) return prc;
   ix->gather = &g;
   int rc = launch_search(ix, B, d_queries, k, search_size, d_out_ids, d_out_dists, d_out_counts, nullptr, nullptr, nullptr, 0,
-                         nullptr, 0, nullptr, static_cast<cudaStream_t>(stream));
+                         nullptr, static_cast<cudaStream_t>(stream));
   ix->gather = nullptr;
   return rc;
 }

@@ -82,10 +82,21 @@ struct SearchArgs {
   float* vis_dists;
   uint32_t* vis_len;
   uint32_t vis_cap;
-  // optional filter (search.go:33-51,93-95)
-  const uint32_t* filter_seed;  // first min(L, n) filter ids ascending
-  uint32_t n_filter_seed;
-  const uint32_t* filter_bits;  // bitmask over rows
+  // optional filters (search.go:33-51,93-95), one per request like shard/index/search.go:59-85:
+  // filter f = ascending ids filter_ids[filter_off[f] .. filter_off[f+1]); query qi uses filter
+  // query_filter[qi] (nullptr: every query uses filter 0). The first min(L, n) ids of a filter
+  // are its seeds. filter_bits: optional dense bitmask over rows of filter 0 (shared-filter calls).
+  const uint32_t* filter_ids;
+  const uint32_t* filter_off;
+  const int32_t* query_filter;
+  const uint32_t* filter_bits;
+  // optional work map: this launch covers queries qmap[0..n_work) (nullptr: 0..B-1). A batch that
+  // mixes filtered and unfiltered requests runs as two launches over disjoint subsets.
+  const uint32_t* qmap;
+  uint32_t n_work;
+  // RETRY launch: one exact visited bitmap over all rows per CTA, in global memory
+  uint32_t* retry_bitmap;
+  uint32_t bitmap_words;
   // work distribution: work_counter hands out batch slots; a query whose visited table
   // overflows is appended to retry_list and re-run by the RETRY launch (bigger table).
   uint32_t vt_slots;  // VisitedCompactN slot count for this launch
@@ -105,7 +116,7 @@ struct VisitedTable {
   uint32_t* t;
   bool failed;
   __device__ __forceinline__ uint32_t limit() const { return LIMIT; }
-  __device__ __forceinline__ void init(unsigned char* base, uint32_t, uint32_t) { t = reinterpret_cast<uint32_t*>(base); }
+  __device__ __forceinline__ void init(unsigned char* base, uint32_t, uint32_t, uint32_t*, uint32_t) { t = reinterpret_cast<uint32_t*>(base); }
   __device__ __forceinline__ void clear(int lane) {
     uint4 e = make_uint4(INVALID_ID, INVALID_ID, INVALID_ID, INVALID_ID);
     uint4* p = reinterpret_cast<uint4*>(t);
@@ -132,6 +143,7 @@ struct VisitedTable {
     n0 = test_and_set(i0, a0, lane);
     n1 = test_and_set(i1, a1, lane);
   }
+  __device__ __forceinline__ bool maybe_new(uint32_t) const { return true; }
 };
 
 // ---- exact visited set, compact form: 8192 x 16-bit entries + a 32-entry u32 stash ------
@@ -152,7 +164,7 @@ struct VisitedCompact {
   uint32_t mask, rb, rmask, dmax;
   bool failed;
   __device__ __forceinline__ uint32_t limit() const { return LIMIT; }
-  __device__ __forceinline__ void init(unsigned char* base, uint32_t rows, uint32_t) {
+  __device__ __forceinline__ void init(unsigned char* base, uint32_t rows, uint32_t, uint32_t*, uint32_t) {
     t = reinterpret_cast<unsigned short*>(base);
     uint32_t b = rows <= SLOTS ? HB : 32 - __clz(rows - 1);
     if (b < HB) b = HB;
@@ -246,6 +258,7 @@ struct VisitedCompact {
     }
     if (__any_sync(SDB_FULL, spill)) failed = true;
   }
+  __device__ __forceinline__ bool maybe_new(uint32_t) const { return true; }
 };
 
 // ---- exact visited set, compact form with a launch-time slot count ------------------------
@@ -263,7 +276,7 @@ struct VisitedCompactN {
   uint32_t nslots, mask, span, magic, used, dmax, lim;
   bool failed;
   __device__ __forceinline__ uint32_t limit() const { return lim; }
-  __device__ __forceinline__ void init(unsigned char* base, uint32_t rows, uint32_t slots) {
+  __device__ __forceinline__ void init(unsigned char* base, uint32_t rows, uint32_t slots, uint32_t*, uint32_t) {
     t = reinterpret_cast<unsigned short*>(base);
     nslots = slots;
     uint32_t b = rows <= 2 ? 1 : 32 - __clz(rows - 1);
@@ -339,6 +352,56 @@ struct VisitedCompactN {
     test_and_set2(id, active, 0, false, n0, n1, lane);
     return n0;
   }
+  // Read-only hint for the speculative row prefetch: false only if id is certainly in the set
+  // (three probes, no loop, no vote); "true" may be wrong, which costs one wasted prefetch.
+  __device__ __forceinline__ bool maybe_new(uint32_t id) const {
+    uint32_t slot, c;
+    home(id, slot, c);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const uint32_t h = t[slot];
+      if (h == c) return false;
+      if (h == 0) return true;
+      slot = slot + 1 == used ? 0 : slot + 1;
+      c += span;
+    }
+    return true;
+  }
+};
+
+// ---- exact visited set of the RETRY launch: one bit per row, in global memory ------------
+// The reference's visited set never fills up (a bitset sized by maxNodeId, distset.go:41,
+// 140-155). A query whose compact shared-memory table overflowed is re-run against this
+// bitmap — one per resident CTA of the RETRY launch, cleared per query — so a search always
+// completes exactly, however many nodes it visits; the overflow marker never reaches a caller.
+struct VisitedBitmap {
+  static __host__ __device__ constexpr size_t bytes(uint32_t) { return 0; }
+  uint32_t* t;
+  uint32_t words;
+  bool failed;
+  __device__ __forceinline__ uint32_t limit() const { return 0xFFFFFFFFu; }
+  __device__ __forceinline__ void init(unsigned char*, uint32_t, uint32_t, uint32_t* g, uint32_t gwords) {
+    t = g + size_t(blockIdx.x) * gwords;
+    words = gwords;
+  }
+  __device__ __forceinline__ void clear(int lane) {
+    uint4 z = make_uint4(0, 0, 0, 0);
+    uint4* p = reinterpret_cast<uint4*>(t);
+    for (uint32_t i = lane; i < words / 4; i += 32) p[i] = z;
+    failed = false;
+    __syncwarp();
+  }
+  __device__ __forceinline__ bool test_and_set(uint32_t id, bool active, int) {
+    if (!active) return false;
+    const uint32_t bit = 1u << (id & 31);
+    return (atomicOr(t + (id >> 5), bit) & bit) == 0;
+  }
+  __device__ __forceinline__ void test_and_set2(uint32_t i0, bool a0, uint32_t i1, bool a1, bool& n0, bool& n1, int lane) {
+    n0 = test_and_set(i0, a0, lane);
+    n1 = test_and_set(i1, a1, lane);
+    __syncwarp();
+  }
+  __device__ __forceinline__ bool maybe_new(uint32_t id) const { return ((t[id >> 5] >> (id & 31)) & 1u) == 0; }
 };
 
 // ---- bounded candidate list (distset.go:133-200) in shared memory ------------------
@@ -746,13 +809,15 @@ struct BitEval {
     const int ci = s * 4 + grp;
     if (g == 0 && ci < n) cdist[ci] = bits_finish(BMETRIC, x, u);
   }
-  __device__ __forceinline__ void eval(const SearchArgs& a, const uint32_t* cid, float* cdist, int n, int lane) {
+  template <class Hook>
+  __device__ __forceinline__ void eval(const SearchArgs& a, const uint32_t* cid, float* cdist, int n, int lane, Hook&& hook) {
     const int g = lane & 7, grp = lane >> 3;
     const int nsets = (n + 3) >> 2;
     uint4 v[SETS][NCH];
 #pragma unroll
     for (int u = 0; u < SETS; ++u)
       if (u < nsets) issue(a, cid, n, u, g, grp, v[u]);
+    hook();  // this hop's first rows are in flight: speculative prefetches for the next hop ride along
     for (int base = 0; base < nsets; base += SETS) {
 #pragma unroll
       for (int u = 0; u < SETS; ++u) {
@@ -771,7 +836,9 @@ struct BitEval {
 // candidate sums M table entries sequentially in f32 (product.go:271-275).
 struct AdcEval {
   const float* table;  // [M*K] for this query (global)
-  __device__ __forceinline__ void eval(const SearchArgs& a, const uint32_t* cid, float* cdist, int n, int lane) {
+  template <class Hook>
+  __device__ __forceinline__ void eval(const SearchArgs& a, const uint32_t* cid, float* cdist, int n, int lane, Hook&& hook) {
+    hook();
     for (int c = lane; c < n; c += 32) {
       const uint8_t* code = a.codes + size_t(cid[c]) * a.codes_pitch;
       float d = 0.0f;
@@ -801,6 +868,7 @@ struct AdcEval {
 // lookup, and the two sums advance as independent sequential f32 chains in sub-vector order
 // (product.go:271-275), so the result is the same float the global-table path and the reference
 // produce.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
@@ -855,8 +923,8 @@ struct AdcEvalSmem {
   // TWO: the hop staged more than 32 candidates, lanes run a second chain for slot lane+32.
   // K256: K = 256 (the reference's maximum and the C4 shape): the table offset of sub-vector i
   // is the compile-time constant i*1024 B, so a lookup is shift/mask + LDS + FADD.
-  template <bool TWO, bool K256>
-  __device__ __forceinline__ void chains(const SearchArgs& a, const uint32_t* cid, float* cdist, int n, int lane) {
+  template <bool TWO, bool K256, class Hook>
+  __device__ __forceinline__ void chains(const SearchArgs& a, const uint32_t* cid, float* cdist, int n, int lane, Hook&& hook) {
     const bool h0 = lane < n, h1 = TWO && lane + 32 < n;
     const uint8_t* r0 = a.codes + size_t(h0 ? cid[lane] : cid[0]) * a.codes_pitch;
     const uint8_t* r1 = a.codes + size_t(h1 ? cid[lane + 32] : cid[0]) * a.codes_pitch;
@@ -871,6 +939,7 @@ struct AdcEvalSmem {
         v0[c] = in ? ldg_u4_stream(r0 + (cb + c) * 16) : make_uint4(0, 0, 0, 0);
         if (TWO) v1[c] = in ? ldg_u4_stream(r1 + (cb + c) * 16) : make_uint4(0, 0, 0, 0);
       }
+      if (cb == 0) hook();  // code rows in flight: speculative prefetches for the next hop ride along
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         const uint32_t w0[4] = {v0[c].x, v0[c].y, v0[c].z, v0[c].w};
@@ -907,13 +976,14 @@ struct AdcEvalSmem {
     if (h1) cdist[lane + 32] = d1;
     __syncwarp();
   }
-  __device__ __forceinline__ void eval(const SearchArgs& a, const uint32_t* cid, float* cdist, int n, int lane) {
+  template <class Hook>
+  __device__ __forceinline__ void eval(const SearchArgs& a, const uint32_t* cid, float* cdist, int n, int lane, Hook&& hook) {
     if (a.pqK == 256) {
-      if (n > 32) chains<true, true>(a, cid, cdist, n, lane);
-      else chains<false, true>(a, cid, cdist, n, lane);
+      if (n > 32) chains<true, true>(a, cid, cdist, n, lane, hook);
+      else chains<false, true>(a, cid, cdist, n, lane, hook);
     } else {
-      if (n > 32) chains<true, false>(a, cid, cdist, n, lane);
-      else chains<false, false>(a, cid, cdist, n, lane);
+      if (n > 32) chains<true, false>(a, cid, cdist, n, lane, hook);
+      else chains<false, false>(a, cid, cdist, n, lane, hook);
     }
   }
 };
@@ -937,13 +1007,13 @@ __host__ __device__ constexpr size_t warp_smem_bytes(uint32_t qfloats, uint32_t 
 // least that many candidates survive.
 // XTRA: the start node has edges beyond R (a.start_extra) — compiled in only when it does.
 template <int KIND, int METRIC, int TRIPS, int SETS, bool LEGACY, int MERGE_MIN, class VT, bool FILTER, bool RETRY, int MINB,
-          bool XTRA>
+          bool XTRA, bool PF>
 __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uint32_t qfloats, uint32_t qwords) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   unsigned char* base = smem_raw;
   VT vt;
-  vt.init(base, a.rows, a.vt_slots);
+  vt.init(base, a.rows, a.vt_slots, a.retry_bitmap, a.bitmap_words);
   base += ((VT::bytes(a.vt_slots) + 15) / 16) * 16;
   CandList list;
   list.id = reinterpret_cast<uint32_t*>(base);
@@ -973,12 +1043,15 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
     __syncwarp();
   }
   const uint32_t lt = (1u << lane) - 1;
+  // speculative L2 prefetch of the runner-up's rows: the small-row evaluators only (see the hop loop)
+  constexpr bool PFROWS = PF && (KIND == EVAL_BITS || KIND == EVAL_ADC_SMEM || KIND == EVAL_ADC);
 
   for (;;) {
     uint32_t qi = 0;
     if (lane == 0) {
       qi = atomicAdd(a.work_counter, 1u);
       if (RETRY) qi = qi < *a.retry_count ? a.retry_list[qi] : 0xFFFFFFFFu;
+      else if (a.qmap) qi = qi < a.n_work ? a.qmap[qi] : 0xFFFFFFFFu;
     }
     qi = __shfl_sync(SDB_FULL, qi, 0);
     if (qi >= a.B) break;
@@ -1004,13 +1077,15 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
     if (KIND == EVAL_FLOAT_GENERIC) ev_gen.load_query(qs, lane);
     if (KIND == EVAL_BITS) ev_bits.encode_query(a, qs, qbits, lane);
     if (KIND == EVAL_ADC) ev_adc.table = a.adc + size_t(qi) * a.pqM * a.pqK;
-    auto evaluate = [&](int n) {
+    auto no_hook = []() {};
+    auto evaluate_h = [&](int n, auto&& hook) {
       if (KIND == EVAL_FLOAT_FIXED) ev_fixed.eval(a, cid, cdist, n, lane);
       if (KIND == EVAL_FLOAT_GENERIC) ev_gen.eval(a, cid, cdist, n, lane);
-      if (KIND == EVAL_BITS) ev_bits.eval(a, cid, cdist, n, lane);
-      if (KIND == EVAL_ADC) ev_adc.eval(a, cid, cdist, n, lane);
-      if (KIND == EVAL_ADC_SMEM) ev_adcs.eval(a, cid, cdist, n, lane);
+      if (KIND == EVAL_BITS) ev_bits.eval(a, cid, cdist, n, lane, hook);
+      if (KIND == EVAL_ADC) ev_adc.eval(a, cid, cdist, n, lane, hook);
+      if (KIND == EVAL_ADC_SMEM) ev_adcs.eval(a, cid, cdist, n, lane, hook);
     };
+    auto evaluate = [&](int n) { evaluate_h(n, no_hook); };
 
     list.len = 0;
     list.cap = int(a.L);
@@ -1061,14 +1136,23 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
       return t0 + __popc(b1);
     };
 
+    // this query's filter: ascending ids fl[0..fn), the first min(fn, L) of them are the seeds
+    const uint32_t* fl = nullptr;
+    uint32_t fn = 0;
+    if (FILTER) {
+      const uint32_t f = a.query_filter ? uint32_t(__ldg(a.query_filter + qi)) : 0u;
+      const uint32_t fb = __ldg(a.filter_off + f);
+      fl = a.filter_ids + fb;
+      fn = __ldg(a.filter_off + f + 1) - fb;
+    }
     if (FILTER) {
       // searchSet.Add(filterPoints...) (plain append, search.go:49) and
       // resultSet.AddWithLimit(filterPoints...) (search.go:50)
-      const int nf = int(min(a.n_filter_seed, a.L));
+      const int nf = int(min(fn, a.L));
       for (int b0 = 0; b0 < nf; b0 += CAND_SLOTS) {
         const int n = min(CAND_SLOTS, nf - b0);
-        uint32_t i0 = lane < n ? __ldg(a.filter_seed + b0 + lane) : 0;
-        uint32_t i1 = lane + 32 < n ? __ldg(a.filter_seed + b0 + lane + 32) : 0;
+        uint32_t i0 = lane < n ? __ldg(fl + b0 + lane) : 0;
+        uint32_t i1 = lane + 32 < n ? __ldg(fl + b0 + lane + 32) : 0;
         const int nn = visit_and_stage(i0, lane < n, i1, lane + 32 < n);
         nvisited += nn;
         ndist += nn;
@@ -1100,7 +1184,7 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
     uint32_t pf_id = INVALID_ID, pf_n0 = INVALID_ID, pf_n1 = INVALID_ID;
     for (;;) {
       const int lim = min(list.len, int(a.L));
-      int pos = -1, pos2 = -1;
+      int pos = -1, pos2 = -1, pos3 = -1;
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         int p = lane + 32 * j;
@@ -1110,12 +1194,17 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
           pos = 32 * j + __ffs(b) - 1;
           b &= b - 1;
         }
-        if (b && pos >= 0 && pos2 < 0) pos2 = 32 * j + __ffs(b) - 1;
+        if (b && pos >= 0 && pos2 < 0) {
+          pos2 = 32 * j + __ffs(b) - 1;
+          b &= b - 1;
+        }
+        if (PFROWS && b && pos2 >= 0 && pos3 < 0) pos3 = 32 * j + __ffs(b) - 1;
       }
       if (pos < 0) break;
       const uint32_t e = list.id[pos];
       const float edist = list.dist[pos];
       const uint32_t e2 = pos2 >= 0 ? list.id[pos2] : INVALID_ID;
+      const uint32_t e3 = (PFROWS && pos3 >= 0) ? list.id[pos3] : INVALID_ID;
       __syncwarp();
       if (lane == 0) list.id[pos] = e | EXPANDED_FLAG;
       if (a.vis_ids != nullptr && lane == 0) {
@@ -1141,6 +1230,30 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
         pf_n0 = lane < int(a.R) ? __ldg(prow + lane) : INVALID_ID;
         pf_n1 = lane + 32 < int(a.R) ? __ldg(prow + lane + 32) : INVALID_ID;
       }
+      // Small rows (bit rows, PQ codes) leave this kernel latency-bound on one warp's dependent
+      // chain adjacency row -> visited test -> row gather, not HBM-bound (profiles/r01_k2_*,
+      // r02_k3_*). Speculation two levels deep takes DRAM latency off that chain:
+      //  * the third unexpanded candidate's adjacency row is pulled into L2 now, so that when it is
+      //    the runner-up next hop its register prefetch above is an L2 hit;
+      //  * once this hop's own rows are in flight (the evaluators call the hook), the rows of the
+      //    runner-up's not-yet-visited neighbours are pulled into L2: if the runner-up is expanded
+      //    next — the common case once the list has settled — its gather hits L2.
+      // Wrong guesses cost bandwidth this kernel has to spare (< 20 % of HBM in use), never results.
+      if (PFROWS && e3 != INVALID_ID && lane < int((a.R * 4 + 127) / 128)) prefetch_l2(a.adj + size_t(e3) * a.R + lane * 32);
+      auto pf_rows = [&]() {
+        if (!PFROWS || pf_id == INVALID_ID) return;
+        const uint32_t ids2[2] = {pf_n0, pf_n1};
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint32_t id = ids2[j];
+          if (id == INVALID_ID || !vt.maybe_new(id)) continue;
+          const unsigned char* row = (KIND == EVAL_BITS) ? reinterpret_cast<const unsigned char*>(a.bits + size_t(id) * a.bits_pitch)
+                                                         : a.codes + size_t(id) * a.codes_pitch;
+          const uint32_t bytes = (KIND == EVAL_BITS) ? a.bits_pitch * 8 : a.codes_pitch;
+          const uint32_t first = uint32_t(reinterpret_cast<uintptr_t>(row) & 127u);
+          for (uint32_t o = 0; o < first + bytes; o += 128) prefetch_l2(row - first + o);
+        }
+      };
       // searchSet.AddWithLimit(neighbours...) (search.go:90), 64 adjacency slots at a time: the
       // row itself, then — for the start node only — its edges beyond R (orphans re-attached
       // after deletes, prune.go:137-151; normally none). One copy of the hop body.
@@ -1150,7 +1263,8 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
         ndist += nnew;
         if (nvisited > vt.limit() || vt.failed) { overflow = true; break; }
         if (nnew > 0) {
-          evaluate(nnew);
+          if (x0 == 0) evaluate_h(nnew, pf_rows);
+          else evaluate(nnew);
           constexpr bool TIEFIX = (KIND == EVAL_BITS || KIND == EVAL_ADC || KIND == EVAL_ADC_SMEM);  // integer-valued / coarse distances
           if (MERGE_MIN == 0 || !list.template merge<TIEFIX>(cid, cdist, nnew, lane, lt, MERGE_MIN)) add_with_limit(list, nnew);
         }
@@ -1164,16 +1278,32 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
         // resultSet.AddWithLimit(distElem.Point) if the expanded node passes the filter
         // (search.go:93-95). resultSet dedupes with its own visited set, which holds the
         // seeds (search.go:50) and every node added here; a node is expanded at most once.
-        bool in_filter = (__ldg(a.filter_bits + (e >> 5)) >> (e & 31)) & 1u;
-        if (in_filter) {
-          bool seeded = false;
-          const uint32_t ns = min(a.n_filter_seed, a.L);
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            uint32_t sidx = lane + 32 * j;
-            seeded |= (sidx < ns) && (__ldg(a.filter_seed + sidx) == e);
+        // filter.Contains(node.Id): the shared filter's dense bitmask when there is one, else a
+        // 32-way search of the query's ascending id list (4 rounds for a million ids)
+        bool in_filter;
+        if (a.filter_bits != nullptr) {
+          in_filter = (__ldg(a.filter_bits + (e >> 5)) >> (e & 31)) & 1u;
+        } else {
+          uint32_t lo = 0, hi = fn;  // invariant: if e is in the list its index is in [lo, hi)
+          while (hi - lo > 32) {
+            const uint32_t stride = (hi - lo + 31) / 32;
+            const uint32_t at = lo + uint32_t(lane) * stride;
+            const bool le = at < hi && __ldg(fl + at) <= e;
+            const uint32_t b = __ballot_sync(SDB_FULL, le);
+            if (b == 0) { hi = lo; break; }  // e is below the first pivot
+            const uint32_t c = 31 - __clz(b);  // pivots ascend: the set lanes form a prefix
+            lo = lo + c * stride;
+            hi = min(lo + stride, hi);
           }
-          if (!__any_sync(SDB_FULL, seeded)) {
+          const bool eq = lo + lane < hi && __ldg(fl + lo + lane) == e;
+          in_filter = __any_sync(SDB_FULL, eq);
+        }
+        if (in_filter) {
+          // the seeds are already in resultSet (search.go:50): ascending list => e is a seed
+          // iff it is not above the last seed
+          const uint32_t ns = min(fn, a.L);
+          const bool seeded = ns > 0 && e <= __ldg(fl + ns - 1);
+          if (!seeded) {
             if (lane == 0) { cid[0] = e; cdist[0] = edist; }
             __syncwarp();
             add_with_limit(res, 1);

@@ -6,6 +6,7 @@
 
 #include "index.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -13,9 +14,9 @@ namespace sdb {
 namespace launch {
 
 template <int KIND, int METRIC, int TRIPS, int SETS, bool LEGACY, int MERGE_MIN, class VT, bool FILTER, bool RETRY, int MINB,
-          bool XTRA>
+          bool XTRA, bool PF = false>
 int launch_variant_x(sdb_index* ix, const SearchArgs& a, cudaStream_t stream) {
-  auto kern = beam_search_kernel<KIND, METRIC, TRIPS, SETS, LEGACY, MERGE_MIN, VT, FILTER, RETRY, MINB, XTRA>;
+  auto kern = beam_search_kernel<KIND, METRIC, TRIPS, SETS, LEGACY, MERGE_MIN, VT, FILTER, RETRY, MINB, XTRA, PF>;
   // FloatEvalGrouped keeps short queries (<= 4 float4 per lane) in registers: no shared copy
   constexpr bool QREG = (KIND == EVAL_FLOAT_FIXED) && !LEGACY && TRIPS <= 4;
   const uint32_t qfloats = (KIND == EVAL_ADC || KIND == EVAL_ADC_SMEM || QREG) ? 0 : (a.dim + 3) / 4 * 4;
@@ -47,13 +48,13 @@ int launch_variant_x(sdb_index* ix, const SearchArgs& a, cudaStream_t stream) {
     cached_dev = ix->device;
   }
   uint32_t resident = uint32_t(ix->sm_count) * ctas_per_sm;
-  uint32_t need = RETRY ? uint32_t(ix->sm_count) : a.B;
+  uint32_t need = RETRY ? std::min<uint32_t>(uint32_t(ix->sm_count), ix->retry_slots) : a.n_work;
   uint32_t grid = need < resident ? need : resident;
   if (grid == 0) grid = 1;
-  if (!RETRY && (a.flags & 2u) && a.B > grid) {
+  if (!RETRY && (a.flags & 2u) && a.n_work > grid) {
     // equal number of queries per resident warp: no half-empty last wave
-    const uint32_t waves = (a.B + grid - 1) / grid;
-    grid = (a.B + waves - 1) / waves;
+    const uint32_t waves = (a.n_work + grid - 1) / grid;
+    grid = (a.n_work + waves - 1) / waves;
   }
   kern<<<grid, 32, smem, stream>>>(a, qfloats, qwords);
   ix->launches++;
@@ -67,18 +68,32 @@ template <int KIND, int METRIC, int TRIPS, int SETS, bool LEGACY, int MERGE_MIN,
 int launch_variant(sdb_index* ix, const SearchArgs& a, cudaStream_t stream) {
   if (a.n_start_extra != 0)
     return launch_variant_x<KIND, METRIC, TRIPS, SETS, LEGACY, MERGE_MIN, VT, FILTER, RETRY, MINB, true>(ix, a, stream);
+  // speculative row prefetch (small-row evaluators, unfiltered first pass); SDB_NO_PF=1 = A/B switch
+  constexpr bool CAN_PF = !FILTER && !RETRY && (KIND == EVAL_BITS || KIND == EVAL_ADC_SMEM || KIND == EVAL_ADC);
+  if (CAN_PF) {
+    static const bool no_pf = getenv("SDB_NO_PF") != nullptr;
+    if (!no_pf)
+      return launch_variant_x<KIND, METRIC, TRIPS, SETS, LEGACY, MERGE_MIN, VT, FILTER, RETRY, MINB, false, CAN_PF>(ix, a, stream);
+  }
   return launch_variant_x<KIND, METRIC, TRIPS, SETS, LEGACY, MERGE_MIN, VT, FILTER, RETRY, MINB, false>(ix, a, stream);
 }
 
 template <int KIND, int METRIC, int TRIPS, int SETS, bool LEGACY, int MERGE_MIN, bool FILTER, int MINB, class VT = VisitedCompactN>
 int launch_with_retry(sdb_index* ix, SearchArgs a, cudaStream_t stream) {
+  const bool prof = ix->prof_on && ix->prof_n < sdb_index::PROF_RING;
+  if (prof) SDB_CUDA(cudaEventRecord(ix->prof_ev[2 * ix->prof_n], stream));
   int rc = launch_variant<KIND, METRIC, TRIPS, SETS, LEGACY, MERGE_MIN, VT, FILTER, false, MINB>(ix, a, stream);
   if (rc) return rc;
-  // second pass over queries whose visited set overflowed (normally none): u32 table, 32768 slots
+  if (prof) {
+    SDB_CUDA(cudaEventRecord(ix->prof_ev[2 * ix->prof_n + 1], stream));
+    ix->prof_n++;
+  }
+  // second pass over queries whose visited set overflowed (normally none): exact visited bitmap
+  // over all rows in global memory (VisitedBitmap) — cannot overflow, so every query completes
   a.work_counter = a.work_counter + 2;
   // same evaluator as the first pass (a re-run query walks ~80 hops alone on its SM: the
-  // pipelined row gather is what keeps that under a millisecond); the ADC table goes back to
-  // global memory because the u32 visited table takes the shared memory
+  // pipelined row gather is what keeps that under a millisecond); the ADC table is read from
+  // global memory
   constexpr int RK = (KIND == EVAL_ADC_SMEM) ? EVAL_ADC : KIND;
   constexpr int RT = (KIND == EVAL_BITS || KIND == EVAL_FLOAT_FIXED) ? TRIPS : 1;  // rows must still be covered
   constexpr int RS = (KIND == EVAL_BITS || KIND == EVAL_FLOAT_FIXED) ? SETS : 1;
@@ -88,7 +103,7 @@ int launch_with_retry(sdb_index* ix, SearchArgs a, cudaStream_t stream) {
     cudaMemcpy(h, a.work_counter - 2, sizeof(h), cudaMemcpyDeviceToHost);
     fprintf(stderr, "[sdb] beam search: %u of %u queries overflowed the compact visited table -> retry launch\n", h[1], a.B);
   }
-  return launch_variant<RK, METRIC, RT, RS, false, 0, VisitedTable<15>, FILTER, true, 1>(ix, a, stream);
+  return launch_variant<RK, METRIC, RT, RS, false, 0, VisitedBitmap, FILTER, true, 1>(ix, a, stream);
 }
 
 // Tuning knob for A/B runs on the GPU (not part of the ABI): SDB_K1_VARIANT picks the

@@ -3,7 +3,8 @@
 // shard/cache/manager.go:151-182) into the batches the GPU kernels need.
 // Callers block in Search(); a single batcher thread collects requests until `max_batch` are
 // waiting or the oldest has waited `window`, runs one sdb_search_batch for all requests that
-// share (limit, searchSize), and hands every caller its own slice of the result.
+// share (limit, searchSize) — each with its own optional filter bitmap, like
+// shard/index/search.go:59-85 — and hands every caller its own slice of the result.
 #pragma once
 #include <chrono>
 #include <condition_variable>
@@ -31,13 +32,19 @@ class SearchCoalescer {
     worker_.join();
   }
 
-  // Same contract as IndexVamana::Search without a filter; thread-safe, blocking.
+  // Same contract as IndexVamana::Search (filter: nullptr = none, empty = matches nothing);
+  // thread-safe, blocking.
   Error Search(const models::SearchVectorVamanaOptions& query, std::vector<uint64_t>* result_set,
                std::vector<models::SearchResult>* results) {
+    return Search(query, nullptr, result_set, results);
+  }
+  Error Search(const models::SearchVectorVamanaOptions& query, const std::vector<uint64_t>* filter,
+               std::vector<uint64_t>* result_set, std::vector<models::SearchResult>* results) {
     if (query.Vector.size() != ix_->Parameters().VectorSize)
       return Error("could not perform graph search: query vector length mismatch");
     Request r;
     r.q = &query;
+    r.filter = filter;
     {
       std::unique_lock<std::mutex> g(mu_);
       queue_.push_back(&r);
@@ -66,6 +73,7 @@ class SearchCoalescer {
  private:
   struct Request {
     const models::SearchVectorVamanaOptions* q = nullptr;
+    const std::vector<uint64_t>* filter = nullptr;
     std::vector<uint64_t> ids;
     std::vector<float> dists;
     uint32_t count = 0;
@@ -109,14 +117,34 @@ class SearchCoalescer {
       ids.assign(size_t(B) * kk, 0);
       dists.assign(size_t(B) * kk, 0.0f);
       counts.assign(B, 0);
-      Error err = ix_->SearchBatch(qbuf.data(), B, uint32_t(k), uint32_t(L), ids.data(), dists.data(), counts.data());
+      std::vector<const std::vector<uint64_t>*> filters(B, nullptr);
+      bool any_filter = false;
+      for (uint32_t b = 0; b < B; ++b) {
+        filters[b] = batch[b]->filter;
+        any_filter |= batch[b]->filter != nullptr;
+      }
+      std::vector<Error> errs(B);
+      Error err = any_filter ? ix_->SearchBatchFilters(qbuf.data(), B, uint32_t(k), uint32_t(L), filters, ids.data(),
+                                                       dists.data(), counts.data())
+                             : ix_->SearchBatch(qbuf.data(), B, uint32_t(k), uint32_t(L), ids.data(), dists.data(), counts.data());
+      if (err && any_filter && B > 1) {
+        // a request whose filter names a missing point fails alone in the reference (search.go:45-48):
+        // re-run the batch request by request so only the offender gets the error
+        for (uint32_t b = 0; b < B; ++b) {
+          std::vector<const std::vector<uint64_t>*> one(1, filters[b]);
+          errs[b] = ix_->SearchBatchFilters(qbuf.data() + size_t(b) * dim, 1, uint32_t(k), uint32_t(L), one,
+                                            ids.data() + size_t(b) * kk, dists.data() + size_t(b) * kk, counts.data() + b);
+        }
+      } else {
+        for (uint32_t b = 0; b < B; ++b) errs[b] = err;
+      }
       g.lock();
       ++batches_;
       queries_ += B;
       for (uint32_t b = 0; b < B; ++b) {
         Request* r = batch[b];
-        r->err = err;
-        if (!err) {
+        r->err = errs[b];
+        if (!errs[b]) {
           r->count = counts[b];
           r->ids.assign(ids.begin() + size_t(b) * kk, ids.begin() + size_t(b) * kk + counts[b]);
           r->dists.assign(dists.begin() + size_t(b) * kk, dists.begin() + size_t(b) * kk + counts[b]);

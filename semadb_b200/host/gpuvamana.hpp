@@ -139,14 +139,22 @@ class IndexVamana {
     std::vector<uint64_t> ids(query.Limit > 0 ? query.Limit : 1);
     std::vector<float> d(ids.size());
     uint32_t cnt = 0;
+    // A non-nil filter — empty included: it then seeds nothing and nothing can be returned
+    // (search.go:33-51,93-95) — goes through the per-request entry point, which does not read
+    // "filtered" off the data pointer (an empty std::vector's data() may be null).
     std::vector<uint64_t> f;
+    int rc;
     if (filter) {
       f = *filter;
       std::sort(f.begin(), f.end());
       f.erase(std::unique(f.begin(), f.end()), f.end());
+      const uint64_t off[2] = {0, f.size()};
+      rc = sdb_search_batch_filters(h_, 1, query.Vector.data(), uint32_t(query.Limit), uint32_t(query.SearchSize), 1,
+                                    f.data(), off, nullptr, ids.data(), d.data(), &cnt);
+    } else {
+      rc = sdb_search_batch(h_, 1, query.Vector.data(), uint32_t(query.Limit), uint32_t(query.SearchSize), nullptr, 0,
+                            ids.data(), d.data(), &cnt);
     }
-    int rc = sdb_search_batch(h_, 1, query.Vector.data(), uint32_t(query.Limit), uint32_t(query.SearchSize),
-                              filter ? f.data() : nullptr, filter ? f.size() : 0, ids.data(), d.data(), &cnt);
     if (Error e = CErr(rc, "could not perform graph search")) return e;
     const float weight = query.Weight ? *query.Weight : 1.0f;
     results->clear();
@@ -167,6 +175,31 @@ class IndexVamana {
   Error SearchBatch(const float* queries, uint32_t B, uint32_t k, uint32_t search_size, uint64_t* out_ids,
                     float* out_dists, uint32_t* out_counts) {
     return CErr(sdb_search_batch(h_, B, queries, k, search_size, nullptr, 0, out_ids, out_dists, out_counts),
+                "could not perform graph search");
+  }
+
+  // B requests, each with its own optional filter (nullptr = none; an empty vector is a filter
+  // that matches nothing), one kernel launch per kind: what shard/index/search.go:59-85 does
+  // request by request.
+  Error SearchBatchFilters(const float* queries, uint32_t B, uint32_t k, uint32_t search_size,
+                           const std::vector<const std::vector<uint64_t>*>& filters, uint64_t* out_ids, float* out_dists,
+                           uint32_t* out_counts) {
+    if (filters.size() != B) return Error("could not perform graph search: one filter slot per request expected");
+    std::vector<uint64_t> flat, off(1, 0);
+    std::vector<int32_t> qf(B, -1);
+    std::vector<uint64_t> f;
+    for (uint32_t b = 0; b < B; ++b) {
+      if (!filters[b]) continue;
+      f = *filters[b];
+      std::sort(f.begin(), f.end());
+      f.erase(std::unique(f.begin(), f.end()), f.end());
+      qf[b] = int32_t(off.size() - 1);
+      flat.insert(flat.end(), f.begin(), f.end());
+      off.push_back(flat.size());
+    }
+    const uint32_t nf = uint32_t(off.size() - 1);
+    return CErr(sdb_search_batch_filters(h_, B, queries, k, search_size, nf, flat.data(), off.data(), qf.data(), out_ids,
+                                         out_dists, out_counts),
                 "could not perform graph search");
   }
 

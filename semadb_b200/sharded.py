@@ -193,6 +193,8 @@ class ShardedSearcher:
         h_dists.copy_(m_d, non_blocking=True)
         h_counts.copy_(m_c, non_blocking=True)
         torch.cuda.synchronize(device)
+        # the step is complete on this GPU: a barrier that gave up on a peer makes it an error
+        _capi.check(lib.sdb_peer_barrier_check(di, 0))
 
     def search_batch_device(self, d_queries, k: int, search_size: int, max_search_limit: int = 75):
         """d_queries: [B, dim] f32 CUDA tensor, identical on every rank (broadcast by the

@@ -80,3 +80,69 @@ def start_vector(dim: int, seed: int) -> np.ndarray:
         s = np.float32(s + np.float32(x * x))
     norm = np.float32(1) / np.float32(np.sqrt(np.float64(s)))
     return (v * norm).astype(np.float32)
+
+
+# ---- device-side generators (bench.py at shard sizes: 6.25M x 1024 floats do not fit a host
+# generator's time budget). Same distributions as above drawn with torch.Generator on the CUDA
+# device: deterministic for a given (seed, GPU model, torch build), NOT bit-equal to the numpy ones.
+# Tests use the numpy generators; the bench states "synthetic (device-generated)".
+
+def _torch_w(latent: int, dim: int, seed: int, device):
+    import torch
+    return torch.from_numpy(_latent_w(latent, dim, seed)).to(device)
+
+
+def latent_gaussian_torch(n: int, dim: int, seed: int, device, w_seed: int | None = None, latent: int = 16,
+                          normalize: bool = False, centres: int = 0, spread: float = 0.3, centre_seed: int = 1234,
+                          chunk: int = 1 << 18):
+    """Yields (start, X) chunks on `device`: x = zW + 0.1e with z ~ N(0, I_latent) — or, with
+    centres > 0, z = c_j + spread * N(0, I) for a random one of `centres` fixed centres
+    c_j ~ N(0, I) (clustered embedding data, C4) — optionally L2-normalised."""
+    import torch
+    w = _torch_w(latent, dim, seed if w_seed is None else w_seed, device)
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed) * 7919 + 17)
+    cent = None
+    if centres:
+        gc = torch.Generator(device=device)
+        gc.manual_seed(int(centre_seed))
+        cent = torch.randn((centres, latent), generator=gc, device=device, dtype=torch.float32)
+    for s in range(0, n, chunk):
+        m = min(chunk, n - s)
+        z = torch.randn((m, latent), generator=g, device=device, dtype=torch.float32)
+        if cent is not None:
+            pick = torch.randint(0, centres, (m,), generator=g, device=device)
+            z = cent[pick] + spread * z
+        x = z @ w
+        x.add_(torch.randn((m, dim), generator=g, device=device, dtype=torch.float32), alpha=0.1)
+        if normalize:
+            x /= x.norm(dim=1, keepdim=True).clamp_min(1e-30)
+        yield s, x
+
+
+def sign_bits_torch(n: int, dim: int, seed: int, device, w_seed: int | None = None, latent: int = 16,
+                    chunk: int = 1 << 18):
+    """C5b (amended): what binary quantisation of embedding vectors produces —
+    bit i = (x_i > 0) of a latent-Gaussian embedding, supplied as 0.0/1.0 floats so the forced
+    0.5 threshold of hamming/jaccard indexes (shard/vectorstore/vectorstore.go:56-66) recovers it."""
+    for s, x in latent_gaussian_torch(n, dim, seed, device, w_seed=w_seed, latent=latent, chunk=chunk):
+        yield s, (x > 0).to(x.dtype)
+
+
+def sign_bits(n: int, dim: int, seed: int, w_seed: int | None = None, latent: int = 16) -> np.ndarray:
+    """numpy twin of sign_bits_torch (tests, small sizes)."""
+    return (latent_gaussian(n, dim, seed, w_seed=w_seed, latent=latent) > 0).astype(np.float32)
+
+
+def clustered_latent(n: int, dim: int, seed: int, w_seed: int | None = None, latent: int = 16, centres: int = 2048,
+                     spread: float = 0.3, centre_seed: int = 1234, normalize: bool = True) -> np.ndarray:
+    """numpy twin of latent_gaussian_torch(centres=...) (tests, small sizes)."""
+    w = _latent_w(latent, dim, seed if w_seed is None else w_seed)
+    cent = np.random.Generator(np.random.PCG64(centre_seed)).standard_normal((centres, latent), dtype=np.float32)
+    rng = np.random.Generator(np.random.PCG64(seed + 7919))
+    pick = rng.integers(0, centres, size=n)
+    z = cent[pick] + np.float32(spread) * rng.standard_normal((n, latent), dtype=np.float32)
+    x = z @ w + np.float32(0.1) * rng.standard_normal((n, dim), dtype=np.float32)
+    if normalize:
+        x /= np.maximum(np.linalg.norm(x, axis=1, keepdims=True), 1e-30)
+    return x.astype(np.float32)

@@ -299,6 +299,29 @@ class _DeviceIndex:
                                          _ptr(cnt, u32p)))
         return ids, d, cnt
 
+    def search_batch_filters(self, queries, filters, query_filter=None, k: int = 10, search_size: Optional[int] = None):
+        """One filter per request (shard/index/search.go:59-85): `filters` is a list of id
+        collections (an empty one filters everything out), query_filter[b] the filter index of
+        request b or -1 for none (None: every request uses filters[0])."""
+        q = _f32(queries)
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise SdbError(_capi.ERR_INVALID, "queries must be [B, dim]")
+        B = q.shape[0]
+        L = self.L if search_size is None else int(search_size)
+        lists = [np.unique(_u64(f)) for f in filters]
+        off = np.zeros(len(lists) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(x) for x in lists])
+        flat = np.concatenate(lists) if lists and off[-1] else np.zeros(0, dtype=np.uint64)
+        qf = None if query_filter is None else np.ascontiguousarray(query_filter, dtype=np.int32)
+        ids = np.zeros((B, k), dtype=np.uint64)
+        d = np.zeros((B, k), dtype=np.float32)
+        cnt = np.zeros(B, dtype=np.uint32)
+        check(self._lib.sdb_search_batch_filters(self._h, B, _ptr(q, f32p), k, L, len(lists),
+                                                 _ptr(flat, u64p) if len(flat) else None, _ptr(off, u64p),
+                                                 None if qf is None else _ptr(qf, _capi.i32p), _ptr(ids, u64p),
+                                                 _ptr(d, f32p), _ptr(cnt, u32p)))
+        return ids, d, cnt
+
     def search_batch_device(self, d_queries, k: int, search_size: int, d_out_ids, d_out_dists, d_out_counts,
                             stream: int = 0):
         """torch CUDA tensors (contiguous): queries f32 [B,dim], out ids int64/uint64 [B,k],
@@ -313,6 +336,18 @@ class _DeviceIndex:
         nd = np.zeros(B, dtype=np.uint32)
         check(self._lib.sdb_last_search_stats(self._h, B, _ptr(hops, u32p), _ptr(nd, u32p)))
         return hops, nd
+
+    def search_profile(self, enable: bool):
+        """CUDA events around the first-pass beam-search kernel of every following search."""
+        check(self._lib.sdb_search_profile(self._h, 1 if enable else 0))
+
+    def search_profile_read(self) -> np.ndarray:
+        """Kernel durations (ms) of the searches recorded since search_profile(True)."""
+        import ctypes as C
+        out = np.zeros(256, dtype=np.float32)
+        n = C.c_uint32(0)
+        check(self._lib.sdb_search_profile_read(self._h, len(out), _ptr(out, f32p), C.byref(n)))
+        return out[:min(n.value, len(out))].copy()
 
     def search_visited(self, queries, search_size: Optional[int] = None, vis_cap: int = 256):
         q = _f32(queries)
@@ -352,6 +387,19 @@ class _DeviceIndex:
         if v.shape != (len(ids), self.dim):
             raise SdbError(_capi.ERR_INVALID, "vectors must be [n, dim]")
         check(self._lib.sdb_insert_batch(self._h, len(ids), _ptr(ids, u64p), _ptr(v, f32p)))
+
+    def insert_batch_device(self, ids, d_vectors):
+        """d_vectors: contiguous f32 CUDA tensor [n, dim] on this index's device."""
+        ids = _u64(ids)
+        assert d_vectors.is_cuda and d_vectors.is_contiguous() and tuple(d_vectors.shape) == (len(ids), self.dim)
+        check(self._lib.sdb_insert_batch_device(self._h, len(ids), _ptr(ids, u64p), d_vectors.data_ptr()))
+
+    def insert_stats(self, reset: bool = False) -> dict:
+        """Totals of the batched insert (sdb_insert_stats)."""
+        out = np.zeros(8, dtype=np.uint64)
+        check(self._lib.sdb_insert_stats(self._h, _ptr(out, u64p), 1 if reset else 0))
+        keys = ("points", "hops", "ndist", "edges", "targets", "prunes", "prune_candidates")
+        return {k: int(v) for k, v in zip(keys, out)}
 
     def insert_update_delete_batch(self, ids, vectors, has_vector=None):
         """sdb_insert_update_delete: the whole classify / insert / removeInboundEdges / drop /

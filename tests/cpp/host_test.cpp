@@ -211,6 +211,13 @@ static void test_insert_search_flush() {
     std::vector<models::SearchResult> res;
     REQUIRE_OK(inv->Search(o, &filter, &rs, &res));
     CHECK(rs.size() == 3 && res.size() == 3 && res[0].NodeId == rps[0].Id);
+    // a non-nil EMPTY bitmap is still a filter: nothing is seeded, nothing passes (search.go:33-51,93-95)
+    std::vector<uint64_t> empty_filter;
+    REQUIRE_OK(inv->Search(o, &empty_filter, &rs, &res));
+    CHECK(rs.empty() && res.empty());
+    // a filter naming a point that does not exist fails like GetMany (search.go:45-48)
+    std::vector<uint64_t> missing{rps[0].Id, 999999};
+    CHECK(bool(inv->Search(o, &missing, &rs, &res)));
     o.SearchSize = 5;  // search.go:23-25
     o.Limit = 10;
     CHECK(bool(inv->Search(o, nullptr, &rs, &res)));
@@ -334,6 +341,49 @@ static void test_coalescer() {
   CHECK(bad.load() == 0);
   CHECK(co.queries() == B);
   CHECK(co.batches() < B / 4);  // requests really were coalesced
+  // per-request filters through the coalescer (shard/index/search.go:59-85): every third request
+  // carries its own bitmap, every 30th an empty one, one names a missing point; each result must
+  // equal the same request served alone
+  {
+    const uint32_t B2 = 600;
+    std::vector<std::vector<uint64_t>> filt(B2);
+    for (uint32_t b = 0; b < B2; ++b) {
+      if (b % 3) continue;
+      if (b % 30 == 0) continue;  // stays empty (but is passed as a filter)
+      for (uint64_t j = 0; j < 40 + b % 50; ++j) filt[b].push_back(pts[(b * 7 + j * 13) % pts.size()].Id);
+    }
+    filt[33].push_back(1u << 30);  // missing point: this request alone must fail
+    std::vector<std::vector<models::SearchResult>> want(B2);
+    std::vector<int> want_err(B2, 0);
+    for (uint32_t b = 0; b < B2; ++b) {
+      models::SearchVectorVamanaOptions o;
+      o.Vector = pts[b].Vector;
+      o.Limit = K;
+      std::vector<uint64_t> rs;
+      want_err[b] = bool(inv->Search(o, b % 3 == 0 ? &filt[b] : nullptr, &rs, &want[b]));
+    }
+    CHECK(want_err[33] == 1 && want_err[30] == 0 && want[30].empty() && want[0].empty() && !want[3].empty());
+    std::atomic<int> bad2{0};
+    std::vector<std::thread> th2;
+    for (int t = 0; t < 32; ++t)
+      th2.emplace_back([&, t] {
+        for (uint32_t b = t; b < B2; b += 32) {
+          models::SearchVectorVamanaOptions o;
+          o.Vector = pts[b].Vector;
+          o.Limit = K;
+          std::vector<uint64_t> rs;
+          std::vector<models::SearchResult> res;
+          Error e = co.Search(o, b % 3 == 0 ? &filt[b] : nullptr, &rs, &res);
+          if (bool(e) != bool(want_err[b])) { ++bad2; continue; }
+          if (e) continue;
+          if (res.size() != want[b].size()) { ++bad2; continue; }
+          for (size_t j = 0; j < res.size(); ++j)
+            if (res[j].NodeId != want[b][j].NodeId || res[j].Distance != want[b][j].Distance) ++bad2;
+        }
+      });
+    for (auto& x : th2) x.join();
+    CHECK(bad2.load() == 0);
+  }
   std::fprintf(stderr, "coalescer: %llu queries in %llu batches\n", (unsigned long long)co.queries(),
                (unsigned long long)co.batches());
 }

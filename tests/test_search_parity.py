@@ -170,3 +170,61 @@ def test_search_batch_pinned_buffers_zero_copy():
     assert (h_ids.numpy().astype(np.uint64) == pi).all() and h_d.numpy().tobytes() == pd.tobytes()
     assert (h_c.numpy().astype(np.uint32) == pc).all()
     assert (pi == ref["ids"].astype(np.uint64)).all() and pd.tobytes() == ref["dists"].tobytes()
+
+
+def test_search_per_request_filters_and_empty_filter():
+    """One filter per request in one batch (shard/index/search.go:59-85 -> vamana/search.go:33-51,
+    93-95): filtered, unfiltered and empty-filter requests mixed; every row must equal the oracle's
+    answer for that request alone. An empty (non-nil) filter returns nothing."""
+    from tests.helpers import mirror_to_gpu, oracle_graph
+    X = synth.uniform(4000, 16, 7)
+    oix, pid, start = oracle_graph(X, threads=1)
+    g = mirror_to_gpu(oix, X, pid, start)
+    rng = np.random.Generator(np.random.PCG64(5))
+    B = 96
+    Q = X[:B]
+    filters = [np.sort(rng.choice(pid, size=nf, replace=False)) for nf in (1, 40, 75, 76, 500, 2500)] + [np.zeros(0, np.uint64)]
+    qf = np.array([(b % (len(filters) + 1)) - 1 for b in range(B)], dtype=np.int32)  # -1 = unfiltered
+    ids, d, cnt = g.search_batch_filters(Q, filters, qf, 10, 75)
+    plain = oix.search(Q, k=10, threads=4)
+    for b in range(B):
+        f = qf[b]
+        if f < 0:
+            ref = {k_: v[b] for k_, v in plain.items()}
+        elif len(filters[f]) == 0:
+            assert cnt[b] == 0 and (ids[b] == 0).all()
+            continue
+        else:
+            r = oix.search(Q[b:b + 1], k=10, filter_ids=filters[f], threads=1)
+            ref = {k_: v[0] for k_, v in r.items()}
+        assert cnt[b] == ref["counts"], (b, f)
+        assert (ids[b] == ref["ids"].astype(np.uint64)).all(), (b, f)
+        assert d[b].tobytes() == ref["dists"].tobytes(), (b, f)
+    # the shared-filter entry point treats a non-NULL empty list the same way
+    ids, d, cnt = g.search_batch(Q[:4], 10, 75, filter_ids=np.zeros(0, np.uint64))
+    assert (cnt == 0).all()
+    # everybody shares filter 0 (query_filter = None)
+    ids, d, cnt = g.search_batch_filters(Q[:8], [filters[3]], None, 10, 75)
+    ref = oix.search(Q[:8], k=10, filter_ids=filters[3], threads=2)
+    assert (ids == ref["ids"].astype(np.uint64)).all() and d.tobytes() == ref["dists"].tobytes()
+
+
+def test_search_retry_bitmap_is_exact(monkeypatch):
+    """A query that overflows the compact shared-memory visited table is re-run against an exact
+    global-memory bitmap (the reference's visited bitset never fills up, distset.go:41,140-155):
+    with a table far too small for any query, every query takes that path and must still equal
+    the oracle — ids, distances, hop and distance counts — and no overflow marker may escape."""
+    from tests.helpers import mirror_to_gpu, oracle_graph
+    X = synth.sift_shaped(20000, 128, 3)
+    oix, pid, start = oracle_graph(X)
+    g = mirror_to_gpu(oix, X, pid, start)
+    Q = synth.sift_shaped(300, 128, 4, w_seed=3)
+    monkeypatch.setenv("SDB_VT_SLOTS", "64")
+    ref = _check_search(oix, g, Q)
+    assert (ref["counts"] <= 10).all()
+    # insert path: the visited list of a re-run query reaches the prune kernel intact
+    vi, vd, vn = g.search_visited(Q[:50], 75, 256)
+    r2 = oix.search(Q[:50], k=1, vis_cap=256, threads=8)
+    assert (vn == r2["vis_len"]).all()
+    for b in range(50):
+        assert (vi[b, :vn[b]] == r2["vis_ids"][b, :vn[b]]).all()
