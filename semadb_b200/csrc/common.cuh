@@ -38,6 +38,13 @@ __device__ __forceinline__ float4 ldg_f4_stream(const float* p) {
                : "l"(p));
   return r;
 }
+// 256-bit read-only load (sm_100: LDG.E.256): one instruction — one L1 wavefront per touched line —
+// for a 32-byte record instead of two
+__device__ __forceinline__ void ldg_f8(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
 __device__ __forceinline__ uint4 ldg_u4_stream(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"

@@ -10,6 +10,9 @@ namespace launch {
 extern template int launch_float<METRIC_EUCLIDEAN>(sdb_index*, const SearchArgs&, bool, cudaStream_t);
 extern template int launch_float<METRIC_DOT>(sdb_index*, const SearchArgs&, bool, cudaStream_t);
 extern template int launch_float<METRIC_COSINE>(sdb_index*, const SearchArgs&, bool, cudaStream_t);
+// search_bits.cu / search_pq.cu: the bit-row and PQ-code evaluators
+int launch_bits(sdb_index* ix, const SearchArgs& a, bool filtered, cudaStream_t stream);
+int launch_pq(sdb_index* ix, const SearchArgs& a, bool filtered, cudaStream_t stream);
 }  // namespace launch
 using namespace launch;
 
@@ -91,9 +94,12 @@ int launch_search(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k,
   ix->retry_check_pending = true;
   ix->last_search_stream = stream;
   if (ix->p.quantizer == SDB_QUANT_PRODUCT && ix->pq_fitted) {
-    if ((rc = ix->d_adc.ensure(size_t(B) * ix->pqM * ix->pqK))) return rc;
-    if ((rc = launch_adc_tables(ix, B, d_queries, ix->d_adc.p, stream))) return rc;
-    a.adc = ix->d_adc.p;
+    a.pq_cent = ix->d_pq_centroids;
+    if (!adc_on_the_fly(ix)) {  // materialised per-query tables (product.go:255-263), K4
+      if ((rc = ix->d_adc.ensure(size_t(B) * ix->pqM * ix->pqK))) return rc;
+      if ((rc = launch_adc_tables(ix, B, d_queries, ix->d_adc.p, stream))) return rc;
+      a.adc = ix->d_adc.p;
+    }
   }
   if (filters == nullptr) return dispatch_search(ix, a, false, stream);
   // per-request filters: the unfiltered requests of the batch run through the fast kernels, the
@@ -118,39 +124,8 @@ int launch_search(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k,
 }
 
 static int dispatch_search(sdb_index* ix, const SearchArgs& a, bool filtered, cudaStream_t stream) {
-  if (ix->p.quantizer == SDB_QUANT_BINARY && ix->bq_fitted) {
-    // KIND = bits: METRIC = hamming / jaccard, TRIPS = 128-byte chunks per row, SETS = pipeline depth
-    const bool jac = ix->bq_metric == SDB_METRIC_JACCARD;
-    const uint32_t nch = (ix->bits_pitch + 15) / 16;
-    if (filtered) {
-      return jac ? launch_with_retry<EVAL_BITS, METRIC_JACCARD, 4, 2, false, 0, true, 1>(ix, a, stream)
-                 : launch_with_retry<EVAL_BITS, METRIC_HAMMING, 4, 2, false, 0, true, 1>(ix, a, stream);
-    }
-    if (jac) {
-      if (nch <= 1) return launch_with_retry<EVAL_BITS, METRIC_JACCARD, 1, 8, false, 2, false, 12>(ix, a, stream);
-      return launch_with_retry<EVAL_BITS, METRIC_JACCARD, 4, 2, false, 2, false, 12>(ix, a, stream);
-    }
-    if (nch <= 1) return launch_with_retry<EVAL_BITS, METRIC_HAMMING, 1, 8, false, 2, false, 12>(ix, a, stream);
-    if (nch <= 2) return launch_with_retry<EVAL_BITS, METRIC_HAMMING, 2, 4, false, 2, false, 12>(ix, a, stream);
-    return launch_with_retry<EVAL_BITS, METRIC_HAMMING, 4, 2, false, 2, false, 12>(ix, a, stream);
-  }
-  if (ix->p.quantizer == SDB_QUANT_PRODUCT && ix->pq_fitted) {
-    // ADC table in shared memory when at least two query-warps per SM can hold theirs (C4:
-    // 96 x 256 x 4 B = 96 KB => exactly two); otherwise the table is read through L1/L2
-    const size_t fixed = warp_smem_bytes<VisitedCompactN, false>(0, 0, 0, ix->pqM * ix->pqK) + 1024;
-    const size_t room = ix->smem_per_sm / 2 > fixed ? (ix->smem_per_sm / 2 - fixed) / 2 : 0;  // 16-bit visited slots
-    if (!filtered && room >= 4096 && !getenv("SDB_ADC_GLOBAL")) {
-      SearchArgs t = a;
-      if (t.vt_slots > room) t.vt_slots = uint32_t(room) / 8 * 8;
-      const uint32_t nch = (ix->pqM + 15) / 16;
-      if (nch <= 2) return launch_with_retry<EVAL_ADC_SMEM, 0, 2, 1, false, 2, false, 12>(ix, t, stream);
-      if (nch <= 4) return launch_with_retry<EVAL_ADC_SMEM, 0, 4, 1, false, 2, false, 12>(ix, t, stream);
-      if (nch <= 6) return launch_with_retry<EVAL_ADC_SMEM, 0, 6, 1, false, 2, false, 12>(ix, t, stream);
-      return launch_with_retry<EVAL_ADC_SMEM, 0, 8, 1, false, 2, false, 12>(ix, t, stream);
-    }
-    return filtered ? launch_with_retry<EVAL_ADC, 0, 1, 1, false, 0, true, 1>(ix, a, stream)
-                    : launch_with_retry<EVAL_ADC, 0, 1, 1, false, 2, false, 12>(ix, a, stream);
-  }
+  if (ix->p.quantizer == SDB_QUANT_BINARY && ix->bq_fitted) return launch_bits(ix, a, filtered, stream);
+  if (ix->p.quantizer == SDB_QUANT_PRODUCT && ix->pq_fitted) return launch_pq(ix, a, filtered, stream);
   switch (ix->store_metric) {
     case SDB_METRIC_EUCLIDEAN: return launch_float<METRIC_EUCLIDEAN>(ix, a, filtered, stream);
     case SDB_METRIC_DOT: return launch_float<METRIC_DOT>(ix, a, filtered, stream);

@@ -58,6 +58,7 @@ struct SearchArgs {
   uint32_t codes_pitch;    // bytes per row (multiple of 16)
   const float* adc;        // [B][M*K] per-query ADC tables (product store)
   uint32_t pqM, pqK;
+  const float* pq_cent;    // [M][K][sub] flatCentroids (EVAL_ADC_FLY: table entries computed on the fly)
   const float* bq_thr;     // [dim] binary threshold (query encode)
   int bit_metric;
   // graph
@@ -988,7 +989,140 @@ struct AdcEvalSmem {
   }
 };
 
-enum EvalKind : int { EVAL_FLOAT_FIXED = 0, EVAL_FLOAT_GENERIC = 1, EVAL_BITS = 2, EVAL_ADC = 3, EVAL_ADC_SMEM = 4 };
+// PQ codes without a materialised table. The reference fills dists[i*K+j] = distFn(x_i, centroid_ij)
+// for all M*K entries of a query and then sums M lookups per point (product.go:255-277). An entry
+// depends only on (query, i, j): computing it where it is needed — the same sequential FMA chain
+// over the sub-vector the table kernel runs (short_dist_thread), so the same float — removes the
+// per-query table (96 KB at C4) from shared memory, where it capped residency at two query-warps
+// per SM and left the search latency-bound at 3 % warp occupancy (profiles/r02_k3_*). The
+// codebook (M*K*sub floats, 786 KB at C4) is shared by every query and stays L2-resident; a
+// lookup becomes one 32-byte sector read + sub FMAs, and twelve query-warps per SM hide it.
+// One lane owns a candidate (two when the hop staged more than 32); the M terms are summed in
+// sub-vector order in f32 (product.go:271-275). SUB = sub-vector length (4, 8 or 16 floats).
+template <int METRIC, int SUB>
+struct AdcEvalFly {
+  static constexpr bool L2 = (METRIC == METRIC_EUCLIDEAN);
+  static constexpr int V4 = SUB / 4;
+  const float* qs;  // the query in shared memory
+  // one centroid (SUB floats, SUB*4-byte aligned): 256-bit loads where the record allows — the
+  // lookups are scattered, so the L1 pays one wavefront per lane per load instruction
+  __device__ __forceinline__ void load_entry(const float* p, float4 (&c)[V4]) const {
+    if (V4 == 1) {
+      c[0] = ldg_f4(p);
+    } else {
+#pragma unroll
+      for (int v = 0; v < V4; v += 2) ldg_f8(p + 4 * v, c[v], c[(v + 1) < V4 ? v + 1 : v]);
+    }
+  }
+  __device__ __forceinline__ float term(const float4 (&c)[V4], uint32_t i) const {
+    float t = 0.0f;
+#pragma unroll
+    for (int v = 0; v < V4; ++v) {
+      const float4 q = *reinterpret_cast<const float4*>(qs + i * SUB + 4 * v);
+      t = tail_accum<L2>(q.x, c[v].x, t);
+      t = tail_accum<L2>(q.y, c[v].y, t);
+      t = tail_accum<L2>(q.z, c[v].z, t);
+      t = tail_accum<L2>(q.w, c[v].w, t);
+    }
+    return metric_epilogue<METRIC>(t);
+  }
+  // LPC lanes share a candidate (hops that stage few candidates — the usual case on a PQ graph,
+  // 6-12 of 64 neighbours are new — would otherwise leave most lanes idle through the M-term
+  // loop): within each 16-byte chunk of the code row lane s of the group computes the terms of
+  // code words s*WPL .. s*WPL+WPL-1 (4 sub-vectors per word), then the 16 terms are added in
+  // sub-vector order through shuffles, so the sum is the same sequential f32 chain. TWO (LPC = 1
+  // only): a second chain for adjacency slot lane + 32.
+  template <int LPC, bool TWO, class Hook>
+  __device__ __forceinline__ void chains(const SearchArgs& a, const uint32_t* cid, float* cdist, int n, int lane, Hook&& hook) {
+    constexpr int WPL = 4 / LPC;  // code words per lane per chunk
+    const int s = lane % LPC, c = lane / LPC;
+    const bool h0 = c < n, h1 = TWO && lane + 32 < n;
+    const uint8_t* r0 = a.codes + size_t(h0 ? cid[c] : cid[0]) * a.codes_pitch + s * WPL * 4;
+    const uint8_t* r1 = a.codes + size_t(h1 ? cid[lane + 32] : cid[0]) * a.codes_pitch;
+    const uint32_t nch = (a.pqM + 15) >> 4;
+    const uint32_t K = a.pqK;
+    float d0 = 0.0f, d1 = 0.0f;
+    auto load_words = [&](const uint8_t* p, uint32_t (&w)[WPL]) {
+      if (WPL == 4) {
+        const uint4 v = ldg_u4_stream(p);
+        w[0] = v.x; w[WPL > 1 ? 1 : 0] = v.y; w[WPL > 2 ? 2 : 0] = v.z; w[WPL > 3 ? 3 : 0] = v.w;
+      } else if (WPL == 2) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+        w[0] = v.x; w[WPL > 1 ? 1 : 0] = v.y;
+      } else {
+        w[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
+      }
+    };
+    uint32_t nx0[WPL], nx1[WPL];
+    load_words(r0, nx0);
+    if (TWO) load_words(r1, nx1);
+    hook();  // first code chunks in flight: speculative prefetches for the next hop ride along
+    for (uint32_t cb = 0; cb < nch; ++cb) {
+      uint32_t w0[WPL], w1[WPL];
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) { w0[k] = nx0[k]; w1[k] = TWO ? nx1[k] : 0u; }
+      if (cb + 1 < nch) {  // next 16 code bytes while this chunk's centroids are fetched
+        load_words(r0 + (cb + 1) * 16, nx0);
+        if (TWO) load_words(r1 + (cb + 1) * 16, nx1);
+      }
+      const uint32_t ibase = cb * 16 + s * WPL * 4;
+      float t0[WPL * 4], t1[WPL * 4];
+#pragma unroll
+      for (int k = 0; k < WPL; ++k) {
+        // the lane's word k covers sub-vectors ibase + 4k .. +3; past M (only when M % 16 != 0, LPC = 1)
+        // the word is skipped warp-uniformly
+        if (LPC == 1 && ibase + 4 * k >= a.pqM) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { t0[4 * k + j] = 0.0f; t1[4 * k + j] = 0.0f; }
+          continue;
+        }
+        float4 c0[4][V4], c1[4][V4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t i = ibase + 4 * k + j;
+          const uint32_t k0 = (w0[k] >> (8 * j)) & 0xFFu;
+          load_entry(a.pq_cent + (size_t(i) * K + k0) * SUB, c0[j]);
+          if (TWO) {
+            const uint32_t k1 = (w1[k] >> (8 * j)) & 0xFFu;
+            load_entry(a.pq_cent + (size_t(i) * K + k1) * SUB, c1[j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t i = ibase + 4 * k + j;
+          t0[4 * k + j] = term(c0[j], i);
+          if (TWO) t1[4 * k + j] = term(c1[j], i);
+        }
+      }
+      // the chunk's terms in sub-vector order: word x of the chunk lives in lane x / WPL of the group
+      const uint32_t left = a.pqM - cb * 16;  // sub-vectors of this chunk that exist (>= 16 except in the last)
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        if (LPC == 1 && uint32_t(4 * x) >= left) break;  // warp-uniform
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float v0 = t0[4 * (x % WPL) + j];
+          if (LPC > 1) v0 = __shfl_sync(SDB_FULL, v0, (lane - s) + x / WPL);
+          d0 = __fadd_rn(d0, v0);
+          if (TWO) d1 = __fadd_rn(d1, t1[4 * x + j]);
+        }
+      }
+    }
+    if (h0 && s == 0) cdist[c] = d0;
+    if (h1) cdist[lane + 32] = d1;
+    __syncwarp();
+  }
+  template <class Hook>
+  __device__ __forceinline__ void eval(const SearchArgs& a, const uint32_t* cid, float* cdist, int n, int lane, Hook&& hook) {
+    const bool whole = (a.pqM & 15u) == 0;  // groups need whole 16-sub-vector chunks
+    if (n > 32) chains<1, true>(a, cid, cdist, n, lane, hook);
+    else if (n > 16 || !whole) chains<1, false>(a, cid, cdist, n, lane, hook);
+    else if (n > 8) chains<2, false>(a, cid, cdist, n, lane, hook);
+    else chains<4, false>(a, cid, cdist, n, lane, hook);
+  }
+};
+
+enum EvalKind : int { EVAL_FLOAT_FIXED = 0, EVAL_FLOAT_GENERIC = 1, EVAL_BITS = 2, EVAL_ADC = 3, EVAL_ADC_SMEM = 4, EVAL_ADC_FLY = 5 };
 
 // ---- shared-memory layout per query-warp ------------------------------------------------
 template <class VT, bool FILTER>
@@ -1044,7 +1178,7 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
   }
   const uint32_t lt = (1u << lane) - 1;
   // speculative L2 prefetch of the runner-up's rows: the small-row evaluators only (see the hop loop)
-  constexpr bool PFROWS = PF && (KIND == EVAL_BITS || KIND == EVAL_ADC_SMEM || KIND == EVAL_ADC);
+  constexpr bool PFROWS = PF && (KIND == EVAL_BITS || KIND == EVAL_ADC_SMEM || KIND == EVAL_ADC || KIND == EVAL_ADC_FLY);
 
   for (;;) {
     uint32_t qi = 0;
@@ -1071,6 +1205,9 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
     BitEval<(BITS ? METRIC : METRIC_HAMMING), (BITS ? TRIPS : 1), (BITS ? SETS : 1)> ev_bits;
     AdcEval ev_adc;
     AdcEvalSmem<(KIND == EVAL_ADC_SMEM ? TRIPS : 1)> ev_adcs;
+    constexpr bool FLY = (KIND == EVAL_ADC_FLY);
+    AdcEvalFly<(FLY && METRIC == METRIC_EUCLIDEAN ? METRIC_EUCLIDEAN : METRIC_DOT), (FLY ? TRIPS : 4)> ev_fly;
+    if (FLY) ev_fly.qs = qs;
     if (KIND == EVAL_ADC_SMEM)
       ev_adcs.load_table(tab, a.adc + size_t(qi) * a.pqM * a.pqK, a.pqM * a.pqK, tbar, tphase, lane);
     if (KIND == EVAL_FLOAT_FIXED) ev_fixed.load_query(qs, a.queries + size_t(qi) * a.dim, lane);
@@ -1084,6 +1221,7 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
       if (KIND == EVAL_BITS) ev_bits.eval(a, cid, cdist, n, lane, hook);
       if (KIND == EVAL_ADC) ev_adc.eval(a, cid, cdist, n, lane, hook);
       if (KIND == EVAL_ADC_SMEM) ev_adcs.eval(a, cid, cdist, n, lane, hook);
+      if (KIND == EVAL_ADC_FLY) ev_fly.eval(a, cid, cdist, n, lane, hook);
     };
     auto evaluate = [&](int n) { evaluate_h(n, no_hook); };
 
@@ -1265,7 +1403,7 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
         if (nnew > 0) {
           if (x0 == 0) evaluate_h(nnew, pf_rows);
           else evaluate(nnew);
-          constexpr bool TIEFIX = (KIND == EVAL_BITS || KIND == EVAL_ADC || KIND == EVAL_ADC_SMEM);  // integer-valued / coarse distances
+          constexpr bool TIEFIX = (KIND == EVAL_BITS || KIND == EVAL_ADC || KIND == EVAL_ADC_SMEM || KIND == EVAL_ADC_FLY);  // integer-valued / coarse distances
           if (MERGE_MIN == 0 || !list.template merge<TIEFIX>(cid, cdist, nnew, lane, lt, MERGE_MIN)) add_with_limit(list, nnew);
         }
         if (!XTRA || e != START_ID || x0 >= a.n_start_extra) break;

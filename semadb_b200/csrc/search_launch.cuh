@@ -69,7 +69,7 @@ int launch_variant(sdb_index* ix, const SearchArgs& a, cudaStream_t stream) {
   if (a.n_start_extra != 0)
     return launch_variant_x<KIND, METRIC, TRIPS, SETS, LEGACY, MERGE_MIN, VT, FILTER, RETRY, MINB, true>(ix, a, stream);
   // speculative row prefetch (small-row evaluators, unfiltered first pass); SDB_NO_PF=1 = A/B switch
-  constexpr bool CAN_PF = !FILTER && !RETRY && (KIND == EVAL_BITS || KIND == EVAL_ADC_SMEM || KIND == EVAL_ADC);
+  constexpr bool CAN_PF = !FILTER && !RETRY && (KIND == EVAL_BITS || KIND == EVAL_ADC_SMEM || KIND == EVAL_ADC || KIND == EVAL_ADC_FLY);
   if (CAN_PF) {
     static const bool no_pf = getenv("SDB_NO_PF") != nullptr;
     if (!no_pf)
@@ -95,7 +95,7 @@ int launch_with_retry(sdb_index* ix, SearchArgs a, cudaStream_t stream) {
   // pipelined row gather is what keeps that under a millisecond); the ADC table is read from
   // global memory
   constexpr int RK = (KIND == EVAL_ADC_SMEM) ? EVAL_ADC : KIND;
-  constexpr int RT = (KIND == EVAL_BITS || KIND == EVAL_FLOAT_FIXED) ? TRIPS : 1;  // rows must still be covered
+  constexpr int RT = (KIND == EVAL_BITS || KIND == EVAL_FLOAT_FIXED || KIND == EVAL_ADC_FLY) ? TRIPS : 1;  // rows must still be covered
   constexpr int RS = (KIND == EVAL_BITS || KIND == EVAL_FLOAT_FIXED) ? SETS : 1;
   if (getenv("SDB_DEBUG_RETRY")) {
     uint32_t h[2] = {0, 0};
@@ -104,6 +104,25 @@ int launch_with_retry(sdb_index* ix, SearchArgs a, cudaStream_t stream) {
     fprintf(stderr, "[sdb] beam search: %u of %u queries overflowed the compact visited table -> retry launch\n", h[1], a.B);
   }
   return launch_variant<RK, METRIC, RT, RS, false, 0, VisitedBitmap, FILTER, true, 1>(ix, a, stream);
+}
+
+// PQ search without per-query tables: sub-vectors of 4, 8 or 16 floats whose number is a multiple
+// of 4 (C4: 96 x 8). SDB_ADC_TABLE=1 keeps the table kernels (A/B; they also serve other shapes).
+inline bool adc_on_the_fly(const sdb_index* ix) {
+  const bool table = getenv("SDB_ADC_TABLE") != nullptr || getenv("SDB_ADC_GLOBAL") != nullptr;
+  return !table && (ix->pqSub == 4 || ix->pqSub == 8 || ix->pqSub == 16) && ix->pqM % 4 == 0 && ix->store_metric != SDB_METRIC_COSINE;
+}
+
+// EVAL_ADC_FLY for sub-vectors of SUB floats; METRIC = the store's (euclidean or dot). Instantiated in
+// search_pq_fly{4,8,16}.cu.
+template <int SUB>
+int launch_pq_fly(sdb_index* ix, const SearchArgs& a, bool filtered, cudaStream_t stream) {
+  const bool l2 = ix->store_metric == SDB_METRIC_EUCLIDEAN;
+  if (filtered)
+    return l2 ? launch_with_retry<EVAL_ADC_FLY, METRIC_EUCLIDEAN, SUB, 1, false, 0, true, 1>(ix, a, stream)
+              : launch_with_retry<EVAL_ADC_FLY, METRIC_DOT, SUB, 1, false, 0, true, 1>(ix, a, stream);
+  return l2 ? launch_with_retry<EVAL_ADC_FLY, METRIC_EUCLIDEAN, SUB, 1, false, 2, false, 12>(ix, a, stream)
+            : launch_with_retry<EVAL_ADC_FLY, METRIC_DOT, SUB, 1, false, 2, false, 12>(ix, a, stream);
 }
 
 // Tuning knob for A/B runs on the GPU (not part of the ABI): SDB_K1_VARIANT picks the

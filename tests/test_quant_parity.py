@@ -184,3 +184,44 @@ def test_product_quantizer_insert_and_search():
     gt = oix.flat_search(Q[:20], k=10, threads=4)
     fi, fd, fc = g.flat_search_batch(Q[:20], 10)
     assert (fi == gt["ids"].astype(np.uint64)).all() and _same(fd, gt["dists"])
+
+
+def test_c4_shape_fit_tables_and_search(monkeypatch):
+    """The C4 shape of BASELINE.json — 768-d dot product, PQ with 96 sub-vectors of 8 floats and
+    256 centroids — against the oracle: k-means centroids, centroidDists, codes and the
+    written-through rows (product.go:175-236, kmeans.go:34-150), the per-query ADC tables
+    (product.go:255-263), and the search itself (product.go:238-277) by each of the three PQ
+    evaluators: entries computed on the fly from the codebook (default), table in shared memory,
+    table through L1/L2 — ids, distances, hop and evaluation counts all equal."""
+    n, dim, M, K = 3000, 768, 96, 256
+    X = synth.latent_gaussian(n, dim, seed=8, latent=16, normalize=True)
+    Q = synth.latent_gaussian(64, dim, seed=9, w_seed=8, latent=16, normalize=True)
+    ids = np.arange(2, n + 2, dtype=np.uint32)
+    oix = O.OracleIndex(dim, "dot", quantizer="product", pq_m=M, pq_k=K, pq_trigger=1000)
+    start = synth.start_vector(dim, 5)
+    oix.set_start(start)
+    params = IndexVectorVamanaParameters(dim, "dot", quantizer=Quantizer(
+        "product", product=ProductQuantizerParameters(K, M, 1000)))
+    g = IndexVamana("c4", params, start_vector=start)
+    g.insert_config(1, 1, 16)  # the reference's sequential schedule: the graph must come out edge for edge
+    oix.insert(ids[:2000], X[:2000], threads=1)
+    g.insert_batch(ids[:2000].astype(np.uint64), X[:2000])
+    assert oix.fit(pq_first=3, pq_alias=True, threads=8) == 1
+    assert g.fit(3) is True
+    ofc, ocd = oix.get_pq()
+    gfc, gcd = g.get_pq()
+    assert _same(gfc, ofc) and _same(gcd, ocd)
+    all_ids = np.concatenate([[1], ids[:2000]]).astype(np.uint32)
+    assert _same(g.get_codes(all_ids.astype(np.uint64)), oix.get_codes(all_ids))
+    assert _same(g.get_vectors(all_ids.astype(np.uint64)), oix.get_vectors(all_ids))
+    tabs = g.adc_tables(Q[:4])
+    for b in range(4):
+        assert _same(tabs[b], oix.adc_table(Q[b]))
+    oix.insert(ids[2000:], X[2000:], threads=1)  # ADC search + SDC prune
+    g.insert_batch(ids[2000:].astype(np.uint64), X[2000:])
+    _check_graph_equal(oix, g, n)
+    _check_search(oix, g, Q)  # on the fly
+    monkeypatch.setenv("SDB_ADC_TABLE", "1")
+    _check_search(oix, g, Q)  # table in shared memory
+    monkeypatch.setenv("SDB_ADC_GLOBAL", "1")
+    _check_search(oix, g, Q)  # table through L1/L2
