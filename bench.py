@@ -661,7 +661,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5b", "c5a"])
     ap.add_argument("--extra", default="auto", help="auto | none | comma list of c3,c4,c5b,c5a")
-    ap.add_argument("--n", type=int, default=0, help="points per GPU shard of the headline workload (0 = the config's)")
+    ap.add_argument("--points", "--n", dest="n", type=int, default=0,
+                    help="points per GPU shard of the headline workload (0 = the config's)")
     ap.add_argument("--extra-n", default="", help="name=points,... overrides for the extra workloads (tests)")
     ap.add_argument("--queries", type=int, default=10_000)
     ap.add_argument("--ref-queries", type=int, default=10_000)

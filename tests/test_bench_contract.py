@@ -13,7 +13,7 @@ ROOT = Path(__file__).resolve().parent.parent
 def _run(extra_env=None):
     env = dict(os.environ)
     env.update(extra_env or {})
-    p = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--n", "20000", "--queries", "300",
+    p = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--points", "20000", "--queries", "300",
                         "--steps", "2", "--warmup", "1", "--gpus", "1"], capture_output=True, text=True, env=env, timeout=600)
     assert p.returncode == 0, p.stderr[-2000:]
     return p.stdout

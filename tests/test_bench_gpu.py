@@ -12,7 +12,7 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 def test_bench_line_contract_small():
-    p = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--n", "50000", "--queries", "2000", "--steps", "3",
+    p = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--points", "50000", "--queries", "2000", "--steps", "3",
                         "--warmup", "3", "--recall-queries", "500", "--extra", "c5a,c3,c5b",
                         "--extra-n", "c5a=40000,c3=30000,c5b=60000"], capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stderr[-2000:]
