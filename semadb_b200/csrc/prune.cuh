@@ -30,10 +30,12 @@ struct PruneShared {
   float* sdist;      // [cap]
   uint8_t* removed;  // [cap]
   uint32_t* edges;   // [64] result
+  uint32_t* kill;    // [MATRIX_MAX][MATRIX_MAX/32] bit (i, j): accepting candidate i removes candidate j
   int n;             // candidates (same value in every thread)
   int* cnt;          // shared: edges written so far
+  static constexpr int MATRIX_MAX = 128;
   static __host__ __device__ size_t bytes(int cap) {
-    return ((size_t(cap) * 17 + 15) / 16) * 16 + 64 * 4 + 16;
+    return ((size_t(cap) * 17 + 15) / 16) * 16 + 64 * 4 + 16 + size_t(MATRIX_MAX) * (MATRIX_MAX / 32) * 4;
   }
   // returns the first byte after the carved area (16-byte aligned)
   __device__ __forceinline__ unsigned char* carve(unsigned char* base, int cap) {
@@ -45,8 +47,9 @@ struct PruneShared {
     unsigned char* p = base + ((size_t(cap) * 17 + 15) / 16) * 16;
     edges = reinterpret_cast<uint32_t*>(p);
     cnt = reinterpret_cast<int*>(p + 64 * 4);
+    kill = reinterpret_cast<uint32_t*>(p + 64 * 4 + 16);
     n = 0;
-    return p + 64 * 4 + 16;
+    return p + 64 * 4 + 16 + size_t(MATRIX_MAX) * (MATRIX_MAX / 32) * 4;
   }
 };
 
@@ -143,8 +146,19 @@ __device__ inline void stage_rows(const StoreView& s, PruneShared& sh, unsigned 
 
 // robustPrune (search.go:106-138) over the sorted candidates in sh.sid/sdist; node = id of
 // the node being pruned (skipped if it appears, search.go:116). Fills sh.edges/sh.cnt.
-__device__ inline void robust_prune_cta(const StoreView& s, PruneShared& sh, const unsigned char* rows, int staged,
-                                 uint32_t node, int R, float alpha) {
+//
+// The reference walks the candidates in ascending order; an accepted candidate p* removes every
+// later candidate c with alpha * d(p*, c) < d(node, c) (search.go:132, strict). Whether p* removes
+// c does not depend on the walk, only on the pair — so for lists of up to MATRIX_MAX candidates
+// (back-edge prunes have R+1 = 65, a new point's visited list ~80-100) all pairs (i < j) are
+// evaluated first, in parallel by the CTA's 8-lane groups with no barrier in the loop, into a
+// bit matrix kill[i] = {j : alpha * d(i, j) < sdist[j]}; one warp then replays the walk with bit
+// operations: skip removed / self, accept, stop at R, removed |= kill[i]. Same distances, same
+// comparisons, same edges as the sequential form (kept below for longer lists), which spent its
+// time in one block-wide barrier per accepted candidate (profiles/r01_ab_insert.txt: 30 % barrier
+// stalls in backedge_kernel).
+__device__ inline void robust_prune_cta_seq(const StoreView& s, PruneShared& sh, const unsigned char* rows, int staged,
+                                            uint32_t node, int R, float alpha) {
   const int n = sh.n;
   const int lane = threadIdx.x & 31;
   const int g = lane & 7;
@@ -173,6 +187,58 @@ __device__ inline void robust_prune_cta(const StoreView& s, PruneShared& sh, con
     __syncthreads();  // removal marks of this round are visible before the next candidate is read
   }
   if (threadIdx.x == 0) *sh.cnt = cnt;
+  __syncthreads();
+}
+
+__device__ inline void robust_prune_cta(const StoreView& s, PruneShared& sh, const unsigned char* rows, int staged,
+                                        uint32_t node, int R, float alpha) {
+  const int n = sh.n;
+  if (n > PruneShared::MATRIX_MAX) {
+    robust_prune_cta_seq(s, sh, rows, staged, node, R, alpha);
+    return;
+  }
+  constexpr int KW = PruneShared::MATRIX_MAX / 32;
+  const int lane = threadIdx.x & 31;
+  const int g = lane & 7;
+  const int grp = threadIdx.x >> 3;
+  for (int t = threadIdx.x; t < n * KW; t += blockDim.x) sh.kill[t] = 0;
+  __syncthreads();
+  // all pairs i < j, flattened so that every group always has a pair: step t covers the pair of
+  // rank t in row-major order of the strict upper triangle
+  const int total = n * (n - 1) / 2;
+  for (int t0 = 0; t0 < total; t0 += PRUNE_GROUPS) {
+    const int t = t0 + grp;
+    const bool act = t < total;
+    // row i of the triangle starts at off(i) = i*(2n-i-1)/2: invert with a float estimate, fix up
+    int i = 0, j = 1;
+    if (act) {
+      const float fn = float(2 * n - 1);
+      i = int((fn - sqrtf(fn * fn - 8.0f * float(t))) * 0.5f);
+      if (i < 0) i = 0;
+      while (i > 0 && i * (2 * n - i - 1) / 2 > t) --i;
+      while ((i + 1) * (2 * n - i - 2) / 2 <= t) ++i;
+      j = i + 1 + (t - i * (2 * n - i - 1) / 2);
+    }
+    const unsigned char* xi = i < staged ? rows + size_t(i) * s.row_bytes : global_row(s, sh.sid[i]);
+    const unsigned char* yj = j < staged ? rows + size_t(j) * s.row_bytes : global_row(s, sh.sid[j]);
+    const float d = row_dist(s, xi, yj, g);
+    if (act && g == 0 && __fmul_rn(alpha, d) < sh.sdist[j]) atomicOr(&sh.kill[i * KW + (j >> 5)], 1u << (j & 31));  // search.go:132
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    // the walk (search.go:113-137), warp-uniform: lane w < KW holds word w of the removed set
+    uint32_t removed = 0;
+    int cnt = 0;
+    for (int i = 0; i < n; ++i) {
+      const uint32_t word = __shfl_sync(SDB_FULL, removed, i >> 5);
+      if (((word >> (i & 31)) & 1u) || sh.sid[i] == node) continue;
+      if (lane == 0) sh.edges[cnt] = sh.sid[i];
+      ++cnt;
+      if (cnt >= R) break;
+      if (lane < KW) removed |= sh.kill[i * KW + lane];
+    }
+    if (lane == 0) *sh.cnt = cnt;
+  }
   __syncthreads();
 }
 

@@ -14,7 +14,13 @@
 // indices* into the device vector array and the update writes in place, which gives the
 // same observable behaviour. Sums are accumulated sequentially in row order per
 // (cluster, dimension) like kmeans.go:125-137, so every f32 value matches the reference.
-// One CTA per sub-vector; the sub-spaces are independent (product.go:201-233).
+// The sub-spaces are independent (product.go:201-233): the farthest-first init runs one CTA per
+// sub-space (K-1 dependent rounds), the Lloyd rounds run as grid-wide kernels — assign over
+// (sub-space x row tiles), ordered sums with a warp per cluster, write-through — with a per
+// sub-space stop flag. sub = dim/M is 8 at C4: the assign is 2*n*K*sub FLOP per sub-space and
+// round with an inner dimension of 8, nothing a tensor-core tile could chew on (and bf16/tf32
+// products would break the exact argmin); it is an exact FFMA kernel.
+#include <algorithm>
 #include <cfloat>
 
 #include "common.cuh"
@@ -38,7 +44,7 @@ __global__ void bq_mean_kernel(const float* vec, uint32_t pitch, const uint32_t*
 struct KmArgs {
   float* vec; uint32_t pitch;
   const uint32_t* row_ids; uint32_t n;
-  uint32_t sub, K, max_iter;
+  uint32_t sub, K, M, max_iter;
   uint32_t first;
   uint8_t* labels;      // [M][n]
   float* min_dist;      // [M][n]
@@ -46,7 +52,11 @@ struct KmArgs {
   uint32_t* counts;     // [M][K]
   uint32_t* cent_row;   // [M][K] index into row_ids
   uint32_t* iters;      // [M]
+  uint32_t* changes;    // [M] labels changed by the current assign round
+  uint32_t* active;     // [M] sub-space still iterating
+  uint32_t* any_active; // [1]
   int stage_centroids;  // K*sub floats fit in shared memory
+  __device__ __forceinline__ float* X(uint32_t m, uint32_t r) const { return vec + size_t(row_ids[r]) * pitch + m * sub; }
 };
 
 struct BestPair {
@@ -59,33 +69,33 @@ __device__ __forceinline__ BestPair better(BestPair a, BestPair b) {
   return a;
 }
 
-__global__ void __launch_bounds__(KM_THREADS) kmeans_kernel(KmArgs a) {
-  extern __shared__ __align__(16) float cs[];  // staged centroids [K][sub] or one centroid [sub]
+// ---- init (kmeans.go:54-83): farthest-first from a given first row. K-1 dependent rounds, each a
+// distance pass over the n rows and a block-wide argmax with the reference's first-max rule: one
+// CTA per sub-space (the sub-spaces are independent, product.go:201-233).
+__global__ void __launch_bounds__(KM_THREADS) km_init_kernel(KmArgs a) {
+  extern __shared__ __align__(16) float cs[];  // the last chosen centre [sub]
   __shared__ BestPair red[32];
-  __shared__ uint32_t s_changes;
-  __shared__ uint32_t s_pick;
   const uint32_t m = blockIdx.x;
-  const uint32_t off = m * a.sub;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   uint8_t* labels = a.labels + size_t(m) * a.n;
   float* md = a.min_dist + size_t(m) * a.n;
-  float* sums = a.sums + size_t(m) * a.K * a.sub;
-  uint32_t* counts = a.counts + size_t(m) * a.K;
   uint32_t* crow = a.cent_row + size_t(m) * a.K;
-  auto X = [&](uint32_t r) -> float* { return a.vec + size_t(a.row_ids[r]) * a.pitch + off; };
-
-  // ---- init (kmeans.go:54-83)
   for (uint32_t j = tid; j < a.n; j += KM_THREADS) { md[j] = FLT_MAX; labels[j] = 0; }
-  if (tid == 0) crow[0] = a.first;
+  if (tid == 0) {
+    crow[0] = a.first;
+    a.active[m] = 1;
+    a.changes[m] = 0;
+    a.iters[m] = 0;
+  }
   __syncthreads();
   for (uint32_t i = 1; i < a.K; ++i) {
-    const float* c = X(crow[i - 1]);
+    const float* c = a.X(m, crow[i - 1]);
     for (uint32_t t = tid; t < a.sub; t += KM_THREADS) cs[t] = c[t];
     __syncthreads();
     BestPair best{0.0f, 0u};
     for (uint32_t j = tid; j < a.n; j += KM_THREADS) {
       if (j == a.first) continue;  // only randId is in alreadyCentroid (kmeans.go:62,69)
-      float d = float_dist_thread<METRIC_EUCLIDEAN>(X(j), cs, int(a.sub));
+      float d = float_dist_thread<METRIC_EUCLIDEAN>(a.X(m, j), cs, int(a.sub));
       float cur = md[j];
       if (d < cur) { cur = d; md[j] = d; }
       best = better(best, BestPair{cur, j});
@@ -108,56 +118,104 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_kernel(KmArgs a) {
     }
     __syncthreads();
   }
+}
 
-  // ---- Lloyd iterations (kmeans.go:95-147)
-  uint32_t iter = 0;
-  for (; iter < a.max_iter; ++iter) {
-    if (a.stage_centroids) {
-      for (uint32_t t = tid; t < a.K * a.sub; t += KM_THREADS) cs[t] = X(crow[t / a.sub])[t % a.sub];
-    }
-    if (tid == 0) s_changes = 0;
-    __syncthreads();
-    uint32_t changes = 0;
-    for (uint32_t j = tid; j < a.n; j += KM_THREADS) {
-      const float* x = X(j);
-      float best = float_dist_thread<METRIC_EUCLIDEAN>(x, a.stage_centroids ? cs : X(crow[0]), int(a.sub));
-      uint32_t bid = 0;
-      for (uint32_t i = 1; i < a.K; ++i) {
-        const float* c = a.stage_centroids ? cs + size_t(i) * a.sub : X(crow[i]);
-        float d = float_dist_thread<METRIC_EUCLIDEAN>(x, c, int(a.sub));
-        if (d < best) { best = d; bid = i; }
-      }
-      if (labels[j] != uint8_t(bid)) { ++changes; labels[j] = uint8_t(bid); }
-    }
-    if (changes) atomicAdd(&s_changes, changes);
-    __syncthreads();
-    if (s_changes == 0) { ++iter; break; }  // kmeans.go:116-118 (this round still counts)
-    // update: per-label sums in row order, sequential f32 (kmeans.go:121-138)
-    for (uint32_t k = tid; k < a.K; k += KM_THREADS) {
-      uint32_t c = 0;
-      for (uint32_t r = 0; r < a.n; ++r) c += (labels[r] == k);
-      counts[k] = c;
-    }
-    for (uint32_t t = tid; t < a.K * a.sub; t += KM_THREADS) {
-      const uint32_t k = t / a.sub, jd = t % a.sub;
-      float s = 0.0f;
-      for (uint32_t r = 0; r < a.n; ++r)
-        if (labels[r] == k) s = __fadd_rn(s, X(r)[jd]);
-      sums[t] = s;
-    }
-    __syncthreads();
-    // means written through the aliased centroid rows, in centroid order (kmeans.go:140-146)
-    for (uint32_t jd = tid; jd < a.sub; jd += KM_THREADS) {
-      for (uint32_t i = 0; i < a.K; ++i) {
-        uint32_t c = counts[i];
-        if (c == 0) continue;
-        X(crow[i])[jd] = __fdiv_rn(sums[size_t(i) * a.sub + jd], float(c));
-      }
-    }
+// ---- assign (kmeans.go:100-115): argmin over the K centres, strict '<' (lowest index wins).
+// One CTA per (row tile, sub-space): the sub-space's centres sit in shared memory, a thread owns a
+// row. SUBT > 0: the row's sub-vector lives in registers. Grid M x ceil(n / tile): every SM works.
+constexpr int KM_TILE = 256;
+template <int SUBT>
+__global__ void __launch_bounds__(KM_TILE) km_assign_kernel(KmArgs a) {
+  extern __shared__ __align__(16) float cs[];  // [K][sub] if staged
+  const uint32_t m = blockIdx.y;
+  if (!a.active[m]) return;
+  const uint32_t sub = SUBT > 0 ? uint32_t(SUBT) : a.sub;
+  uint32_t* crow = a.cent_row + size_t(m) * a.K;
+  if (a.stage_centroids) {
+    for (uint32_t t = threadIdx.x; t < a.K * sub; t += KM_TILE) cs[t] = a.X(m, crow[t / sub])[t % sub];
     __syncthreads();
   }
-  if (tid == 0) a.iters[m] = iter;
-  (void)s_pick;
+  uint8_t* labels = a.labels + size_t(m) * a.n;
+  uint32_t changes = 0;
+  for (uint32_t j = blockIdx.x * KM_TILE + threadIdx.x; j < a.n; j += gridDim.x * KM_TILE) {
+    const float* xg = a.X(m, j);
+    float xr[SUBT > 0 ? SUBT : 1];
+    if (SUBT > 0) {
+#pragma unroll
+      for (int t = 0; t < SUBT; ++t) xr[t] = xg[t];
+    }
+    const float* x = SUBT > 0 ? xr : xg;
+    float best = float_dist_thread<METRIC_EUCLIDEAN>(x, a.stage_centroids ? cs : a.X(m, crow[0]), int(sub));
+    uint32_t bid = 0;
+    for (uint32_t i = 1; i < a.K; ++i) {
+      const float* c = a.stage_centroids ? cs + size_t(i) * sub : a.X(m, crow[i]);
+      float d = float_dist_thread<METRIC_EUCLIDEAN>(x, c, int(sub));
+      if (d < best) { best = d; bid = i; }
+    }
+    if (labels[j] != uint8_t(bid)) { ++changes; labels[j] = uint8_t(bid); }
+  }
+  changes = __reduce_add_sync(SDB_FULL, changes);
+  if ((threadIdx.x & 31) == 0 && changes) atomicAdd(a.changes + m, changes);
+}
+
+// ---- "no label changed => stop" (kmeans.go:116-118), per sub-space; the round still counts
+__global__ void km_flags_kernel(KmArgs a, uint32_t iter) {
+  const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= a.M) return;
+  if (a.active[m]) {
+    a.iters[m] = iter + 1;
+    if (a.changes[m] == 0) a.active[m] = 0;
+    else atomicOr(a.any_active, 1u);
+    a.changes[m] = 0;
+  }
+}
+
+// ---- update (kmeans.go:121-138): per-(cluster, dimension) sums in ROW ORDER, sequential f32.
+// One warp per cluster walks the label array once, 32 rows per step: a ballot marks the rows of
+// its cluster and they are added in ascending order, lane jd owning dimension jd — the same
+// chain of additions as the reference, without every (cluster, dimension) thread scanning all
+// n labels on its own.
+__global__ void __launch_bounds__(256) km_update_kernel(KmArgs a) {
+  const uint32_t m = blockIdx.y;
+  if (!a.active[m]) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (k >= a.K) return;
+  const uint8_t* labels = a.labels + size_t(m) * a.n;
+  for (uint32_t jd0 = 0; jd0 < a.sub; jd0 += 32) {
+    const uint32_t jd = jd0 + lane;
+    float s = 0.0f;
+    uint32_t cnt = 0;
+    for (uint32_t r0 = 0; r0 < a.n; r0 += 32) {
+      const uint32_t r = r0 + lane;
+      uint32_t mask = __ballot_sync(SDB_FULL, r < a.n && labels[r] == uint8_t(k));
+      cnt += __popc(mask);
+      while (mask) {
+        const uint32_t rr = r0 + __ffs(mask) - 1;
+        mask &= mask - 1;
+        if (jd < a.sub) s = __fadd_rn(s, a.X(m, rr)[jd]);
+      }
+    }
+    if (jd < a.sub) a.sums[(size_t(m) * a.K + k) * a.sub + jd] = s;
+    if (jd0 == 0 && lane == 0) a.counts[size_t(m) * a.K + k] = cnt;
+  }
+}
+
+// ---- means written through the aliased centroid rows, in centroid order (kmeans.go:140-146):
+// the centres ARE rows of the stored vectors (kmeans.go:63,82), so this overwrites caller data
+// exactly like the reference; an empty cluster keeps its centre.
+__global__ void km_write_kernel(KmArgs a) {
+  const uint32_t m = blockIdx.x;
+  if (!a.active[m]) return;
+  const uint32_t* crow = a.cent_row + size_t(m) * a.K;
+  const uint32_t* counts = a.counts + size_t(m) * a.K;
+  for (uint32_t jd = threadIdx.x; jd < a.sub; jd += blockDim.x) {
+    for (uint32_t i = 0; i < a.K; ++i) {
+      const uint32_t c = counts[i];
+      if (c == 0) continue;
+      a.X(m, crow[i])[jd] = __fdiv_rn(a.sums[(size_t(m) * a.K + i) * a.sub + jd], float(c));
+    }
+  }
 }
 
 // codes of the training rows = k-means labels (product.go:216-218); flatCentroids copy
@@ -219,7 +277,7 @@ int fit_locked(sdb_index* ix, uint64_t pq_first_row, int32_t* fitted) {
   sdb::DevBuf<uint32_t> d_counts;
   auto cleanup = [&]() { d_labels.release(); d_md.release(); d_sums.release(); d_counts.release(); };
   if ((rc = d_labels.ensure(size_t(M) * n)) || (rc = d_md.ensure(size_t(M) * n)) || (rc = d_sums.ensure(size_t(M) * K * sub)) ||
-      (rc = d_counts.ensure(size_t(M) * K * 2 + M))) {
+      (rc = d_counts.ensure(size_t(M) * K * 2 + 4 * size_t(M) + 8))) {
     cleanup();
     return rc;
   }
@@ -234,18 +292,46 @@ int fit_locked(sdb_index* ix, uint64_t pq_first_row, int32_t* fitted) {
   }
   KmArgs ka{};
   ka.vec = ix->d_vec; ka.pitch = ix->vec_pitch; ka.row_ids = ix->d_tmp32.p; ka.n = n;
-  ka.sub = sub; ka.K = K; ka.max_iter = 100;  // product.go:209
+  ka.sub = sub; ka.K = K; ka.M = M; ka.max_iter = 100;  // product.go:209
   ka.first = uint32_t(pq_first_row);
   ka.labels = d_labels.p; ka.min_dist = d_md.p; ka.sums = d_sums.p;
   ka.counts = d_counts.p; ka.cent_row = d_counts.p + size_t(M) * K; ka.iters = d_counts.p + size_t(M) * K * 2;
+  ka.changes = ka.iters + M; ka.active = ka.changes + M; ka.any_active = ka.active + M;
   size_t full = size_t(K) * sub * sizeof(float);
   ka.stage_centroids = full <= 96 * 1024;
-  size_t smem = ka.stage_centroids ? full : size_t(sub) * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(kmeans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "cudaFuncSetAttribute(kmeans)"); }
-  kmeans_kernel<<<M, KM_THREADS, smem, st>>>(ka);
+  cudaError_t e;
+#define KM_CUDA(expr)                                                  \
+  do {                                                                 \
+    if ((e = (expr)) != cudaSuccess) { cleanup(); return cuda_fail(e, #expr); } \
+  } while (0)
+  KM_CUDA(cudaFuncSetAttribute(km_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(sub) * 4)));
+  km_init_kernel<<<M, KM_THREADS, size_t(sub) * 4, st>>>(ka);
   ix->launches++;
-  if ((e = cudaGetLastError()) != cudaSuccess) { cleanup(); return cuda_fail(e, "kmeans_kernel"); }
+  KM_CUDA(cudaGetLastError());
+  // Lloyd iterations (kmeans.go:95-147): assign over (sub-space x row tiles), the stop test per
+  // sub-space, then the ordered sums and the write-through — sub-spaces that have converged drop out
+  const size_t asmem = ka.stage_centroids ? full : 0;
+  auto assign = sub == 4 ? km_assign_kernel<4> : sub == 8 ? km_assign_kernel<8> : sub == 16 ? km_assign_kernel<16> : km_assign_kernel<0>;
+  KM_CUDA(cudaFuncSetAttribute(assign, cudaFuncAttributeMaxDynamicSharedMemorySize, int(asmem)));
+  const dim3 agrid(std::max<uint32_t>(1, std::min<uint32_t>((n + KM_TILE - 1) / KM_TILE, 64)), M);
+  const dim3 ugrid((K + 7) / 8, M);
+  uint32_t* h_any = nullptr;
+  KM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_any), sizeof(uint32_t)));
+  for (uint32_t it = 0; it < ka.max_iter; ++it) {
+    assign<<<agrid, KM_TILE, asmem, st>>>(ka);
+    cudaMemsetAsync(ka.any_active, 0, sizeof(uint32_t), st);
+    km_flags_kernel<<<(M + 127) / 128, 128, 0, st>>>(ka, it);
+    cudaMemcpyAsync(h_any, ka.any_active, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    ix->launches += 2;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { cudaFreeHost(h_any); cleanup(); return cuda_fail(e, "k-means iteration"); }
+    if (*h_any == 0) break;
+    km_update_kernel<<<ugrid, 256, 0, st>>>(ka);
+    km_write_kernel<<<M, 64, 0, st>>>(ka);
+    ix->launches += 2;
+  }
+  cudaFreeHost(h_any);
+  KM_CUDA(cudaGetLastError());
+#undef KM_CUDA
   if (ix->store_metric == SDB_METRIC_EUCLIDEAN)
     pq_finalize_kernel<METRIC_EUCLIDEAN><<<M, 256, 0, st>>>(ix->d_vec, ix->vec_pitch, ix->d_tmp32.p, n, M, K, sub, d_labels.p, ka.cent_row, ix->d_codes, ix->codes_pitch, ix->d_pq_centroids, ix->d_pq_cdist);
   else
