@@ -30,12 +30,13 @@ struct PruneShared {
   float* sdist;      // [cap]
   uint8_t* removed;  // [cap]
   uint32_t* edges;   // [64] result
-  uint32_t* kill;    // [MATRIX_MAX][MATRIX_MAX/32] bit (i, j): accepting candidate i removes candidate j
+  uint32_t* kill;    // [MATRIX_MAX][MATRIX_MAX/32] bit (i, j): accepting candidate i removes candidate j;
+                     // overlays id/dist, which are dead once the candidates are sorted (nullptr if they are too small)
   int n;             // candidates (same value in every thread)
   int* cnt;          // shared: edges written so far
   static constexpr int MATRIX_MAX = 128;
   static __host__ __device__ size_t bytes(int cap) {
-    return ((size_t(cap) * 17 + 15) / 16) * 16 + 64 * 4 + 16 + size_t(MATRIX_MAX) * (MATRIX_MAX / 32) * 4;
+    return ((size_t(cap) * 17 + 15) / 16) * 16 + 64 * 4 + 16;
   }
   // returns the first byte after the carved area (16-byte aligned)
   __device__ __forceinline__ unsigned char* carve(unsigned char* base, int cap) {
@@ -47,9 +48,9 @@ struct PruneShared {
     unsigned char* p = base + ((size_t(cap) * 17 + 15) / 16) * 16;
     edges = reinterpret_cast<uint32_t*>(p);
     cnt = reinterpret_cast<int*>(p + 64 * 4);
-    kill = reinterpret_cast<uint32_t*>(p + 64 * 4 + 16);
+    kill = size_t(cap) * 8 >= size_t(MATRIX_MAX) * (MATRIX_MAX / 32) * 4 ? reinterpret_cast<uint32_t*>(base) : nullptr;
     n = 0;
-    return p + 64 * 4 + 16 + size_t(MATRIX_MAX) * (MATRIX_MAX / 32) * 4;
+    return p + 64 * 4 + 16;
   }
 };
 
@@ -69,6 +70,22 @@ __device__ __forceinline__ float group_float_dist(const float* x, const float* y
   if (g == 0)
     for (uint32_t i = trips << 5; i < dim; ++i) tail = tail_accum<L2>(x[i], y[i], tail);
   return metric_epilogue<METRIC>(group_reduce(acc, tail));
+}
+
+// same for two rows known to sit in shared memory, dim = 32 * TRIPS
+template <int METRIC, int TRIPS>
+__device__ __forceinline__ float smem_float_dist(const float* x, const float* y, int g) {
+  constexpr bool L2 = (METRIC == METRIC_EUCLIDEAN);
+  const uint32_t xa = uint32_t(__cvta_generic_to_shared(x)) + 16u * g, ya = uint32_t(__cvta_generic_to_shared(y)) + 16u * g;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int t = 0; t < TRIPS; ++t) {
+    float4 a, b;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(xa + 128u * t));
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(ya + 128u * t));
+    trip_accum<L2>(a, b, acc);
+  }
+  return metric_epilogue<METRIC>(group_reduce(acc, 0.0f));
 }
 
 __device__ __forceinline__ float row_dist(const StoreView& s, const unsigned char* x, const unsigned char* y, int g) {
@@ -190,54 +207,117 @@ __device__ inline void robust_prune_cta_seq(const StoreView& s, PruneShared& sh,
   __syncthreads();
 }
 
-__device__ inline void robust_prune_cta(const StoreView& s, PruneShared& sh, const unsigned char* rows, int staged,
-                                        uint32_t node, int R, float alpha) {
+// All pairs (i < j) of the sorted candidates into the kill matrix. Rows are handed out in mirrored
+// pairs (u, n-2-u) — n-1-u and u+1 columns, n steps together — so every 8-lane group runs the same
+// number of steps and no index arithmetic beyond a compare is needed; a middle row (odd number of
+// rows) forms a unit of its own. DIST(xi, yj, g) = DistanceFromPoint of the store, valid in lane 0
+// of the group.
+template <bool ALLSTAGED, class Dist>
+__device__ __forceinline__ void prune_fill_kill(const StoreView& s, PruneShared& sh, const unsigned char* rows, int staged,
+                                                float alpha, Dist&& dist) {
+  constexpr int KW = PruneShared::MATRIX_MAX / 32;
   const int n = sh.n;
-  if (n > PruneShared::MATRIX_MAX) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane & 7;
+  const int grp = threadIdx.x >> 3;
+  const int nrows = n - 1;          // rows 0 .. n-2 have at least one column
+  const int P = nrows / 2;          // mirrored pairs
+  const int U = P + (nrows & 1);    // + the middle row
+  for (int u0 = 0; u0 < U; u0 += PRUNE_GROUPS) {
+    const int u = u0 + grp;
+    const bool has = u < U;
+    const int ra = has ? u : 0;                      // first row of the unit
+    const int la = has ? n - 1 - ra : 0;             // its columns
+    const int rb = n - 2 - u;                        // mirrored row (none for the middle unit)
+    const int lb = (has && u < P) ? u + 1 : 0;
+    for (int step = 0; step < n; ++step) {           // la + lb <= n
+      const bool first = step < la;
+      const bool act = first || step - la < lb;
+      if (!__any_sync(SDB_FULL, act)) continue;      // warp-uniform
+      const int i = act ? (first ? ra : rb) : 0;
+      const int j = act ? (first ? ra + 1 + step : rb + 1 + (step - la)) : 1;
+      const unsigned char* xi = (ALLSTAGED || i < staged) ? rows + uint32_t(i) * s.row_bytes : global_row(s, sh.sid[i]);
+      const unsigned char* yj = (ALLSTAGED || j < staged) ? rows + uint32_t(j) * s.row_bytes : global_row(s, sh.sid[j]);
+      const float d = dist(xi, yj, g);
+      if (act && g == 0 && __fmul_rn(alpha, d) < sh.sdist[j]) atomicOr(&sh.kill[i * KW + (j >> 5)], 1u << (j & 31));  // search.go:132
+    }
+  }
+}
+
+__device__ inline void robust_prune_cta(const StoreView& s, PruneShared& sh, const unsigned char* rows, int staged,
+                                        uint32_t node, int R, float alpha, int matrix_max = PruneShared::MATRIX_MAX) {
+  const int n = sh.n;
+  if (n > matrix_max || n > PruneShared::MATRIX_MAX || sh.kill == nullptr) {
     robust_prune_cta_seq(s, sh, rows, staged, node, R, alpha);
     return;
   }
   constexpr int KW = PruneShared::MATRIX_MAX / 32;
   const int lane = threadIdx.x & 31;
-  const int g = lane & 7;
-  const int grp = threadIdx.x >> 3;
   for (int t = threadIdx.x; t < n * KW; t += blockDim.x) sh.kill[t] = 0;
   __syncthreads();
-  // all pairs i < j, flattened so that every group always has a pair: step t covers the pair of
-  // rank t in row-major order of the strict upper triangle
-  const int total = n * (n - 1) / 2;
-  for (int t0 = 0; t0 < total; t0 += PRUNE_GROUPS) {
-    const int t = t0 + grp;
-    const bool act = t < total;
-    // row i of the triangle starts at off(i) = i*(2n-i-1)/2: invert with a float estimate, fix up
-    int i = 0, j = 1;
-    if (act) {
-      const float fn = float(2 * n - 1);
-      i = int((fn - sqrtf(fn * fn - 8.0f * float(t))) * 0.5f);
-      if (i < 0) i = 0;
-      while (i > 0 && i * (2 * n - i - 1) / 2 > t) --i;
-      while ((i + 1) * (2 * n - i - 2) / 2 <= t) ++i;
-      j = i + 1 + (t - i * (2 * n - i - 1) / 2);
-    }
-    const unsigned char* xi = i < staged ? rows + size_t(i) * s.row_bytes : global_row(s, sh.sid[i]);
-    const unsigned char* yj = j < staged ? rows + size_t(j) * s.row_bytes : global_row(s, sh.sid[j]);
-    const float d = row_dist(s, xi, yj, g);
-    if (act && g == 0 && __fmul_rn(alpha, d) < sh.sdist[j]) atomicOr(&sh.kill[i * KW + (j >> 5)], 1u << (j & 31));  // search.go:132
+  // the store's DistanceFromPoint, resolved once per prune rather than per pair. Fast path: f32 rows
+  // of 32*TRIPS floats, every candidate staged in shared memory (the back-edge prune of a dim-128
+  // store): compile-time trip count, shared-memory loads only.
+  const bool all_staged = s.mode == 0 && staged >= n && (s.dim & 31u) == 0;
+  const int trips = int(s.dim >> 5);
+#define SDB_PRUNE_FAST(M, T)                                                                                     \
+  prune_fill_kill<true>(s, sh, rows, staged, alpha, [&](const unsigned char* x, const unsigned char* y, int g) { \
+    return smem_float_dist<M, T>(reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(y), g);      \
+  })
+  if (all_staged && s.metric == METRIC_EUCLIDEAN && trips == 4) {
+    SDB_PRUNE_FAST(METRIC_EUCLIDEAN, 4);
+  } else if (all_staged && s.metric == METRIC_EUCLIDEAN && trips == 12) {
+    SDB_PRUNE_FAST(METRIC_EUCLIDEAN, 12);
+  } else if (all_staged && s.metric == METRIC_COSINE && trips == 12) {
+    SDB_PRUNE_FAST(METRIC_COSINE, 12);
+  } else if (all_staged && s.metric == METRIC_DOT && trips == 24) {
+    SDB_PRUNE_FAST(METRIC_DOT, 24);
+  } else
+#undef SDB_PRUNE_FAST
+  if (s.mode == 0 && s.metric == METRIC_EUCLIDEAN) {
+    prune_fill_kill<false>(s, sh, rows, staged, alpha, [&](const unsigned char* x, const unsigned char* y, int g) {
+      return group_float_dist<METRIC_EUCLIDEAN>(reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(y), s.dim, g);
+    });
+  } else if (s.mode == 0 && s.metric == METRIC_DOT) {
+    prune_fill_kill<false>(s, sh, rows, staged, alpha, [&](const unsigned char* x, const unsigned char* y, int g) {
+      return group_float_dist<METRIC_DOT>(reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(y), s.dim, g);
+    });
+  } else if (s.mode == 0 && s.metric == METRIC_COSINE) {
+    prune_fill_kill<false>(s, sh, rows, staged, alpha, [&](const unsigned char* x, const unsigned char* y, int g) {
+      return group_float_dist<METRIC_COSINE>(reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(y), s.dim, g);
+    });
+  } else {
+    prune_fill_kill<false>(s, sh, rows, staged, alpha,
+                    [&](const unsigned char* x, const unsigned char* y, int g) { return row_dist(s, x, y, g); });
   }
   __syncthreads();
-  if (threadIdx.x < 32) {
-    // the walk (search.go:113-137), warp-uniform: lane w < KW holds word w of the removed set
-    uint32_t removed = 0;
+  if (threadIdx.x == 0) {
+    // the walk (search.go:113-137) by one thread: the removed set lives in KW registers, a kill row
+    // is one 128-bit shared-memory load, fetched one candidate ahead of its use so that the chain
+    // removed -> test -> accept does not wait on it
+    static_assert(KW == 4, "the walk keeps the removed set in four registers");
+    uint32_t rem[KW] = {0u, 0u, 0u, 0u};
     int cnt = 0;
-    for (int i = 0; i < n; ++i) {
-      const uint32_t word = __shfl_sync(SDB_FULL, removed, i >> 5);
-      if (((word >> (i & 31)) & 1u) || sh.sid[i] == node) continue;
-      if (lane == 0) sh.edges[cnt] = sh.sid[i];
-      ++cnt;
-      if (cnt >= R) break;
-      if (lane < KW) removed |= sh.kill[i * KW + lane];
+    const uint4* krow = reinterpret_cast<const uint4*>(sh.kill);
+    uint4 nextk = n > 0 ? krow[0] : make_uint4(0, 0, 0, 0);
+    uint32_t nextid = n > 0 ? sh.sid[0] : 0u;
+    bool done = false;
+#pragma unroll
+    for (int w = 0; w < KW; ++w) {
+      for (int b = 0; b < 32 && !done; ++b) {
+        const int i = 32 * w + b;
+        if (i >= n) { done = true; break; }
+        const uint4 k = nextk;
+        const uint32_t id = nextid;
+        if (i + 1 < n) { nextk = krow[i + 1]; nextid = sh.sid[i + 1]; }
+        if (((rem[w] >> b) & 1u) || id == node) continue;
+        sh.edges[cnt] = id;
+        ++cnt;
+        if (cnt >= R) { done = true; break; }
+        rem[0] |= k.x; rem[1] |= k.y; rem[2] |= k.z; rem[3] |= k.w;
+      }
     }
-    if (lane == 0) *sh.cnt = cnt;
+    *sh.cnt = cnt;
   }
   __syncthreads();
 }
