@@ -423,6 +423,8 @@ def run_search(cx, name, n, B, steps, warmup, graph, headline):
     w = WORKLOADS[name]
     lib = _capi.lib()
     rank, world, dev = cx.rank, cx.world, cx.dev
+    replicated = args.mode == "replicated"
+    data_rank = 0 if replicated else rank  # replicas hold the same points
     nq_recall = min(args.recall_queries, B)
     oix = None
     X = None
@@ -431,9 +433,9 @@ def run_search(cx, name, n, B, steps, warmup, graph, headline):
     t0 = time.time()
     if name == "c2":
         from semadb_b200 import synth
-        X, Q = c2_data(n, rank, B)
-        start = synth.start_vector(128, 99 + rank)
-        g, _ = new_index("c2", rank, cx.local_rank)
+        X, Q = c2_data(n, data_rank, B)
+        start = synth.start_vector(128, 99 + data_rank)
+        g, _ = new_index("c2", data_rank, cx.local_rank)
         ids = np.arange(2, n + 2, dtype=np.uint64)
         if graph == "oracle":
             # BASELINE.json config[1]: "searching the reference-built graph" — at every N, so that the
@@ -457,7 +459,12 @@ def run_search(cx, name, n, B, steps, warmup, graph, headline):
     log(f"[rank {rank}] {name}: setup {time.time() - t0:.1f}s (build {build_s:.1f}s)")
 
     d_q = torch.from_numpy(Q).to(dev)  # the broadcast query batch, resident on every rank
-    searcher = ShardedSearcher(g, rank, world, exchange=args.exchange)
+    if replicated:
+        from semadb_b200.sharded import ReplicatedSearcher
+        searcher = ReplicatedSearcher(g, rank, world)
+        searcher.exchange = "nccl"
+    else:
+        searcher = ShardedSearcher(g, rank, world, exchange=args.exchange)
     stream = torch.cuda.current_stream()
     launches = [0]
     result = [None]
@@ -516,6 +523,13 @@ def run_search(cx, name, n, B, steps, warmup, graph, headline):
         # fans requests out to shards, cluster/actions.go:316-351), runs the sharded search (K1 with
         # the fused peer gather, barrier, K6) and receives the merged lists. The buffers are
         # page-locked: the kernels read the queries in place (mapped host memory).
+        if replicated:
+            r_ids, r_d, r_c = searcher.search_batch_device(h_q.to(dev, non_blocking=True), K, L)
+            h_ids.copy_(r_ids, non_blocking=True)
+            h_d.copy_(r_d, non_blocking=True)
+            h_c.copy_(r_c, non_blocking=True)
+            torch.cuda.synchronize()
+            return
         searcher.search_batch_pinned(h_q, K, L, h_ids, h_d, h_c, dev)
 
     for _ in range(2):
@@ -536,9 +550,12 @@ def run_search(cx, name, n, B, steps, warmup, graph, headline):
         t_ids, t_d = truth_float  # exact fp32 -dot over the raw vectors (what a PQ search approximates)
     else:
         t_ids, t_d, _ = g.flat_search_batch(Q[:nq_recall], K)  # exact ground truth on the GPU (K5)
-    mt_ids, mt_d = merged_truth(cx, t_ids, t_d)
+    if replicated:
+        mt_ids, mt_d = t_ids.astype(np.int64), t_d
+    else:
+        mt_ids, mt_d = merged_truth(cx, t_ids, t_d)
     got_ids, got_d, got_c = m_ids.cpu().numpy()[:nq_recall], m_d.cpu().numpy()[:nq_recall], m_c.cpu().numpy()[:nq_recall]
-    if world == 1:
+    if world == 1 and not replicated:
         from semadb_b200.sharded import SHARD_SHIFT
         got_ids = got_ids + (rank << SHARD_SHIFT)
     strict, tie = recall_of(got_ids, got_d, got_c, mt_ids, mt_d)
@@ -549,7 +566,12 @@ def run_search(cx, name, n, B, steps, warmup, graph, headline):
         out["recall_at_10_vs_exhaustive_adc"], out["recall_at_10_vs_exhaustive_adc_tie_aware"] = recall_of(
             got_ids, got_d, got_c, ma_ids, ma_d)
     parity_merged = None
-    if world > 1 and searcher.exchange != "nccl":
+    if replicated:
+        # every rank's concatenated lists must be what one GPU returns for the whole batch
+        same = bool((k_ids == m_ids).all().item() and (k_c == m_c).all().item() and
+                    k_d.cpu().numpy().tobytes() == m_d.cpu().numpy().tobytes())
+        parity_merged = {"replicated_lists_equal_single_gpu_search_on_every_rank": bool(cx.min_over_ranks(1.0 if same else 0.0) == 1.0)}
+    if world > 1 and not replicated and searcher.exchange != "nccl":
         # the fused exchange must give exactly what the NCCL all-gather + K6 path gives (actions.go:357-376)
         ref_s = ShardedSearcher(g, rank, world, exchange="nccl")
         n_ids, n_d, n_c = ref_s.search_batch_device(d_q, K, L)
@@ -575,16 +597,17 @@ def run_search(cx, name, n, B, steps, warmup, graph, headline):
 
     ms_step = ms_total / steps
     bytes_q = float(ndist.mean()) * w["row_bytes"] + float(hops.mean()) * R * 4
-    achieved = bytes_q * B / (kern_ms * 1e-3) / 1e9
+    launch_queries = -(-B // world) if replicated else B  # queries one launch of the kernel processes
+    achieved = bytes_q * launch_queries / (kern_ms * 1e-3) / 1e9
     peak, peak_kind = measured_peaks()
     out.update({
         "name": name, "g": g, "oix": oix, "X": X, "Q": Q, "start": start, "graph": graph,
-        "ms_step": ms_step, "value": world * B / (ms_step * 1e-3), "user_qps": B / (ms_step * 1e-3),
-        "kern_ms": kern_ms, "e2e_s": e2e_s, "e2e_value": world * B / e2e_s, "n_launch": n_launch,
+        "ms_step": ms_step, "value": (1 if replicated else world) * B / (ms_step * 1e-3), "user_qps": B / (ms_step * 1e-3),
+        "kern_ms": kern_ms, "e2e_s": e2e_s, "e2e_value": (1 if replicated else world) * B / e2e_s, "n_launch": n_launch,
         "mean_hops": float(hops.mean()), "mean_ndist": float(ndist.mean()), "bytes_q": bytes_q,
         "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "clocks": clocks, "build_s": build_s, "fit_s": fit_s,
         "parity": parity, "parity_merged": parity_merged, "oracle_recall": oracle_recall, "k_ids": k_ids, "k_d": k_d,
-        "exchange": searcher.exchange, "searcher": searcher,
+        "exchange": searcher.exchange, "searcher": searcher, "launch_queries": launch_queries,
     })
     return out
 
@@ -664,6 +687,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5b", "c5a"])
     ap.add_argument("--extra", default="auto", help="auto | none | comma list of c3,c4,c5b,c5a")
+    ap.add_argument("--mode", default="sharded", choices=["sharded", "replicated"],
+                    help="sharded: one shard per GPU, every query visits every shard (weak scaling, the reference's "
+                         "cluster semantics); replicated: the whole index on every GPU, the batch split N ways (strong scaling)")
     ap.add_argument("--points", "--n", dest="n", type=int, default=0,
                     help="points per GPU shard of the headline workload (0 = the config's)")
     ap.add_argument("--extra-n", default="", help="name=points,... overrides for the extra workloads (tests)")
@@ -705,6 +731,14 @@ def main():
         return
 
     name = args.workload
+    if args.mode == "replicated":
+        if name != "c2":
+            raise SystemExit("--mode replicated is measured on c2")
+        # every replica must hold the same graph: the batched GPU build is deterministic, the oracle's
+        # concurrent workers are not
+        args.graph = "gpu"
+        if args.extra == "auto":
+            args.extra = "none"
     n = args.n or WORKLOADS[name]["n"]
     h = run_search(cx, name, n, B, args.steps, max(3, args.warmup), args.graph, headline=True)
     h["n"] = n
@@ -782,7 +816,11 @@ def main():
     if rank == 0:
         w = WORKLOADS[name]
         cfg = workload_config(name, n, B, world, h["graph"])
-        if world > 1:
+        if args.mode == "replicated":
+            cfg.update(parallelism=f"replicated x{world}: the whole {n}-point index on every GPU, the batch split {world} ways, "
+                                   f"slices concatenated by one NCCL all-gather per result tensor",
+                       parity_merged=h["parity_merged"])
+        elif world > 1:
             cfg.update(exchange="fused peer stores over NVLink + flag barrier (sdb_search_batch_gather_device)"
                        if h["exchange"] != "nccl" else "NCCL all-gather per result tensor",
                        parity_merged=h["parity_merged"])
@@ -798,12 +836,13 @@ def main():
         out = {
             "metric": "vamana_search_qps", "value": h["value"], "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": h["ms_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64" if w["integer"] else "f32",
+            "scaling": "strong" if args.mode == "replicated" else "weak", "vs_baseline": None,
+            "dtype": "u64" if w["integer"] else "f32",
             "data": "synthetic" if name == "c2" else "synthetic (device-generated)", "config": cfg,
             "roofline": {"bound": "hbm", "achieved": h["achieved"], "peak": h["peak"], "unit": "GB/s",
                          "frac": h["achieved"] / h["peak"],
                          "traffic": measured_traffic() if (name == "c2" and n == 1_000_000 and B == 10_000) else None,
-                         "algorithmic_bytes_per_launch": h["bytes_q"] * B, "peak_kind": h["peak_kind"],
+                         "algorithmic_bytes_per_launch": h["bytes_q"] * h["launch_queries"], "peak_kind": h["peak_kind"],
                          "kernel": "beam_search_kernel", "kernel_ms": h["kern_ms"],
                          "kernel_ms_how": "CUDA events around the kernel inside the timed loop, mean over its steps, max over ranks"},
             "cpu_baseline": cpu,

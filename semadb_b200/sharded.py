@@ -244,3 +244,51 @@ class ShardedSearcher:
                                                       g_d.data_ptr(), g_c.data_ptr(), m_ids.data_ptr(),
                                                       m_d.data_ptr(), m_c.data_ptr(), stream))
         return m_ids, m_d, m_c
+
+
+def replica_slice(B: int, rank: int, world: int):
+    """Batch positions [lo, hi) served by replica `rank`: contiguous, sizes differing by at most one."""
+    base, rem = divmod(B, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class ReplicatedSearcher:
+    """Replicated mode: every GPU holds the WHOLE index and serves a contiguous
+    slice of the query batch; the slices are concatenated with one all-gather per result tensor.
+    Results are those of a single-GPU search — same graph, same queries — so user-visible QPS grows
+    with the number of GPUs (strong scaling) for collections that fit one GPU. The reference's
+    counterpart is several replicas of a shard behind its RPC layer, each serving whole requests
+    (shard/cache/manager.go:151-182 serves concurrent readers of one shard)."""
+
+    def __init__(self, index, rank: Optional[int] = None, world: Optional[int] = None, group=None):
+        import torch.distributed as dist
+        self.index, self.group = index, group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self._bufs = None
+
+    def search_batch_device(self, d_queries, k: int, search_size: int):
+        """d_queries [B, dim] identical on every rank; returns (ids [B,k], dists [B,k], counts [B]) on every rank."""
+        import torch
+        import torch.distributed as dist
+        B = int(d_queries.shape[0])
+        dev = d_queries.device
+        per = (B + self.world - 1) // self.world  # padded slice so that the gather is regular
+        if self._bufs is None or self._bufs[0].shape != (per, k):
+            self._bufs = (torch.zeros((per, k), dtype=torch.int64, device=dev), torch.zeros((per, k), dtype=torch.float32, device=dev),
+                          torch.zeros((per,), dtype=torch.int32, device=dev))
+        l_ids, l_d, l_c = self._bufs
+        lo, hi = replica_slice(B, self.rank, self.world)
+        if hi > lo:
+            self.index.search_batch_device(d_queries[lo:hi], k, search_size, l_ids, l_d, l_c,
+                                           torch.cuda.current_stream(dev).cuda_stream if d_queries.is_cuda else 0)
+        if self.world == 1:
+            return l_ids[:B], l_d[:B], l_c[:B]
+        outs = []
+        for t in (l_ids, l_d, l_c):
+            g = torch.empty((self.world * per,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+            dist.all_gather_into_tensor(g, t, group=self.group)
+            outs.append(g.view((self.world, per) + tuple(t.shape[1:])))
+        sizes = [replica_slice(B, r, self.world) for r in range(self.world)]
+        return tuple(torch.cat([o[r, :hi_ - lo_] for r, (lo_, hi_) in enumerate(sizes)]) for o in outs)

@@ -28,3 +28,16 @@ def test_host_index_on_gpu():
     r = subprocess.run([str(BIN), "gpu"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr + r.stdout
     assert "host_test gpu: ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_single_process_two_gpu_exchange_through_the_c_abi():
+    """One process, two GPUs, cudaDeviceEnablePeerAccess, C ABI only (tests/cpp/multigpu_test.cpp):
+    the fused exchange + barrier + merge equals the host-side merge of the per-shard results.
+    Skips itself (exit 0, 'SKIP') on a single-GPU box."""
+    subprocess.run(["make", "-C", str(ROOT / "tests" / "cpp"), "multigpu_test"], check=True, capture_output=True)
+    r = subprocess.run([str(ROOT / "tests" / "cpp" / "multigpu_test")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout
+    if "SKIP" in r.stdout:
+        pytest.skip(r.stdout.strip())
+    assert "multigpu_test: ok" in r.stdout

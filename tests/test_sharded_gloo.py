@@ -74,3 +74,40 @@ def test_shard_limit_matches_reference_formula():
         for s in (1, 2, 4, 8, 16):
             assert sharded.shard_limit(limit, s) == O.shard_limit(limit, s)
     assert sharded.shard_limit(10, 8) == 10 and sharded.shard_limit(100, 5) == 38
+
+
+class _FakeIndex:
+    """Stands in for the device index on CPU: 'searches' by writing a function of the query."""
+
+    def search_batch_device(self, q, k, L, ids, d, c, stream=0):
+        n = q.shape[0]
+        ids[:n] = (q[:, :1] * 1000).long() + torch.arange(k)[None, :]
+        d[:n] = q[:, :1] + torch.arange(k, dtype=torch.float32)[None, :]
+        c[:n] = k
+
+
+def _replica_worker(rank, world, port, B, k, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    q = torch.arange(B, dtype=torch.float32)[:, None].repeat(1, 4)
+    s = sharded.ReplicatedSearcher(_FakeIndex(), rank, world)
+    ids, d, c = s.search_batch_device(q, k, 75)
+    np.savez(os.path.join(out_dir, f"rep{rank}.npz"), ids=ids.numpy(), d=d.numpy(), c=c.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [64, 7, 1])
+def test_replicated_mode_world2_concatenates_slices_in_batch_order(tmp_path, B):
+    """Replicated mode: each rank serves its contiguous slice, every rank ends with the full batch
+    in order — including ragged (7) and smaller-than-world (1) batches."""
+    world, k = 2, 10
+    mp.spawn(_replica_worker, args=(world, _free_port(), B, k, str(tmp_path)), nprocs=world, join=True)
+    want_ids = (np.arange(B)[:, None] * 1000 + np.arange(k)[None, :]).astype(np.int64)
+    for r in range(world):
+        z = np.load(tmp_path / f"rep{r}.npz")
+        assert z["ids"].shape == (B, k) and (z["ids"] == want_ids).all()
+        assert (z["d"][:, 0] == np.arange(B)).all() and (z["c"] == k).all()
+    lo, hi = sharded.replica_slice(7, 0, 2)
+    assert (lo, hi) == (0, 4) and sharded.replica_slice(7, 1, 2) == (4, 7) and sharded.replica_slice(1, 1, 2) == (1, 1)
