@@ -487,11 +487,15 @@ def run_search(cx, name, n, B, steps, warmup, graph, headline):
     g.search_profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     cx.barrier()
+    if os.environ.get("SDB_PROFILE"):  # ncu --profile-from-start off: capture the timed searches only
+        torch.cuda.profiler.start()
     e0.record(stream)
     for _ in range(steps):
         step()
     e1.record(stream)
     cx.barrier()
+    if os.environ.get("SDB_PROFILE"):
+        torch.cuda.profiler.stop()
     ms_total = e0.elapsed_time(e1)
     kern = g.search_profile_read()
     g.search_profile(False)
@@ -825,7 +829,8 @@ def main():
                        if h["exchange"] != "nccl" else "NCCL all-gather per result tensor",
                        parity_merged=h["parity_merged"])
         cfg.update(user_qps=h["user_qps"], recall_at_10=h["recall_at_10"],
-                   recall_scope="merged top-k of all shards vs exact top-k of the union" if world > 1 else "single shard vs exact flat scan",
+                   recall_scope=("merged top-k of all shards vs exact top-k of the union"
+                                 if world > 1 and args.mode != "replicated" else "single shard vs exact flat scan"),
                    mean_hops=h["mean_hops"], mean_ndist=h["mean_ndist"], bytes_per_query=h["bytes_q"],
                    parity=h["parity"], host_cores=os.cpu_count(), setup_build_s=h["build_s"])
         if w["integer"]:
