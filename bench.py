@@ -63,9 +63,19 @@ WORKLOADS = {
     "c4": dict(dim=768, metric="dot", n=1_250_000, row_bytes=96, data_seed=8, query_seed=9, integer=False,
                desc="C4: {n}x768 (latent-16, L2-normalised) dot-product shard per GPU, product quantizer M=96 K=256 "
                     "trained on the first 10k points, ADC table search"),
+    # the same points under the cosine metric (PQ then works on squared L2, product.go:52-61): for
+    # L2-normalised vectors the ranking is the dot product's, but distances are positive, so alpha scales
+    # them the way robustPrune expects (search.go:132) — with "dot" the distances are negative and the
+    # reference's prune keeps ~9 edges per node (both implementations alike)
+    "c4cos": dict(dim=768, metric="cosine", n=1_250_000, row_bytes=96, data_seed=8, query_seed=9, integer=False,
+                  desc="C4 (cosine variant): {n}x768 (latent-16, L2-normalised) cosine shard per GPU, product quantizer M=96 "
+                       "K=256 trained on the first 10k points, ADC table search"),
     "c5b": dict(dim=1024, metric="hamming", n=6_250_000, row_bytes=128, data_seed=7, query_seed=10, integer=True,
                 desc="C5b: {n}x1024-bit binary-quantized (sign bits of a latent-16 embedding) hamming Vamana shard per GPU"),
 }
+
+
+PQ_WORKLOADS = ("c4", "c4cos")
 
 
 def log(*a):
@@ -298,7 +308,7 @@ def new_index(name, rank, local_rank):
     from semadb_b200 import synth
     from semadb_b200.vamana import (IndexVamana, IndexVectorVamanaParameters, ProductQuantizerParameters, Quantizer)
     w = WORKLOADS[name]
-    q = Quantizer("product", product=ProductQuantizerParameters(256, 96, 10000)) if name == "c4" else None
+    q = Quantizer("product", product=ProductQuantizerParameters(256, 96, 10000)) if name in PQ_WORKLOADS else None
     start = synth.start_vector(w["dim"], 99 + rank)
     g = IndexVamana(name, IndexVectorVamanaParameters(w["dim"], w["metric"], L, R, ALPHA, q), device=local_rank,
                     start_vector=start)
@@ -315,14 +325,14 @@ def build_device_generated(cx, name, n, Qr):
     t_ins = 0.0
     fit_s = None
     truth = None
-    if name == "c4":  # exact -dot top-k of the recall queries over this shard, accumulated chunk by chunk (fp32)
+    if name in PQ_WORKLOADS:  # exact -dot top-k of the recall queries over this shard, accumulated chunk by chunk (fp32)
         torch.backends.cuda.matmul.allow_tf32 = False
         d_qr = torch.from_numpy(Qr).to(cx.dev)
         best_d = torch.full((len(Qr), K), float("inf"), device=cx.dev)
         best_i = torch.zeros((len(Qr), K), dtype=torch.int64, device=cx.dev)
     for s, x in device_chunks(name, n, cx.rank, cx.dev):
         ids = np.arange(2 + s, 2 + s + len(x), dtype=np.uint64)
-        if name == "c4":
+        if name in PQ_WORKLOADS:
             sc = -(d_qr @ x.T)
             cd, ci = torch.topk(sc, K, dim=1, largest=False)
             alld = torch.cat([best_d, cd], 1)
@@ -331,7 +341,7 @@ def build_device_generated(cx, name, n, Qr):
             best_d, best_i = torch.gather(alld, 1, o), torch.gather(alli, 1, o)
         torch.cuda.synchronize()
         t = time.time()
-        if name == "c4" and fit_s is None:
+        if name in PQ_WORKLOADS and fit_s is None:
             g.insert_batch_device(ids[:10000], x[:10000].contiguous())
             t1 = time.time()
             g.fit(0)
@@ -341,7 +351,7 @@ def build_device_generated(cx, name, n, Qr):
             g.insert_batch_device(ids, x)
         t_ins += time.time() - t
         del x
-    if name == "c4":
+    if name in PQ_WORKLOADS:
         truth = (best_i.cpu().numpy().astype(np.uint64), best_d.cpu().numpy())
     return g, start, t_ins, fit_s, truth
 
@@ -382,7 +392,7 @@ def oracle_probe(cx, name, g, start, n, Q, local_ids, local_d, oix=None):
     nq = len(Q)
     t = time.time()
     if oix is None:
-        if name == "c4":
+        if name in PQ_WORKLOADS:
             oix = O.OracleIndex(w["dim"], w["metric"], L, R, ALPHA, quantizer="product", pq_m=96, pq_k=256, pq_trigger=10000)
             fc, cd = g.get_pq()
             oix.set_pq(fc, cd, reencode=False)
@@ -398,7 +408,7 @@ def oracle_probe(cx, name, g, start, n, Q, local_ids, local_d, oix=None):
             blk = adj[1 + s:1 + s + len(dg)]
             blk[m] = e[m].astype(np.uint32)
             deg[1 + s:1 + s + len(dg)] = dg
-        if name in ("c5b", "c4"):
+        if name == "c5b" or name in PQ_WORKLOADS:
             for s in range(0, len(ids), step):  # codes only, like hydrating n<id>q keys
                 oix.set_codes(ids[s:s + step].astype(np.uint32), g.get_codes(ids[s:s + step]))
         else:
@@ -564,7 +574,7 @@ def run_search(cx, name, n, B, steps, warmup, graph, headline):
         got_ids = got_ids + (rank << SHARD_SHIFT)
     strict, tie = recall_of(got_ids, got_d, got_c, mt_ids, mt_d)
     out = {"recall_at_10": strict, "recall_at_10_tie_aware": tie}
-    if name == "c4":  # how much of the loss is the quantizer's: recall against the exhaustive ADC ranking
+    if name in PQ_WORKLOADS:  # how much of the loss is the quantizer's: recall against the exhaustive ADC ranking
         a_ids, a_d, _ = g.flat_search_batch(Q[:nq_recall], K)
         ma_ids, ma_d = merged_truth(cx, a_ids, a_d)
         out["recall_at_10_vs_exhaustive_adc"], out["recall_at_10_vs_exhaustive_adc_tie_aware"] = recall_of(
@@ -591,7 +601,7 @@ def run_search(cx, name, n, B, steps, warmup, graph, headline):
         npq = B if (name == "c2" and world == 1 and graph == "oracle") else min(args.probe_queries, B)
         try:
             parity, oix, ref = oracle_probe(cx, name, g, start, n, Q[:npq], k_ids.cpu().numpy(), k_d.cpu().numpy(), oix)
-            if name == "c4" and world == 1:
+            if name in PQ_WORKLOADS and world == 1:
                 nn = min(npq, nq_recall)
                 oracle_recall = recall_of(ref["ids"][:nn].astype(np.int64), ref["dists"][:nn], ref["counts"][:nn],
                                           mt_ids[:nn], mt_d[:nn])[0]
@@ -622,7 +632,8 @@ def extra_block(r, world, B):
     d = {"workload": w["desc"].format(n=r["n"]) + f", {B}-query batch, k={K}, GPU-built graph (K8)",
          "shard_searches_per_s": r["value"], "user_qps": r["user_qps"], "ms_per_step": r["ms_step"],
          "e2e_shard_searches_per_s": r["e2e_value"], "recall_at_10_merged": r["recall_at_10"],
-         "recall_at_10_merged_tie_aware": r["recall_at_10_tie_aware"], "mean_hops": r["mean_hops"],
+         "recall_at_10_merged_tie_aware": r["recall_at_10_tie_aware"] if w["integer"] or r["name"] == "c3" else None,
+         "mean_hops": r["mean_hops"],
          "mean_ndist": r["mean_ndist"], "bytes_per_query": r["bytes_q"],
          "roofline": {"bound": "hbm", "achieved": r["achieved"], "peak": r["peak"], "unit": "GB/s",
                       "frac": r["achieved"] / r["peak"], "kernel_ms": r["kern_ms"], "per": "GPU"},
@@ -689,7 +700,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5b", "c5a"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c4cos", "c5b", "c5a"])
     ap.add_argument("--extra", default="auto", help="auto | none | comma list of c3,c4,c5b,c5a")
     ap.add_argument("--mode", default="sharded", choices=["sharded", "replicated"],
                     help="sharded: one shard per GPU, every query visits every shard (weak scaling, the reference's "
