@@ -949,6 +949,145 @@ __global__ void seed_cand_kernel(const uint64_t* prev_ids, const uint32_t* prev_
   cand_cnt[q] = c;
 }
 
+// Exact re-score, one WARP per query (four queries per CTA, no block-wide barrier): the candidates'
+// rows are gathered 16 at a time (an 8-lane group per row, all 16 row loads of a lane in flight),
+// scored with the reference's summation order, and offered to a k-slot list sorted by (distance asc,
+// id asc) that lives in shared memory (k * 8 bytes per query instead of CAND_CAP * 8): a candidate
+// that does not beat the current k-th is dropped by the lane that holds it, so the warp-wide
+// insertion runs ~k ln(n/k) times per query. implicit_n > 0: the candidates are the implicit_n
+// points first_id, first_id+1, ... (level 0: the exact top-k of the first points, no list in memory).
+constexpr int RW_WARPS = 4;
+constexpr int RW_SLOTS = 96;  // >= max k (75), lanes cover slots lane + 32 j
+template <int METRIC>
+__global__ void __launch_bounds__(32 * RW_WARPS) rescore_warp_kernel(
+    const float* vec, uint32_t vec_pitch, uint32_t dim, const float* queries, uint32_t B, const uint32_t* cand,
+    const uint32_t* cand_cnt, uint32_t k, uint64_t* out_ids, float* out_d, uint32_t* out_cnt, uint32_t* overflow_list,
+    uint32_t* overflow_cnt, uint32_t* overflow_flag, int last_level, uint32_t first_id, uint32_t implicit_n,
+    const uint8_t* exists) {
+  __shared__ float s_kd[RW_WARPS][RW_SLOTS];
+  __shared__ uint32_t s_ki[RW_WARPS][RW_SLOTS];
+  extern __shared__ __align__(16) float s_qall[];  // [RW_WARPS][dim rounded up to 4]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane & 7, grp = lane >> 3;
+  const uint32_t q = blockIdx.x * RW_WARPS + wid;
+  if (q >= B) return;
+  const uint32_t dpad = (dim + 3) & ~3u;
+  float* s_q = s_qall + size_t(wid) * dpad;
+  float* kd = s_kd[wid];
+  uint32_t* ki = s_ki[wid];
+  const uint32_t n = implicit_n ? implicit_n : cand_cnt[q];
+  if (!implicit_n && n > CAND_CAP) {
+    // Levels cover disjoint point ranges, so a list that overflowed at any level has lost
+    // candidates for good: the query goes to the exact scan after the last level (once: the
+    // per-query flag). Its outputs of this level stay as they were (the previous bound).
+    if (lane == 0) {
+      if (atomicExch(&overflow_flag[q], 1u) == 0u) overflow_list[atomicAdd(overflow_cnt, 1u)] = q;
+      if (last_level) out_cnt[q] = 0;
+    }
+    return;
+  }
+  for (uint32_t i = lane; i < dpad; i += 32) s_q[i] = i < dim ? queries[size_t(q) * dim + i] : 0.0f;
+  __syncwarp();
+  constexpr bool L2 = (METRIC == METRIC_EUCLIDEAN);
+  const int trips = dim >> 5;
+  uint32_t len = 0;
+  // offer (d, id), held by every lane, to the sorted list; warp-synchronous
+  auto insert = [&](float d, uint32_t id) {
+    uint32_t pos = 0;
+#pragma unroll
+    for (int j = 0; j < RW_SLOTS / 32; ++j) {
+      const uint32_t p = lane + 32 * j;
+      const bool before = p < len && (kd[p] < d || (kd[p] == d && ki[p] < id));
+      pos += __popc(__ballot_sync(SDB_FULL, before));
+    }
+    if (pos >= k) return;
+    const uint32_t last = len < k ? len : k - 1;  // elements [pos, last) move up by one
+    float mvd[RW_SLOTS / 32];
+    uint32_t mvi[RW_SLOTS / 32];
+#pragma unroll
+    for (int j = 0; j < RW_SLOTS / 32; ++j) {
+      const uint32_t p = lane + 32 * j;
+      if (p >= pos && p < last) { mvd[j] = kd[p]; mvi[j] = ki[p]; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < RW_SLOTS / 32; ++j) {
+      const uint32_t p = lane + 32 * j;
+      if (p >= pos && p < last) { kd[p + 1] = mvd[j]; ki[p + 1] = mvi[j]; }
+    }
+    if (lane == 0) { kd[pos] = d; ki[pos] = id; }
+    if (len < k) ++len;
+    __syncwarp();
+  };
+  // the lanes that hold a fresh (d, id) (lane 0 of each group) offer it if it can enter the list
+  auto offer = [&](float d, uint32_t id, bool have) {
+    bool want = have;
+    if (have && len == k) {
+      const float wd = kd[k - 1];
+      want = d < wd || (d == wd && id < ki[k - 1]);
+    }
+    uint32_t m = __ballot_sync(SDB_FULL, want);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      insert(__shfl_sync(SDB_FULL, d, src), __shfl_sync(SDB_FULL, id, src));
+    }
+  };
+  auto cand_id = [&](uint32_t c) -> uint32_t { return implicit_n ? first_id + c : cand[size_t(q) * CAND_CAP + c]; };
+  uint32_t c0 = 0;
+  if (trips <= 4) {
+    for (; c0 < n; c0 += 16) {
+      float4 y[4][4];
+      uint32_t pid[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t c = c0 + u * 4 + grp;
+        pid[u] = cand_id(c < n ? c : 0);
+        const float* row = vec + size_t(pid[u]) * vec_pitch + 4 * g;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) y[u][t] = t < trips ? ldg_f4_stream(row + 32 * t) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t c = c0 + u * 4 + grp;
+        const float* row = vec + size_t(pid[u]) * vec_pitch;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (t < trips) trip_accum<L2>(*reinterpret_cast<const float4*>(s_q + 32 * t + 4 * g), y[u][t], acc);
+        float tail = 0.0f;
+        if (g == 0)
+          for (uint32_t i = trips << 5; i < dim; ++i) tail = tail_accum<L2>(s_q[i], __ldg(row + i), tail);
+        const float r = metric_epilogue<METRIC>(group_reduce(acc, tail));
+        const bool have = g == 0 && c < n && (!implicit_n || exists[pid[u]]);
+        offer(r, pid[u], have);
+      }
+    }
+  }
+  for (; c0 < n; c0 += 4) {
+    const uint32_t c = c0 + grp;
+    const bool act = c < n;
+    const uint32_t pid = cand_id(act ? c : 0);
+    const float* row = vec + size_t(pid) * vec_pitch;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < trips; ++t) {
+      const float4 x = *reinterpret_cast<const float4*>(s_q + 32 * t + 4 * g);
+      const float4 yy = ldg_f4(row + 32 * t + 4 * g);
+      trip_accum<L2>(x, yy, acc);
+    }
+    float tail = 0.0f;
+    if (g == 0)
+      for (uint32_t i = trips << 5; i < dim; ++i) tail = tail_accum<L2>(s_q[i], __ldg(row + i), tail);
+    const float r = metric_epilogue<METRIC>(group_reduce(acc, tail));
+    offer(r, pid, g == 0 && act && (!implicit_n || exists[pid]));
+  }
+  __syncwarp();
+  for (uint32_t r = lane; r < k; r += 32) {
+    out_ids[size_t(q) * k + r] = r < len ? uint64_t(ki[r]) : 0;
+    out_d[size_t(q) * k + r] = r < len ? kd[r] : __int_as_float(0x7f800000);
+  }
+  if (lane == 0) out_cnt[q] = len;
+}
+
 // Exact re-score of one query's candidates + top-k by (distance asc, id asc). One CTA per query.
 template <int METRIC>
 __global__ void __launch_bounds__(128) rescore_kernel(const float* vec, uint32_t vec_pitch, uint32_t dim, const float* queries,
@@ -1095,6 +1234,21 @@ static uint32_t level0_points() {
   return LEVEL0;
 }
 
+// growth of the levels: intermediate levels multiply the covered prefix by ratio_mid, the last level
+// may cover up to ratio_last times the prefix before it (a level's re-score handles ~k * ratio
+// candidates per query; the intermediate re-scores only serve the next threshold, so they are kept
+// small). A/B: SDB_FLAT_RATIO="mid,last".
+static void level_ratios(uint32_t* mid, uint32_t* last) {
+  // measured on 10k x 1M x 128 (host buffers in and out): 32,32 4.64 ms; 16,32 4.83; 8,32 4.19; 8,64 4.25;
+  // 4,32 4.40; 8,16 4.13 ms
+  *mid = 8;
+  *last = 16;
+  if (const char* e = getenv("SDB_FLAT_RATIO")) {
+    int a = 0, b = 0;
+    if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 2 && a <= 256 && b >= 2 && b <= 256) { *mid = uint32_t(a); *last = uint32_t(b); }
+  }
+}
+
 bool flat_tc_eligible(const sdb_index* ix, uint32_t k, bool filtered) {
   if (getenv("SDB_FLAT_EXACT")) return false;
   if (filtered || ix->quant_active()) return false;
@@ -1148,8 +1302,35 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
     attr_set = true;
   }
   // ---- level 0: exact scan of the first LEVEL0 points bounds every query's k-th distance
-  if ((rc = launch_flat_exact(ix, B, d_queries, k, nullptr, ix->d_sample_ids.p, ix->d_sample_d.p, ix->d_sample_cnt.p, stream,
-                              first_id, first_id + level0_points())))
+  const bool warp_rescore = getenv("SDB_FLAT_RESCORE_CTA") == nullptr;
+  const size_t wsmem = size_t(RW_WARPS) * ((dim + 3) & ~3u) * sizeof(float);
+  auto rescore_warp = [&](uint64_t* o_ids, float* o_d, uint32_t* o_c, int last, uint32_t impl_first, uint32_t impl_n) {
+    const uint32_t grid = (B + RW_WARPS - 1) / RW_WARPS;
+    switch (ix->store_metric) {
+      case SDB_METRIC_EUCLIDEAN:
+        rescore_warp_kernel<METRIC_EUCLIDEAN><<<grid, 32 * RW_WARPS, wsmem, stream>>>(
+            ix->d_vec, ix->vec_pitch, dim, d_queries, B, ix->d_cand.p, d_cnt, k, o_ids, o_d, o_c, d_ovf_list, d_misc + 1, d_ovf_flag,
+            last, impl_first, impl_n, ix->d_exists);
+        break;
+      case SDB_METRIC_DOT:
+        rescore_warp_kernel<METRIC_DOT><<<grid, 32 * RW_WARPS, wsmem, stream>>>(
+            ix->d_vec, ix->vec_pitch, dim, d_queries, B, ix->d_cand.p, d_cnt, k, o_ids, o_d, o_c, d_ovf_list, d_misc + 1, d_ovf_flag,
+            last, impl_first, impl_n, ix->d_exists);
+        break;
+      default:
+        rescore_warp_kernel<METRIC_COSINE><<<grid, 32 * RW_WARPS, wsmem, stream>>>(
+            ix->d_vec, ix->vec_pitch, dim, d_queries, B, ix->d_cand.p, d_cnt, k, o_ids, o_d, o_c, d_ovf_list, d_misc + 1, d_ovf_flag,
+            last, impl_first, impl_n, ix->d_exists);
+        break;
+    }
+  };
+  if (warp_rescore) {
+    rescore_warp(ix->d_sample_ids.p, ix->d_sample_d.p, ix->d_sample_cnt.p, 0, first_id,
+                 std::min<uint32_t>(level0_points(), end_id - first_id));
+    ix->launches++;
+    SDB_CUDA(cudaGetLastError());
+  } else if ((rc = launch_flat_exact(ix, B, d_queries, k, nullptr, ix->d_sample_ids.p, ix->d_sample_d.p, ix->d_sample_cnt.p, stream,
+                                     first_id, first_id + level0_points())))
     return rc;
   // ---- levels 1..: tensor-core pass over a 32x larger prefix, thresholds from the level before
   const uint32_t npts = end_id - first_id;
@@ -1157,8 +1338,10 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
   const size_t qsmem = size_t((dim + 3) & ~3u) * sizeof(float);
   uint64_t covered = level0_points();
   uint32_t lvl_begin = first_id + uint32_t(covered);  // levels cover disjoint ranges [lvl_begin, lvl_end)
+  uint32_t ratio_mid, ratio_last;
+  level_ratios(&ratio_mid, &ratio_last);
   while (covered < npts) {
-    covered = std::min<uint64_t>(npts, covered * LEVEL_RATIO);
+    covered = covered * ratio_last >= npts ? npts : std::min<uint64_t>(npts, covered * ratio_mid);
     // whole 256-point tiles: what a level scans past its nominal end is not scanned again
     uint64_t span = (first_id + covered - lvl_begin + 255) / 256 * 256;
     const bool last = lvl_begin + span >= end_id;
@@ -1194,7 +1377,8 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
     uint64_t* o_ids = last ? d_out_ids : ix->d_sample_ids.p;
     float* o_d = last ? d_out_dists : ix->d_sample_d.p;
     uint32_t* o_c = last ? d_out_counts : ix->d_sample_cnt.p;
-    switch (ix->store_metric) {
+    if (warp_rescore) rescore_warp(o_ids, o_d, o_c, last ? 1 : 0, 0, 0);
+    else switch (ix->store_metric) {
       case SDB_METRIC_EUCLIDEAN:
         rescore_kernel<METRIC_EUCLIDEAN><<<B, 128, qsmem, stream>>>(ix->d_vec, ix->vec_pitch, dim, d_queries, ix->d_cand.p, d_cnt, k,
                                                                     o_ids, o_d, o_c, d_ovf_list, d_misc + 1, d_ovf_flag, last ? 1 : 0);

@@ -292,28 +292,31 @@ __device__ inline void robust_prune_cta(const StoreView& s, PruneShared& sh, con
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    // the walk (search.go:113-137) by one thread: the removed set lives in KW registers, a kill row
-    // is one 128-bit shared-memory load, fetched one candidate ahead of its use so that the chain
-    // removed -> test -> accept does not wait on it
+    // the walk (search.go:113-137) by one thread: the removed set lives in KW registers and the
+    // next candidate still alive is found with a find-first-set over ~removed, so the loop runs
+    // once per ACCEPTED candidate (~35 of 65); a kill row is one 128-bit shared-memory load
     static_assert(KW == 4, "the walk keeps the removed set in four registers");
     uint32_t rem[KW] = {0u, 0u, 0u, 0u};
     int cnt = 0;
     const uint4* krow = reinterpret_cast<const uint4*>(sh.kill);
-    uint4 nextk = n > 0 ? krow[0] : make_uint4(0, 0, 0, 0);
-    uint32_t nextid = n > 0 ? sh.sid[0] : 0u;
     bool done = false;
 #pragma unroll
     for (int w = 0; w < KW; ++w) {
-      for (int b = 0; b < 32 && !done; ++b) {
+      if (done || 32 * w >= n) break;
+      const uint32_t valid = n - 32 * w >= 32 ? 0xFFFFFFFFu : ((1u << (n - 32 * w)) - 1u);
+      uint32_t todo = valid;  // candidates of this word not yet looked at
+      while (true) {
+        const uint32_t avail = ~rem[w] & todo;
+        if (!avail) break;
+        const int b = __ffs(avail) - 1;
+        todo = b == 31 ? 0u : (todo & ~((2u << b) - 1u));
         const int i = 32 * w + b;
-        if (i >= n) { done = true; break; }
-        const uint4 k = nextk;
-        const uint32_t id = nextid;
-        if (i + 1 < n) { nextk = krow[i + 1]; nextid = sh.sid[i + 1]; }
-        if (((rem[w] >> b) & 1u) || id == node) continue;
+        const uint32_t id = sh.sid[i];
+        if (id == node) continue;
         sh.edges[cnt] = id;
         ++cnt;
         if (cnt >= R) { done = true; break; }
+        const uint4 k = krow[i];
         rem[0] |= k.x; rem[1] |= k.y; rem[2] |= k.z; rem[3] |= k.w;
       }
     }
