@@ -607,6 +607,25 @@ def run_search(cx, name, n, B, steps, warmup, graph, headline):
                                           mt_ids[:nn], mt_d[:nn])[0]
         except MemoryError as e:  # noqa: PERF203
             parity = {"skipped": f"host memory: {e}"}
+    # K7 beside the oracle: productQuantizer.Fit on the same first 10 000 points (product.go:175-236,
+    # kmeans.go:34-150) on the host cores, and the centroids / centroidDists it yields
+    fit_cpu = None
+    if name in PQ_WORKLOADS and rank == 0 and not args.no_probe:
+        from oracle import oraclelib as O
+        _, x0 = next(iter(device_chunks(name, n, rank, dev)))
+        x0 = x0[:10000].cpu().numpy()
+        of = O.OracleIndex(w["dim"], w["metric"], L, R, ALPHA, quantizer="product", pq_m=96, pq_k=256, pq_trigger=10000)
+        of.set_start(start)
+        of.set_vectors(np.arange(2, 2 + len(x0), dtype=np.uint32), x0)
+        t = time.time()
+        of.fit(0, True, O.hw_threads())
+        fit_cpu_s = time.time() - t
+        ofc, ocd = of.get_pq()
+        gfc, gcd = g.get_pq()
+        fit_cpu = {"oracle_fit_s": fit_cpu_s, "oracle_threads": O.hw_threads(), "gpu_fit_s": fit_s,
+                   "centroids_bit_identical": bool(ofc.tobytes() == gfc.tobytes()),
+                   "centroid_dists_bit_identical": bool(ocd.tobytes() == gcd.tobytes())}
+        del of
     cx.barrier()
 
     ms_step = ms_total / steps
@@ -621,6 +640,7 @@ def run_search(cx, name, n, B, steps, warmup, graph, headline):
         "mean_hops": float(hops.mean()), "mean_ndist": float(ndist.mean()), "bytes_q": bytes_q,
         "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "clocks": clocks, "build_s": build_s, "fit_s": fit_s,
         "parity": parity, "parity_merged": parity_merged, "oracle_recall": oracle_recall, "k_ids": k_ids, "k_d": k_d,
+        "pq_fit": fit_cpu,
         "exchange": searcher.exchange, "searcher": searcher, "launch_queries": launch_queries,
     })
     return out
@@ -643,7 +663,7 @@ def extra_block(r, world, B):
                                  "traffic is lower than that and the fraction of the measured copy peak can exceed 1")
     if w["integer"]:
         d["recall_note"] = "integer distances: tie-aware recall counts a result as a hit when its distance <= the k-th true distance"
-    for k_ in ("recall_at_10_vs_exhaustive_adc", "recall_at_10_vs_exhaustive_adc_tie_aware", "oracle_recall", "fit_s"):
+    for k_ in ("recall_at_10_vs_exhaustive_adc", "recall_at_10_vs_exhaustive_adc_tie_aware", "oracle_recall", "fit_s", "pq_fit"):
         if r.get(k_) is not None:
             d[k_] = r[k_]
     return d
@@ -846,7 +866,7 @@ def main():
                    parity=h["parity"], host_cores=os.cpu_count(), setup_build_s=h["build_s"])
         if w["integer"]:
             cfg["recall_at_10_tie_aware"] = h["recall_at_10_tie_aware"]
-        for k_ in ("recall_at_10_vs_exhaustive_adc", "oracle_recall", "fit_s"):
+        for k_ in ("recall_at_10_vs_exhaustive_adc", "oracle_recall", "fit_s", "pq_fit"):
             if h.get(k_) is not None:
                 cfg[k_] = h[k_]
         out = {

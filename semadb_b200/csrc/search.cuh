@@ -263,88 +263,91 @@ struct VisitedCompact {
 };
 
 // ---- exact visited set, compact form with a launch-time slot count ------------------------
-// Same quotienting idea as VisitedCompact with any slot count (multiple of 8), chosen per launch
-// (SearchArgs::vt_slots): 5888 slots (11.5 KB) keep a dim-128 query-warp at 12.9 KB of shared
-// memory, which leaves more of the unified array to L1 — where in-flight loads land — than
-// 8192 did; workloads that visit more nodes per query (more hops, saturated degrees) get a
-// bigger table instead of falling into the RETRY launch (search.cu adapts the size).
-// pi(id) = id*A mod 2^b as before; span = ceil(2^b / slots), home slot = pi / span, remainder
-// = pi % span, entry = 1 + remainder + disp*span (16 bits). disp <= dmax = (65535 - span) /
-// span: 382 at 1M rows and 5888 slots; beyond that (or above 87.5 % load) -> RETRY launch.
+// 16-bit entries in BUCKETS of four (one 64-bit shared-memory word): pi(id) = id*A mod 2^b is a
+// bijection on the b-bit id space; span = ceil(2^b / buckets), home bucket = pi / span, remainder
+// = pi % span, entry = 1 + remainder + disp*span (disp = bucket displacement, 0 = empty slot) —
+// quotienting makes a 16-bit entry identify the id exactly. One 64-bit load shows a bucket's four
+// entries, a SWAR compare finds the id or a free slot, one 64-bit CAS claims it: at the load
+// factors of a search (<= 50 % typically, 87.5 % at most) almost every id resolves in its home
+// bucket, where the linear-probe table of round 1 needed 4-6 vote-loop iterations per hop for the
+// longest of its 64 chains (31 % of the hamming kernel's instructions, profiles/r02_k2_*).
+// slots = 4 * buckets is chosen per launch (SearchArgs::vt_slots: 5888 keeps a dim-128 query-warp
+// at 12.9 KB of shared memory; search.cu steps it up for workloads that visit more nodes).
+// disp <= dmax = (65535 - span) / span; beyond that, above 87.5 % load, or when span does not fit
+// 16 bits (more than ~96 M rows at 5888 slots) the query goes to the RETRY launch (exact bitmap).
 struct VisitedCompactN {
   static __host__ __device__ constexpr size_t bytes(uint32_t slots) { return size_t(slots) * 2; }
-  unsigned short* t;
-  uint32_t nslots, mask, span, magic, used, dmax, lim;
-  bool failed;
+  unsigned long long* t;
+  uint32_t nbuckets, mask, span, magic, used, dmax, lim;
+  bool failed, unusable;
+  static constexpr unsigned long long ONES = 0x0001000100010001ull, HIGHS = 0x8000800080008000ull;
   __device__ __forceinline__ uint32_t limit() const { return lim; }
   __device__ __forceinline__ void init(unsigned char* base, uint32_t rows, uint32_t slots, uint32_t*, uint32_t) {
-    t = reinterpret_cast<unsigned short*>(base);
-    nslots = slots;
+    t = reinterpret_cast<unsigned long long*>(base);
+    nbuckets = slots / 4;
     uint32_t b = rows <= 2 ? 1 : 32 - __clz(rows - 1);
     if (b < 16) b = 16;
     mask = b >= 32 ? 0xFFFFFFFFu : ((1u << b) - 1);
     const uint64_t space = uint64_t(1) << b;
-    span = uint32_t((space + slots - 1) / slots);
+    span = uint32_t((space + nbuckets - 1) / nbuckets);
     magic = uint32_t((uint64_t(1) << 32) / span);
-    used = uint32_t((space + span - 1) / span);
-    dmax = span >= 32768 ? 0 : (65535u - span) / span;
+    used = uint32_t((space + span - 1) / span);  // buckets that can be a home
+    unusable = span > 65534u;
+    dmax = unusable ? 0 : (65535u - span) / span;
     if (dmax > 4096) dmax = 4096;
-    lim = used - used / 8;
+    lim = unusable ? 0 : used * 4 - used / 2;  // 87.5 % of the entries
   }
   __device__ __forceinline__ void clear(int lane) {
     uint4 z = make_uint4(0, 0, 0, 0);
     uint4* p = reinterpret_cast<uint4*>(t);
-    for (uint32_t i = lane; i < nslots * 2 / 16; i += 32) p[i] = z;
-    failed = false;
+    for (uint32_t i = lane; i < nbuckets / 2; i += 32) p[i] = z;
+    if ((nbuckets & 1u) && lane == 0) t[nbuckets - 1] = 0ull;
+    failed = unusable;
   }
-  __device__ __forceinline__ void home(uint32_t id, uint32_t& slot, uint32_t& code) const {
+  __device__ __forceinline__ void home(uint32_t id, uint32_t& bucket, uint32_t& code) const {
     const uint32_t v = (id * 0x9E3779B1u) & mask;
     uint32_t q = __umulhi(v, magic);
     uint32_t r = v - q * span;
     if (r >= span) { ++q; r -= span; }  // the estimate is short by at most one
-    slot = q;
+    bucket = q;
     code = 1 + r;
   }
+  // which 16-bit lane of w equals c (bit 15 of that lane set in the result), 0 if none
+  static __device__ __forceinline__ unsigned long long match16(unsigned long long w, uint32_t c) {
+    const unsigned long long x = w ^ (ONES * c);
+    return (x - ONES) & ~x & HIGHS;
+  }
+  // one probe step of one id: returns true when the id is resolved
+  __device__ __forceinline__ bool step(uint32_t& bucket, uint32_t& code, uint32_t& disp, bool& isnew, bool& spill) {
+    volatile unsigned long long* tw = t;
+    const unsigned long long w = tw[bucket];
+    if (match16(w, code)) return true;               // already visited
+    const unsigned long long z = match16(w, 0u);      // free slots of the bucket
+    if (z) {
+      const int sh = (__ffsll((long long)z) - 1) & ~15;  // bit offset of the first free 16-bit slot
+      const unsigned long long old = atomicCAS(const_cast<unsigned long long*>(tw) + bucket, w, w | ((unsigned long long)code << sh));
+      if (old == w) { isnew = true; return true; }
+      return false;                                    // the word changed under us: look again
+    }
+    bucket = bucket + 1 == used ? 0 : bucket + 1;     // bucket full of other ids
+    code += span;
+    if (++disp > dmax) { spill = true; return true; }
+    return false;
+  }
+  // Two ids per lane (adjacency slots lane and lane+32) probed in one vote-driven loop — a
+  // data-dependent `while` around the CAS makes ptxas emit WARPSYNC.COLLECTIVE trampolines for
+  // every later shuffle.
   __device__ __forceinline__ void test_and_set2(uint32_t i0, bool a0, uint32_t i1, bool a1, bool& n0, bool& n1, int) {
-    uint32_t slot0, slot1, c0, c1;
-    home(i0, slot0, c0);
-    home(i1, slot1, c1);
-    uint32_t disp0 = 0, disp1 = 0;
-    bool p0 = a0, p1 = a1, spill = false;
+    uint32_t b0, b1, c0, c1;
+    home(i0, b0, c0);
+    home(i1, b1, c1);
+    uint32_t d0 = 0, d1 = 0;
+    bool p0 = a0 && !unusable, p1 = a1 && !unusable, spill = false;
     n0 = false;
     n1 = false;
-    volatile uint32_t* tw = reinterpret_cast<volatile uint32_t*>(t);
     while (__any_sync(SDB_FULL, p0 || p1)) {
-      if (p0) {
-        const uint32_t sh = (slot0 & 1) * 16;
-        const uint32_t w = tw[slot0 >> 1];
-        const uint32_t half = (w >> sh) & 0xFFFFu;
-        if (half == 0) {
-          const uint32_t old = atomicCAS(const_cast<uint32_t*>(tw) + (slot0 >> 1), w, w | (c0 << sh));
-          if (old == w) { n0 = true; p0 = false; }
-        } else if (half == c0) {
-          p0 = false;
-        } else {
-          slot0 = slot0 + 1 == used ? 0 : slot0 + 1;
-          c0 += span;
-          if (++disp0 > dmax) { p0 = false; spill = true; }
-        }
-      }
-      if (p1) {
-        const uint32_t sh = (slot1 & 1) * 16;
-        const uint32_t w = tw[slot1 >> 1];
-        const uint32_t half = (w >> sh) & 0xFFFFu;
-        if (half == 0) {
-          const uint32_t old = atomicCAS(const_cast<uint32_t*>(tw) + (slot1 >> 1), w, w | (c1 << sh));
-          if (old == w) { n1 = true; p1 = false; }
-        } else if (half == c1) {
-          p1 = false;
-        } else {
-          slot1 = slot1 + 1 == used ? 0 : slot1 + 1;
-          c1 += span;
-          if (++disp1 > dmax) { p1 = false; spill = true; }
-        }
-      }
+      if (p0) p0 = !step(b0, c0, d0, n0, spill);
+      if (p1) p1 = !step(b1, c1, d1, n1, spill);
     }
     if (__any_sync(SDB_FULL, spill)) failed = true;
   }
@@ -354,16 +357,17 @@ struct VisitedCompactN {
     return n0;
   }
   // Read-only hint for the speculative row prefetch: false only if id is certainly in the set
-  // (three probes, no loop, no vote); "true" may be wrong, which costs one wasted prefetch.
+  // (home bucket and the next one, no loop, no vote); "true" may be wrong, which costs one wasted
+  // prefetch.
   __device__ __forceinline__ bool maybe_new(uint32_t id) const {
-    uint32_t slot, c;
-    home(id, slot, c);
+    uint32_t bucket, c;
+    home(id, bucket, c);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const uint32_t h = t[slot];
-      if (h == c) return false;
-      if (h == 0) return true;
-      slot = slot + 1 == used ? 0 : slot + 1;
+    for (int i = 0; i < 2; ++i) {
+      const unsigned long long w = t[bucket];
+      if (match16(w, c)) return false;
+      if (match16(w, 0u)) return true;
+      bucket = bucket + 1 == used ? 0 : bucket + 1;
       c += span;
     }
     return true;

@@ -69,7 +69,8 @@ int launch_variant(sdb_index* ix, const SearchArgs& a, cudaStream_t stream) {
   if (a.n_start_extra != 0)
     return launch_variant_x<KIND, METRIC, TRIPS, SETS, LEGACY, MERGE_MIN, VT, FILTER, RETRY, MINB, true>(ix, a, stream);
   // speculative row prefetch (small-row evaluators, unfiltered first pass); SDB_NO_PF=1 = A/B switch
-  constexpr bool CAN_PF = !FILTER && !RETRY && (KIND == EVAL_BITS || KIND == EVAL_ADC_SMEM || KIND == EVAL_ADC || KIND == EVAL_ADC_FLY);
+  // (PQ kernels: +1.6 %; bit rows: -1.6 %, the probes cost more than the L2 hits save — off there)
+  constexpr bool CAN_PF = !FILTER && !RETRY && (KIND == EVAL_ADC_SMEM || KIND == EVAL_ADC || KIND == EVAL_ADC_FLY);
   if (CAN_PF) {
     static const bool no_pf = getenv("SDB_NO_PF") != nullptr;
     if (!no_pf)
