@@ -119,9 +119,27 @@ __device__ __forceinline__ float row_dist(const StoreView& s, const unsigned cha
       u += __shfl_down_sync(SDB_FULL, u, o, 8);
     }
     r = bits_finish(s.metric, c, u);
-  } else if (g == 0) {
-    // SDC: sum_i centroidDists[i][cx[i]][cy[i]] sequential f32 (product.go:299-303)
-    for (uint32_t m = 0; m < s.pqM; ++m) r = __fadd_rn(r, __ldg(s.cdist + (size_t(m) * s.pqK + x[m]) * s.pqK + y[m]));
+  } else {
+    // SDC: sum_i centroidDists[i][cx[i]][cy[i]], added sequentially in f32 (product.go:299-303).
+    // The M table reads are independent: the group's 8 lanes fetch 32 of them at a time (4 each, all
+    // in flight together), then the terms are added in sub-vector order through shuffles — the same
+    // chain of additions, without M dependent L2 round trips in one lane.
+    for (uint32_t m0 = 0; m0 < s.pqM; m0 += 32) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t m = m0 + 8 * u + g;
+        v[u] = m < s.pqM ? __ldg(s.cdist + (size_t(m) * s.pqK + x[m]) * s.pqK + y[m]) : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+          const float t = __shfl_sync(SDB_FULL, v[u], l, 8);
+          if (m0 + 8 * u + l < s.pqM) r = __fadd_rn(r, t);  // warp-uniform
+        }
+      }
+    }
   }
   return r;
 }
