@@ -836,6 +836,76 @@ struct BitEval {
   }
 };
 
+// Rows of up to 1024 bits whose pitch is a multiple of 32 bytes (NCH = 0 selects this form): FOUR
+// lanes own a row, 32 bytes per lane in one 256-bit load (LDG.E.256), eight rows per warp-wide
+// load, two shuffle steps per reduction — half the instructions per row of the 8-lane form, which
+// is what the hamming search is bound by once the visited probe is cheap (profiles/r02_k2_*: the
+// evaluator was 41 % of its instructions). SETS sets of 8 rows stay in flight.
+template <int BMETRIC, int SETS>
+struct BitEval<BMETRIC, 0, SETS> {
+  uint64_t q[4];  // this lane's 32-byte slice of the encoded query
+  __device__ __forceinline__ void encode_query(const SearchArgs& a, const float* qsmem, uint64_t* qbits, int lane) {
+    for (uint32_t w = 0; w < a.bits_pitch; ++w) {
+      uint64_t word = 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t i = w * 64 + h * 32 + lane;
+        bool on = (i < a.dim) && (qsmem[i] > __ldg(a.bq_thr + i));
+        uint32_t b = __ballot_sync(SDB_FULL, on);
+        word |= uint64_t(b) << (32 * h);
+      }
+      if (lane == 0) qbits[w] = word;
+    }
+    __syncwarp();
+    const uint32_t w0 = 4u * (lane & 3);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) q[j] = w0 + j < a.bits_pitch ? qbits[w0 + j] : 0;
+  }
+  __device__ __forceinline__ void issue(const SearchArgs& a, const uint32_t* cid, int n, int s, int h, int grp, uint4 (&v)[2]) {
+    const int ci = s * 8 + grp;  // groups past the end re-read the first candidate's row (result discarded)
+    const uint64_t* row = a.bits + size_t(cid[ci < n ? ci : 0]) * a.bits_pitch;
+    if (4u * h < a.bits_pitch) ldg_u8_stream(row + 4 * h, v[0], v[1]);
+    else { v[0] = make_uint4(0, 0, 0, 0); v[1] = v[0]; }
+  }
+  __device__ __forceinline__ void consume(float* cdist, int n, int s, int h, int grp, const uint4 (&v)[2]) {
+    const uint64_t r[4] = {(uint64_t(v[0].y) << 32) | v[0].x, (uint64_t(v[0].w) << 32) | v[0].z,
+                           (uint64_t(v[1].y) << 32) | v[1].x, (uint64_t(v[1].w) << 32) | v[1].z};
+    int x = 0, u = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (BMETRIC == METRIC_JACCARD) { x += __popcll(q[j] & r[j]); u += __popcll(q[j] | r[j]); }
+      else x += __popcll(q[j] ^ r[j]);
+    }
+#pragma unroll
+    for (int o = 2; o >= 1; o >>= 1) {
+      x += __shfl_down_sync(SDB_FULL, x, o, 4);
+      if (BMETRIC == METRIC_JACCARD) u += __shfl_down_sync(SDB_FULL, u, o, 4);
+    }
+    const int ci = s * 8 + grp;
+    if (h == 0 && ci < n) cdist[ci] = bits_finish(BMETRIC, x, u);
+  }
+  template <class Hook>
+  __device__ __forceinline__ void eval(const SearchArgs& a, const uint32_t* cid, float* cdist, int n, int lane, Hook&& hook) {
+    const int h = lane & 3, grp = lane >> 2;
+    const int nsets = (n + 7) >> 3;
+    uint4 v[SETS][2];
+#pragma unroll
+    for (int u = 0; u < SETS; ++u)
+      if (u < nsets) issue(a, cid, n, u, h, grp, v[u]);
+    hook();
+    for (int base = 0; base < nsets; base += SETS) {
+#pragma unroll
+      for (int u = 0; u < SETS; ++u) {
+        const int s = base + u;
+        if (s >= nsets) break;  // warp-uniform
+        consume(cdist, n, s, h, grp, v[u]);
+        if (s + SETS < nsets) issue(a, cid, n, s + SETS, h, grp, v[u]);
+      }
+    }
+    __syncwarp();
+  }
+};
+
 // PQ codes (productQuantizer.DistanceFromFloat, product.go:238-277): per-query ADC table
 // (built by a separate kernel, product.go:255-263) read through L1/L2; one lane per
 // candidate sums M table entries sequentially in f32 (product.go:271-275).

@@ -44,7 +44,7 @@ def _check_graph_equal(oix, g, n):
 
 
 @pytest.mark.parametrize("metric", ["hamming", "jaccard"])
-@pytest.mark.parametrize("dim", [1024, 100, 64, 2048, 4000])
+@pytest.mark.parametrize("dim", [1024, 100, 64, 2048, 4000, 256, 768])
 def test_bit_metric_search_matches_oracle(metric, dim):
     """C5b-shaped: 0/1 floats, binary store forced on with threshold 0.5 (vectorstore.go:56-66);
     integer distances make boundary ties ubiquitous (SURVEY.md §7.3-②)."""
