@@ -476,6 +476,9 @@ def run_search(cx, name, n, B, steps, warmup, graph, headline):
     else:
         searcher = ShardedSearcher(g, rank, world, exchange=args.exchange)
     stream = torch.cuda.current_stream()
+    # device-resident loop at N > 1: the exchange (barrier + K6) of step e runs on a side stream under the
+    # search of step e+1 (ShardedSearcher pipeline, three gather buffers); SDB_NO_PIPELINE=1 = A/B
+    pipelined = world > 1 and not replicated and not os.environ.get("SDB_NO_PIPELINE")
     launches = [0]
     result = [None]
 
@@ -490,6 +493,12 @@ def run_search(cx, name, n, B, steps, warmup, graph, headline):
         step()
         torch.cuda.synchronize()  # the visited-table size adapts between searches that find the stream idle
     cx.barrier()
+    if pipelined and searcher.exchange != "nccl" and searcher._peer is not None:
+        searcher.pipeline = True
+        for _ in range(3):
+            step()
+        searcher.wait_pipeline()
+        cx.barrier()
     sampler = ClockSampler(cx.local_rank) if headline else None
     if sampler:
         sampler.start()
@@ -502,10 +511,14 @@ def run_search(cx, name, n, B, steps, warmup, graph, headline):
     e0.record(stream)
     for _ in range(steps):
         step()
+    if searcher.__dict__.get("pipeline"):
+        searcher.wait_pipeline()  # the last steps' exchanges are part of the timed region
     e1.record(stream)
     cx.barrier()
     if os.environ.get("SDB_PROFILE"):
         torch.cuda.profiler.stop()
+    if searcher.__dict__.get("pipeline"):
+        searcher.pipeline = False  # the untimed tail and the e2e loop use the one-stream path
     ms_total = e0.elapsed_time(e1)
     kern = g.search_profile_read()
     g.search_profile(False)
@@ -641,7 +654,7 @@ def run_search(cx, name, n, B, steps, warmup, graph, headline):
         "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "clocks": clocks, "build_s": build_s, "fit_s": fit_s,
         "parity": parity, "parity_merged": parity_merged, "oracle_recall": oracle_recall, "k_ids": k_ids, "k_d": k_d,
         "pq_fit": fit_cpu,
-        "exchange": searcher.exchange, "searcher": searcher, "launch_queries": launch_queries,
+        "exchange": searcher.exchange, "searcher": searcher, "launch_queries": launch_queries, "pipelined": pipelined,
     })
     return out
 
@@ -858,6 +871,9 @@ def main():
         elif world > 1:
             cfg.update(exchange="fused peer stores over NVLink + flag barrier (sdb_search_batch_gather_device)"
                        if h["exchange"] != "nccl" else "NCCL all-gather per result tensor",
+                       exchange_pipelining=("barrier + merge of step e on a side stream under the search of step e+1 "
+                                            "(three gather buffers); value is steady-state throughput, e2e is one "
+                                            "synchronous call per step") if h["pipelined"] and h["exchange"] != "nccl" else "none",
                        parity_merged=h["parity_merged"])
         cfg.update(user_qps=h["user_qps"], recall_at_10=h["recall_at_10"],
                    recall_scope=("merged top-k of all shards vs exact top-k of the union"

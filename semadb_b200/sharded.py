@@ -71,12 +71,13 @@ def exchange_topk(ids, dists, counts, group=None):
 class PeerGatherBuffers:
     """Peer-mapped gather buffers for the exchange fused into the search kernel
     (sdb_search_batch_gather_device): one symmetric allocation per rank, laid out as
-    [flag words | buffer 0 | buffer 1], each buffer = ids [S][B][k] u64, dists [S][B][k] f32,
+    [flag words | buffer 0 | buffer 1 | buffer 2], each buffer = ids [S][B][k] u64, dists [S][B][k] f32,
     counts [S][B] u32. torch symmetric memory only allocates and maps the pages across the
     processes (the job cudaDeviceEnablePeerAccess does inside one Go process); the stores, the
     barrier and the merge are this library's kernels."""
 
     FLAG_BYTES = 256  # 2 * SDB_MAX_PEERS u32 words, padded
+    NBUF = 3          # gather buffers, used round-robin by epoch (see ShardedSearcher: pipeline)
 
     def __init__(self, rank: int, world: int, B: int, k: int, device, group=None):
         import torch
@@ -86,7 +87,7 @@ class PeerGatherBuffers:
         ids_b, d_b, c_b = world * B * k * 8, world * B * k * 4, world * B * 4
         self.buf_bytes = (ids_b + d_b + c_b + 255) // 256 * 256
         self.off_d, self.off_c = ids_b, ids_b + d_b
-        total = self.FLAG_BYTES + 2 * self.buf_bytes
+        total = self.FLAG_BYTES + self.NBUF * self.buf_bytes
         grp = group if group is not None else dist.group.WORLD
         self.t = symm.empty(total, dtype=torch.uint8, device=device)
         self.t.zero_()
@@ -100,7 +101,7 @@ class PeerGatherBuffers:
         self.device = device
         self._flags = (C.c_void_p * world)(*self.peer_base)
         self._pg = []
-        for par in range(2):
+        for par in range(self.NBUF):
             pg = _capi.SdbPeerGather()
             pg.n_peers, pg.shard, pg.per_shard_limit = world, rank, 0
             for p, base in enumerate(self.peer_base):
@@ -129,15 +130,41 @@ class ShardedSearcher:
     warning on stderr if symmetric memory cannot be set up on this box."""
 
     def __init__(self, index, rank: Optional[int] = None, world: Optional[int] = None, group=None,
-                 exchange: str = "auto"):
+                 exchange: str = "auto", pipeline: bool = False):
         import torch.distributed as dist
         self.index = index
         self.group = group
         self.exchange = exchange
+        self.pipeline = pipeline  # fused exchange only: barrier + merge of step e overlap the search of step e+1
+        self._side = None
+        self._pending = False
         self._peer = None
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
         self._bufs = None
+
+    def _ensure_pipeline(self, B, k, device):
+        import torch
+        if self._side is not None and self._pipe_out[0][0].shape == (B, k):
+            return
+        self._side = torch.cuda.Stream(device, priority=-1)
+        n = self._peer.NBUF
+        self._bar_done = [torch.cuda.Event() for _ in range(n)]
+        self._k1_done = torch.cuda.Event()
+        self._pipe_out = [(torch.zeros((B, k), dtype=torch.int64, device=device), torch.zeros((B, k), dtype=torch.float32, device=device),
+                           torch.zeros((B,), dtype=torch.int32, device=device)) for _ in range(n)]
+
+    def wait_pipeline(self):
+        """Block the caller's stream until the exchange of every submitted step has completed."""
+        import torch
+        if self._side is not None and self._pending:
+            torch.cuda.current_stream(self._side.device).wait_stream(self._side)
+            self._pending = False
+
+    def _drain_pipeline(self):
+        if self._pending:
+            self._side.synchronize()
+            self._pending = False
 
     def _ensure(self, B, k, device):
         import torch
@@ -173,8 +200,9 @@ class ShardedSearcher:
             return
         l_ids, l_d, l_c = self._bufs[0], self._bufs[1], self._bufs[2]
         pb = self._peer
+        self._drain_pipeline()
         pb.epoch += 1
-        par = pb.epoch & 1
+        par = pb.epoch % pb.NBUF
         pg = pb._pg[par]
         pg.per_shard_limit = shard_limit(k, self.world, max_search_limit)
         lib = _capi.lib()
@@ -221,19 +249,51 @@ class ShardedSearcher:
                     self.exchange = "nccl"
         if self.world > 1 and self._peer is not None and self.exchange != "nccl":
             pb = self._peer
+            lib = _capi.lib()
+            di = dev.index or 0
+            if not self.pipeline:
+                pb.epoch += 1
+                par = pb.epoch % pb.NBUF
+                pg = pb._pg[par]
+                pg.per_shard_limit = per_shard
+                _capi.check(lib.sdb_search_batch_gather_device(self.index._h, B, d_queries.data_ptr(), k, search_size,
+                                                               l_ids.data_ptr(), l_d.data_ptr(), l_c.data_ptr(),
+                                                               C.byref(pg), stream))
+                _capi.check(lib.sdb_peer_barrier_device(di, self.world, self.rank, pb._flags, pb.epoch, stream))
+                g_i, g_dd, g_cc = pb.local(par)
+                _capi.check(lib.sdb_merge_topk_device(di, self.world, B, k, g_i, g_dd, g_cc, m_ids.data_ptr(),
+                                                      m_d.data_ptr(), m_c.data_ptr(), stream))
+                return m_ids, m_d, m_c
+            # Pipelined steps: the search of step e runs on the caller's stream; its barrier and merge
+            # run on a side stream, so the search of step e+1 starts without waiting for the slowest
+            # peer of step e. Three gather buffers: step e+3 reuses the buffer of step e, and every
+            # rank's merge(e) has completed once the barrier of step e+1 has (a rank reaches that
+            # barrier after its own merge(e), side-stream order) — so search(e) waits for the local
+            # barrier(e-2). Results of a step are valid once the side stream has drained
+            # (torch.cuda.synchronize / wait_pipeline).
+            self._ensure_pipeline(B, k, dev)
+            main = torch.cuda.current_stream(dev)
+            side = self._side
             pb.epoch += 1
-            par = pb.epoch & 1
+            e = pb.epoch
+            par = e % pb.NBUF
+            if e >= 3:
+                main.wait_event(self._bar_done[(e - 2) % pb.NBUF])
             pg = pb._pg[par]
             pg.per_shard_limit = per_shard
-            lib = _capi.lib()
             _capi.check(lib.sdb_search_batch_gather_device(self.index._h, B, d_queries.data_ptr(), k, search_size,
                                                            l_ids.data_ptr(), l_d.data_ptr(), l_c.data_ptr(),
-                                                           C.byref(pg), stream))
-            _capi.check(lib.sdb_peer_barrier_device(dev.index or 0, self.world, self.rank, pb._flags, pb.epoch, stream))
+                                                           C.byref(pg), main.cuda_stream))
+            self._k1_done.record(main)
+            side.wait_event(self._k1_done)
+            o_ids, o_d, o_c = self._pipe_out[par]
+            _capi.check(lib.sdb_peer_barrier_device(di, self.world, self.rank, pb._flags, e, side.cuda_stream))
+            self._bar_done[par].record(side)
             g_i, g_dd, g_cc = pb.local(par)
-            _capi.check(lib.sdb_merge_topk_device(dev.index or 0, self.world, B, k, g_i, g_dd, g_cc, m_ids.data_ptr(),
-                                                  m_d.data_ptr(), m_c.data_ptr(), stream))
-            return m_ids, m_d, m_c
+            _capi.check(lib.sdb_merge_topk_device(di, self.world, B, k, g_i, g_dd, g_cc, o_ids.data_ptr(),
+                                                  o_d.data_ptr(), o_c.data_ptr(), side.cuda_stream))
+            self._pending = True
+            return o_ids, o_d, o_c
         self.index.search_batch_device(d_queries, k, search_size, l_ids, l_d, l_c, stream)
         if per_shard < k:
             l_c.clamp_(max=per_shard)

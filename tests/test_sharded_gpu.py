@@ -159,8 +159,29 @@ def _p2p_worker(rank, world, port, out_dir):
         b.search_batch_pinned(h_q, k, 75, h_i, h_d, h_c, dev)
         same = same and bool((h_i == ref[0].cpu()).all()) and bool((h_d == ref[1].cpu()).all()) and \
             bool((h_c == ref[2].cpu()).all())
-    failed = b._peer.barrier_failed()
-    np.savez(os.path.join(out_dir, f"p2p{rank}.npz"), same=same, failed=failed, ids=ref[0].cpu().numpy())
+    # pipelined steps: the exchange of step e overlaps the search of step e+1 (three gather
+    # buffers, side stream). Different query batches per step, submitted back to back: every
+    # step's lists must equal the unpipelined answer for its batch.
+    c = sharded.ShardedSearcher(g, rank, world, exchange="p2p", pipeline=True)
+    batches = [torch.roll(d_q, shifts=7 * i, dims=0).contiguous() for i in range(7)]
+    want = []
+    for qb in batches:
+        want.append([t.clone() for t in a.search_batch_device(qb, k, 75)])
+    torch.cuda.synchronize()
+    got_p = []
+    for i, qb in enumerate(batches):
+        out = c.search_batch_device(qb, k, 75)
+        if i >= 2:  # results of step i-2 are about to lose their buffer: take them (stream-ordered)
+            c.wait_pipeline()
+        got_p.append([t.clone() for t in out])  # clone is ordered after wait_pipeline on the current stream only from i >= 2
+    c.wait_pipeline()
+    torch.cuda.synchronize()
+    final = [t.clone() for t in out]
+    same_pipe = all(bool((x == y).all().item()) for x, y in zip(final, want[-1]))
+    for i in range(2, len(batches)):
+        same_pipe = same_pipe and all(bool((x == y).all().item()) for x, y in zip(got_p[i], want[i]))
+    failed = b._peer.barrier_failed() or c._peer.barrier_failed()
+    np.savez(os.path.join(out_dir, f"p2p{rank}.npz"), same=same and same_pipe, failed=failed, ids=ref[0].cpu().numpy())
     dist.barrier()
     dist.destroy_process_group()
 
