@@ -719,7 +719,8 @@ def run_build(cx, n, steps, warmup):
     g.close()
     return {"workload": f"C5a: batched graph build from empty, {n}x128 f32 L2 per GPU (greedySearch + robustPrune + "
                         f"back-edges, K8), vectors resident in HBM",
-            "points_per_s": cx.world * n / dt, "build_s": dt, "builds_timed": len(times), "n_gpus": cx.world,
+            "points_per_s": cx.world * n / dt, "build_s": dt, "builds_timed": len(times), "build_s_each": [round(t, 4) for t in times],
+            "n_gpus": cx.world,
             "recall_at_10_of_built_graph": rec, "insert_stats": stats,
             "roofline": {"bound": "hbm", "achieved": by / dt / 1e9, "peak": peak, "unit": "GB/s", "frac": by / dt / 1e9 / peak,
                          "algorithmic_bytes_per_point": by / max(1, stats["points"]), "per": "GPU"}}
@@ -771,7 +772,7 @@ def main():
                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                    "data": "synthetic", "config": {"workload": r["workload"], "points_per_gpu": n,
                                                    "recall_at_10_of_built_graph": r["recall_at_10_of_built_graph"],
-                                                   "insert_stats": r["insert_stats"]},
+                                                   "build_s_each": r["build_s_each"], "insert_stats": r["insert_stats"]},
                    "roofline": r["roofline"], "cpu_baseline": None, "e2e": None, "gpu_launches": None}
             print(json.dumps(out), file=_OUT, flush=True)
         if world > 1:
