@@ -762,13 +762,14 @@ template <int BMETRIC, int NCH, int SETS>
 struct BitEval {
   uint64_t q[NCH][2];  // this lane's slice of the encoded query
   __device__ __forceinline__ void encode_query(const SearchArgs& a, const float* qsmem, uint64_t* qbits, int lane) {
-    // bit i%64 of word i/64 = q[i] > thr[i]
+    // bit i%64 of word i/64 = q[i] > thr[i]; qsmem = the query in GLOBAL (or mapped host) memory, read
+    // once, coalesced — a shared-memory copy of the floats (4 KB at 1024 dims) would only cost residency
     for (uint32_t w = 0; w < a.bits_pitch; ++w) {
       uint64_t word = 0;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t i = w * 64 + h * 32 + lane;
-        bool on = (i < a.dim) && (qsmem[i] > __ldg(a.bq_thr + i));
+        bool on = (i < a.dim) && (__ldg(qsmem + (i < a.dim ? i : 0)) > __ldg(a.bq_thr + (i < a.dim ? i : 0)));
         uint32_t b = __ballot_sync(SDB_FULL, on);
         word |= uint64_t(b) << (32 * h);
       }
@@ -850,7 +851,7 @@ struct BitEval<BMETRIC, 0, SETS> {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t i = w * 64 + h * 32 + lane;
-        bool on = (i < a.dim) && (qsmem[i] > __ldg(a.bq_thr + i));
+        bool on = (i < a.dim) && (__ldg(qsmem + (i < a.dim ? i : 0)) > __ldg(a.bq_thr + (i < a.dim ? i : 0)));
         uint32_t b = __ballot_sync(SDB_FULL, on);
         word |= uint64_t(b) << (32 * h);
       }
@@ -1266,7 +1267,7 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
 
     // ---- per-query setup
     vt.clear(lane);
-    if (KIND != EVAL_ADC && KIND != EVAL_ADC_SMEM) {
+    if (KIND != EVAL_ADC && KIND != EVAL_ADC_SMEM && KIND != EVAL_BITS) {
       const float* qg = a.queries + size_t(qi) * a.dim;
       for (uint32_t i = lane; i < qfloats; i += 32) qs[i] = i < a.dim ? __ldg(qg + i) : 0.0f;
     }
@@ -1286,7 +1287,7 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
       ev_adcs.load_table(tab, a.adc + size_t(qi) * a.pqM * a.pqK, a.pqM * a.pqK, tbar, tphase, lane);
     if (KIND == EVAL_FLOAT_FIXED) ev_fixed.load_query(qs, a.queries + size_t(qi) * a.dim, lane);
     if (KIND == EVAL_FLOAT_GENERIC) ev_gen.load_query(qs, lane);
-    if (KIND == EVAL_BITS) ev_bits.encode_query(a, qs, qbits, lane);
+    if (KIND == EVAL_BITS) ev_bits.encode_query(a, a.queries + size_t(qi) * a.dim, qbits, lane);
     if (KIND == EVAL_ADC) ev_adc.table = a.adc + size_t(qi) * a.pqM * a.pqK;
     auto no_hook = []() {};
     auto evaluate_h = [&](int n, auto&& hook) {

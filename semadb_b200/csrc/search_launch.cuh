@@ -19,7 +19,7 @@ int launch_variant_x(sdb_index* ix, const SearchArgs& a, cudaStream_t stream) {
   auto kern = beam_search_kernel<KIND, METRIC, TRIPS, SETS, LEGACY, MERGE_MIN, VT, FILTER, RETRY, MINB, XTRA, PF>;
   // FloatEvalGrouped keeps short queries (<= 4 float4 per lane) in registers: no shared copy
   constexpr bool QREG = (KIND == EVAL_FLOAT_FIXED) && !LEGACY && TRIPS <= 4;
-  const uint32_t qfloats = (KIND == EVAL_ADC || KIND == EVAL_ADC_SMEM || QREG) ? 0 : (a.dim + 3) / 4 * 4;
+  const uint32_t qfloats = (KIND == EVAL_ADC || KIND == EVAL_ADC_SMEM || KIND == EVAL_BITS || QREG) ? 0 : (a.dim + 3) / 4 * 4;
   const uint32_t qwords = (KIND == EVAL_BITS) ? a.bits_pitch : 0;
   const uint32_t table_floats = (KIND == EVAL_ADC_SMEM) ? a.pqM * a.pqK : 0;
   const size_t smem = warp_smem_bytes<VT, FILTER>(qfloats, qwords, a.vt_slots, table_floats);
