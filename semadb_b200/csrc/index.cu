@@ -515,6 +515,9 @@ static int stage_filters(sdb_index* ix, uint32_t B, uint32_t n_filters, const ui
   if (n_filters == 0 || !filter_offsets) return fail(SDB_ERR_INVALID, "filters: need at least one filter and its offsets");
   std::vector<uint32_t> ids, off(size_t(n_filters) + 1, 0), qf_plain, qf_filtered;
   std::vector<int32_t> qfil;
+  for (uint32_t f = 0; f < n_filters; ++f)
+    if (filter_offsets[f + 1] < filter_offsets[f]) return fail(SDB_ERR_INVALID, "filters: offsets must ascend");
+  if (filter_offsets[n_filters] - filter_offsets[0] >= (uint64_t(1) << 32)) return fail(SDB_ERR_INVALID, "filters: too many ids in one batch");
   ids.reserve(size_t(filter_offsets[n_filters] - filter_offsets[0]));
   for (uint32_t f = 0; f < n_filters; ++f) {
     const uint64_t b0 = filter_offsets[f], b1 = filter_offsets[f + 1];

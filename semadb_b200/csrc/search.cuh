@@ -1392,10 +1392,13 @@ __global__ void __launch_bounds__(32, MINB) beam_search_kernel(SearchArgs a, uin
       add_with_limit(list, 1);
     }
 
+    // a table that cannot hold this store's ids at all (span beyond 16 bits) refuses every probe:
+    // the query goes to the RETRY launch before it has searched anything
+    if (vt.failed) overflow = true;
     // main loop (search.go:65-98). pf_*: adjacency row of the runner-up candidate, fetched
     // one hop early; used if that candidate is indeed expanded next.
     uint32_t pf_id = INVALID_ID, pf_n0 = INVALID_ID, pf_n1 = INVALID_ID;
-    for (;;) {
+    for (; !overflow;) {
       const int lim = min(list.len, int(a.L));
       int pos = -1, pos2 = -1, pos3 = -1;
 #pragma unroll
