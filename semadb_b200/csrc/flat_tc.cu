@@ -75,14 +75,17 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
 // so the rounding is that of v), columns [kp, pitch) = 0 (the K extension, filled in by
 // bias_kernel / thresh_kernel); squared norms of the unscaled rows (fp32, sequential per lane then
 // tree: the norm only feeds the candidate bound, not a result)
+// mu != nullptr (squared-L2 only): rows are centred, v = src - mu. Distances do not change under a
+// common translation, while the candidate bound scales with |q - mu| |x - mu| instead of |q| |x|
+// (mu itself need not be exact: any vector is a valid translation, results are re-scored exactly).
 __global__ void to_bf16_kernel(const float* src, uint32_t src_pitch, uint32_t dim, uint32_t n, uint32_t n_pad,
-                               __nv_bfloat16* dst, uint32_t kp, uint32_t pitch, float scale, float* norms) {
+                               __nv_bfloat16* dst, uint32_t kp, uint32_t pitch, float scale, float* norms, const float* mu) {
   const uint32_t row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x & 31;
   if (row >= n_pad) return;
   float s = 0.0f;
   for (uint32_t i = lane; i < pitch; i += 32) {
-    float v = (row < n && i < dim) ? src[size_t(row) * src_pitch + i] : 0.0f;
+    float v = (row < n && i < dim) ? src[size_t(row) * src_pitch + i] - (mu ? mu[i] : 0.0f) : 0.0f;
     s += v * v;
     dst[size_t(row) * pitch + i] = __float2bfloat16_rn(scale * v);
   }
@@ -158,6 +161,106 @@ __global__ void thresh_kernel(const float* sample_d, const uint32_t* sample_cnt,
   put(tt, tt);
 }
 
+// ---- centring (squared-L2): mean of an evenly strided sample of the stored rows, fixed summation order
+constexpr uint32_t MU_PARTS = 64;
+__global__ void mean_partial_kernel(const float* vec, uint32_t vec_pitch, uint32_t dim, const uint8_t* exists, uint32_t first,
+                                    uint32_t end, uint32_t stride, uint32_t per_part, float* partial, uint32_t* cnt) {
+  const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x, part = blockIdx.y;
+  float s = 0.0f;
+  uint32_t c = 0;
+  for (uint32_t i = 0; i < per_part; ++i) {
+    const uint64_t r = uint64_t(first) + (uint64_t(part) * per_part + i) * stride;
+    if (r >= end) break;
+    if (!exists[r]) continue;
+    ++c;
+    if (d < dim) s += vec[size_t(r) * vec_pitch + d];
+  }
+  if (d < dim) partial[size_t(part) * dim + d] = s;
+  if (d == 0) cnt[part] = c;
+}
+__global__ void mean_final_kernel(const float* partial, const uint32_t* cnt, uint32_t dim, float* mu) {
+  const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= dim) return;
+  float s = 0.0f;
+  uint32_t c = 0;
+  for (uint32_t p = 0; p < MU_PARTS; ++p) { s += partial[size_t(p) * dim + d]; c += cnt[p]; }
+  mu[d] = c ? s / float(c) : 0.0f;
+}
+
+// K extension of the query rows for the minimum-mode pass: threshold 0 (the accumulator is the score)
+__global__ void ext_zero_kernel(__nv_bfloat16* q16, uint32_t kp, uint32_t pitch, uint32_t B_pad) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= B_pad) return;
+  __nv_bfloat16* e = q16 + size_t(q) * pitch + kp;
+  const __nv_bfloat16 one = __float2bfloat16_rn(1.0f), zero = __float2bfloat16_rn(0.0f);
+  e[0] = one; e[1] = one; e[2] = one; e[3] = zero; e[4] = zero; e[5] = zero;
+}
+
+// Threshold of the candidate pass from the minimum-mode pass over a sample prefix. The k smallest of
+// a query's group minima belong to k different points (the groups are disjoint point sets), each
+// with an exact score <= approximate score + E (E = the bf16 / fp32 error bound thresh_kernel
+// uses): the k-th true score over ALL points is <= m_k + E, and every point that good has an
+// approximate score <= m_k + 2E. One warp per query: k rounds of warp-wide minimum extraction
+// over the <= 512 group minima held in registers.
+constexpr uint32_t KTH_MAX_GROUPS = 512;
+__global__ void __launch_bounds__(128) kth_thresh_kernel(const float* gmin, uint32_t gmin_pitch, uint32_t G, uint32_t k, const float* qn,
+                                                         const uint32_t* xmax_bits, int metric, uint32_t dim, uint32_t B,
+                                                         uint32_t B_pad, float* thr, __nv_bfloat16* q16, uint32_t kp, uint32_t pitch,
+                                                         uint32_t* cand_cnt) {
+  const uint32_t q = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x & 31;
+  if (q >= B_pad) return;
+  float t_out;
+  if (q >= B) {
+    t_out = T5_PASS_NONE;  // padding rows never pass
+  } else {
+    float v[KTH_MAX_GROUPS / 32];
+#pragma unroll
+    for (uint32_t i = 0; i < KTH_MAX_GROUPS / 32; ++i) {
+      const uint32_t g = lane + 32 * i;
+      v[i] = g < G ? gmin[size_t(g) * gmin_pitch + q] : INFINITY;
+      if (!(v[i] == v[i])) v[i] = INFINITY;  // NaN (inf - inf in a degenerate row): no information
+    }
+    float mk = INFINITY;
+    for (uint32_t r = 0; r < k; ++r) {
+      float m = v[0];
+      int mi = 0;
+#pragma unroll
+      for (int i = 1; i < int(KTH_MAX_GROUPS / 32); ++i)
+        if (v[i] < m) { m = v[i]; mi = i; }
+      float w = m;
+      for (int o = 16; o >= 1; o >>= 1) w = fminf(w, __shfl_xor_sync(SDB_FULL, w, o));
+      const uint32_t holders = __ballot_sync(SDB_FULL, m == w);
+      if (lane == __ffs(holders) - 1) {
+#pragma unroll
+        for (int i = 0; i < int(KTH_MAX_GROUPS / 32); ++i)
+          if (i == mi) v[i] = INFINITY;
+      }
+      mk = w;
+      if (!(w < 1.0e37f)) break;  // fewer than k groups hold a point
+    }
+    if (!(mk < 1.0e37f)) {
+      t_out = T5_PASS_ALL;
+    } else {
+      const float x2 = __uint_as_float(*xmax_bits), q2 = qn[q];
+      const float nq = sqrtf(q2), nx = sqrtf(x2);
+      const float c1 = 0.02f, c2 = float(dim + 32) * 4.8e-7f;  // as in thresh_kernel
+      const float E = metric == METRIC_EUCLIDEAN ? c1 * nq * nx + c2 * (q2 + x2) : (0.5f * c1 + c2) * nq * nx;
+      const float t = mk + 2.0f * E;
+      t_out = fminf(t + fabsf(t) * 1e-6f + 1e-30f, T5_PASS_ALL);
+    }
+  }
+  if (lane == 0) {
+    thr[q] = t_out;
+    __nv_bfloat16 h, m, l;
+    split3(-t_out, h, m, l);
+    __nv_bfloat16* e = q16 + size_t(q) * pitch + kp;
+    const __nv_bfloat16 one = __float2bfloat16_rn(1.0f);
+    e[0] = one; e[1] = one; e[2] = one; e[3] = h; e[4] = m; e[5] = l;
+    if (q < B) cand_cnt[q] = 0;
+  }
+}
+
 struct TcArgs {
   const __nv_bfloat16* q16;   // [B_pad][pitch]: scale * q, then the K extension
   const __nv_bfloat16* x16;   // [rows_pad][pitch]
@@ -171,6 +274,12 @@ struct TcArgs {
   uint32_t B;
   uint32_t rows_alloc;        // rows of x16 / bias (tcgen05 path: point tiles may reach past end_id)
   const float* bias;          // [rows_alloc] tcgen05 path
+  // tcgen05 path, minimum mode (gmin != nullptr): no candidates; the smallest accumulator of every
+  // (query, group of `fold` point tiles, column half) goes to gmin[group * gmin_pitch + query]
+  float* gmin;
+  uint32_t gmin_pitch, fold;
+  uint32_t tile_stride;       // minimum mode: tile t covers the points from first_id + t * tile_stride * 256 (an evenly
+                              // spread sample instead of a prefix); 0 or 1 = contiguous
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 2) tc_filter_kernel(TcArgs a) {
@@ -460,8 +569,9 @@ tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
       int s = 0, es = 0;
       uint32_t ph = 0, eph = 0;
+      const uint32_t tstride = a.tile_stride ? a.tile_stride : 1u;
       for (uint32_t t = tile_begin; t < tile_end; ++t) {
-        const int32_t p0 = int32_t(a.first_id + t * T5_N);
+        const int32_t p0 = int32_t(a.first_id + t * tstride * T5_N);
         for (uint32_t kb = 0; kb < nkb; ++kb) {
           t5_mbar_wait(bar_empty(s), ph ^ 1u);
           t5_mbar_expect_tx(bar_full(s), T5_XBLK_BYTES);
@@ -550,6 +660,41 @@ tc5_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       nh = 0;
     };
     uint32_t it = 0;
+    if (a.gmin) {
+      // ===== minimum mode: the thresholds are zero, the accumulator is the approximate score; keep
+      // the smallest one per (query, group of `fold` tiles, column half). The launch makes
+      // tiles_per_cta a multiple of fold, so every group belongs to one thread: plain stores.
+      float gm = INFINITY;
+      for (uint32_t t = tile_begin; t < tile_end; ++t, ++it) {
+        const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
+        t5_mbar_wait(bar_tfull(acc), aph);
+        t5_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * (T5_QT * T5_N) + uint32_t(qt) * T5_N + uint32_t(col0);
+        uint32_t v[2][32];
+        t5_ld32(taddr, v[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          t5_wait_ld();
+          if (c + 1 < 4) t5_ld32(taddr + uint32_t(c + 1) * 32, v[(c + 1) & 1]);
+          float m0 = INFINITY, m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            m0 = fminf(m0, __uint_as_float(v[c & 1][j]));
+            m1 = fminf(m1, __uint_as_float(v[c & 1][j + 1]));
+            m2 = fminf(m2, __uint_as_float(v[c & 1][j + 2]));
+            m3 = fminf(m3, __uint_as_float(v[c & 1][j + 3]));
+          }
+          gm = fminf(gm, fminf(fminf(m0, m1), fminf(m2, m3)));
+        }
+        t5_fence_before();
+        __syncwarp();
+        if (lane == 0) t5_mbar_arrive(bar_tempty(acc));
+        if ((t + 1) % a.fold == 0 || t + 1 == tile_end) {
+          if (q_ok) a.gmin[size_t((t / a.fold) * 2 + uint32_t(e >> 2)) * a.gmin_pitch + q] = gm;
+          gm = INFINITY;
+        }
+      }
+    } else
     for (uint32_t t = tile_begin; t < tile_end; ++t, ++it) {
       const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
       const uint32_t p0 = a.first_id + t * T5_N;
@@ -902,8 +1047,9 @@ int launch_tc5_filter(sdb_index* ix, TcArgs ta, uint32_t B_pad, cudaStream_t str
     }
   }
   ta.tiles_per_cta = (ntiles + ysplit - 1) / ysplit;
+  if (ta.gmin) ta.tiles_per_cta = (ta.tiles_per_cta + ta.fold - 1) / ta.fold * ta.fold;  // a group never spans two CTAs
   ysplit = (ntiles + ta.tiles_per_cta - 1) / ta.tiles_per_cta;
-  if (getenv("SDB_FLAT_2CTA") && qtiles % 2 == 0) {
+  if (!ta.gmin && getenv("SDB_FLAT_2CTA") && qtiles % 2 == 0) {
     // two-SM variant: X maps with 128-row boxes (each CTA loads its half of a point tile)
     const uint32_t fixed2 = t2_layout(nkb, 0).total + 1024;
     int st2 = int((227u * 1024u - fixed2) / T2_XBLK_BYTES);
@@ -952,29 +1098,28 @@ __global__ void seed_cand_kernel(const uint64_t* prev_ids, const uint32_t* prev_
 // Exact re-score, one WARP per query (four queries per CTA, no block-wide barrier): the candidates'
 // rows are gathered 16 at a time (an 8-lane group per row, all 16 row loads of a lane in flight),
 // scored with the reference's summation order, and offered to a k-slot list sorted by (distance asc,
-// id asc) that lives in shared memory (k * 8 bytes per query instead of CAND_CAP * 8): a candidate
-// that does not beat the current k-th is dropped by the lane that holds it, so the warp-wide
-// insertion runs ~k ln(n/k) times per query. implicit_n > 0: the candidates are the implicit_n
-// points first_id, first_id+1, ... (level 0: the exact top-k of the first points, no list in memory).
+// id asc) that lives in REGISTERS (slot p = lane + 32 j, NS slots per lane: 1 for k <= 32, 3 up to
+// k = 96): an insertion is three ballots' worth of compares and two shuffles per slot row, no
+// shared-memory round trip. A candidate that does not beat the current k-th (kept in a uniform
+// register pair) is dropped by the lane that holds it, so the warp-wide insertion runs
+// ~k ln(n/k) times per query. implicit_n > 0: the candidates are the implicit_n points first_id,
+// first_id+1, ... (level 0 of the level scheme: no list in memory). cand_total: optional running
+// sum of the list lengths (the sdb_flat_last_stats diagnostic).
 constexpr int RW_WARPS = 4;
-constexpr int RW_SLOTS = 96;  // >= max k (75), lanes cover slots lane + 32 j
-template <int METRIC>
+template <int METRIC, int NS>
 __global__ void __launch_bounds__(32 * RW_WARPS) rescore_warp_kernel(
     const float* vec, uint32_t vec_pitch, uint32_t dim, const float* queries, uint32_t B, const uint32_t* cand,
     const uint32_t* cand_cnt, uint32_t k, uint64_t* out_ids, float* out_d, uint32_t* out_cnt, uint32_t* overflow_list,
     uint32_t* overflow_cnt, uint32_t* overflow_flag, int last_level, uint32_t first_id, uint32_t implicit_n,
-    const uint8_t* exists) {
-  __shared__ float s_kd[RW_WARPS][RW_SLOTS];
-  __shared__ uint32_t s_ki[RW_WARPS][RW_SLOTS];
+    const uint8_t* exists, unsigned long long* cand_total) {
   extern __shared__ __align__(16) float s_qall[];  // [RW_WARPS][dim rounded up to 4]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane & 7, grp = lane >> 3;
   const uint32_t q = blockIdx.x * RW_WARPS + wid;
   if (q >= B) return;
   const uint32_t dpad = (dim + 3) & ~3u;
   float* s_q = s_qall + size_t(wid) * dpad;
-  float* kd = s_kd[wid];
-  uint32_t* ki = s_ki[wid];
   const uint32_t n = implicit_n ? implicit_n : cand_cnt[q];
+  if (cand_total && lane == 0 && !implicit_n) atomicAdd(cand_total, static_cast<unsigned long long>(n));
   if (!implicit_n && n > CAND_CAP) {
     // Levels cover disjoint point ranges, so a list that overflowed at any level has lost
     // candidates for good: the query goes to the exact scan after the last level (once: the
@@ -989,42 +1134,51 @@ __global__ void __launch_bounds__(32 * RW_WARPS) rescore_warp_kernel(
   __syncwarp();
   constexpr bool L2 = (METRIC == METRIC_EUCLIDEAN);
   const int trips = dim >> 5;
+  float kd[NS];
+  uint32_t ki[NS];
+#pragma unroll
+  for (int j = 0; j < NS; ++j) { kd[j] = 0.0f; ki[j] = 0u; }
   uint32_t len = 0;
+  float wd = 0.0f;   // the k-th entry once the list is full (uniform)
+  uint32_t wi = 0u;
+  const int wj = int(k - 1) >> 5, wl = int(k - 1) & 31;
   // offer (d, id), held by every lane, to the sorted list; warp-synchronous
   auto insert = [&](float d, uint32_t id) {
     uint32_t pos = 0;
 #pragma unroll
-    for (int j = 0; j < RW_SLOTS / 32; ++j) {
+    for (int j = 0; j < NS; ++j) {
       const uint32_t p = lane + 32 * j;
-      const bool before = p < len && (kd[p] < d || (kd[p] == d && ki[p] < id));
+      const bool before = p < len && (kd[j] < d || (kd[j] == d && ki[j] < id));
       pos += __popc(__ballot_sync(SDB_FULL, before));
     }
     if (pos >= k) return;
-    const uint32_t last = len < k ? len : k - 1;  // elements [pos, last) move up by one
-    float mvd[RW_SLOTS / 32];
-    uint32_t mvi[RW_SLOTS / 32];
 #pragma unroll
-    for (int j = 0; j < RW_SLOTS / 32; ++j) {
+    for (int j = NS - 1; j >= 0; --j) {  // slots >= pos move up by one; the rows below are still unmodified
+      float pd = __shfl_up_sync(SDB_FULL, kd[j], 1);
+      uint32_t pi = __shfl_up_sync(SDB_FULL, ki[j], 1);
+      if (j > 0) {
+        const float cd = __shfl_sync(SDB_FULL, kd[j > 0 ? j - 1 : 0], 31);
+        const uint32_t ci = __shfl_sync(SDB_FULL, ki[j > 0 ? j - 1 : 0], 31);
+        if (lane == 0) { pd = cd; pi = ci; }
+      }
       const uint32_t p = lane + 32 * j;
-      if (p >= pos && p < last) { mvd[j] = kd[p]; mvi[j] = ki[p]; }
+      if (p > pos) { kd[j] = pd; ki[j] = pi; }
+      else if (p == pos) { kd[j] = d; ki[j] = id; }
     }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < RW_SLOTS / 32; ++j) {
-      const uint32_t p = lane + 32 * j;
-      if (p >= pos && p < last) { kd[p + 1] = mvd[j]; ki[p + 1] = mvi[j]; }
-    }
-    if (lane == 0) { kd[pos] = d; ki[pos] = id; }
     if (len < k) ++len;
-    __syncwarp();
+    if (len == k) {
+      float sd = kd[0];
+      uint32_t si = ki[0];
+#pragma unroll
+      for (int j = 1; j < NS; ++j)
+        if (j == wj) { sd = kd[j]; si = ki[j]; }
+      wd = __shfl_sync(SDB_FULL, sd, wl);
+      wi = __shfl_sync(SDB_FULL, si, wl);
+    }
   };
   // the lanes that hold a fresh (d, id) (lane 0 of each group) offer it if it can enter the list
   auto offer = [&](float d, uint32_t id, bool have) {
-    bool want = have;
-    if (have && len == k) {
-      const float wd = kd[k - 1];
-      want = d < wd || (d == wd && id < ki[k - 1]);
-    }
+    const bool want = have && (len < k || d < wd || (d == wd && id < wi));
     uint32_t m = __ballot_sync(SDB_FULL, want);
     while (m) {
       const int src = __ffs(m) - 1;
@@ -1080,10 +1234,13 @@ __global__ void __launch_bounds__(32 * RW_WARPS) rescore_warp_kernel(
     const float r = metric_epilogue<METRIC>(group_reduce(acc, tail));
     offer(r, pid, g == 0 && act && (!implicit_n || exists[pid]));
   }
-  __syncwarp();
-  for (uint32_t r = lane; r < k; r += 32) {
-    out_ids[size_t(q) * k + r] = r < len ? uint64_t(ki[r]) : 0;
-    out_d[size_t(q) * k + r] = r < len ? kd[r] : __int_as_float(0x7f800000);
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    const uint32_t r = lane + 32 * j;
+    if (r < k) {
+      out_ids[size_t(q) * k + r] = r < len ? uint64_t(ki[j]) : 0;
+      out_d[size_t(q) * k + r] = r < len ? kd[j] : __int_as_float(0x7f800000);
+    }
   }
   if (lane == 0) out_cnt[q] = len;
 }
@@ -1207,6 +1364,20 @@ __global__ void __launch_bounds__(128) rescore_kernel(const float* vec, uint32_t
   if (tid == 0) out_cnt[q] = kk;
 }
 
+__global__ void sum_counts_kernel(const uint32_t* cnt, uint32_t n, unsigned long long* out) {
+  __shared__ unsigned long long part[8];
+  unsigned long long v = 0;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) v += cnt[i];
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (uint32_t w = 0; w < blockDim.x / 32; ++w) t += part[w];
+    *out = t;
+  }
+}
+
 __global__ void gather_queries_kernel(const uint32_t* list, uint32_t n, const float* src, uint32_t dim, float* dst) {
   const uint32_t i = blockIdx.x;
   if (i >= n) return;
@@ -1269,17 +1440,38 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
   // ---- bf16 shadow of the store (rebuilt when the store changed)
   const uint32_t pitch = kp + T5_KB;  // one more 64-wide K block: the extension (bias / threshold pieces)
   const bool l2 = ix->store_metric == SDB_METRIC_EUCLIDEAN;
-  if (ix->tc_epoch != ix->vec_epoch || ix->d_x16.n < size_t(rows_pad) * pitch) {
+  // squared-L2: the shadow holds x - mu (mu = mean of a sample of the rows), see to_bf16_kernel
+  const int center = (l2 && !getenv("SDB_FLAT_NO_CENTER")) ? 1 : 0;
+  if (ix->tc_epoch != ix->vec_epoch || ix->d_x16.n < size_t(rows_pad) * pitch || ix->tc_centered != center) {
     if ((rc = ix->d_x16.ensure(size_t(rows_pad) * pitch)) || (rc = ix->d_xn.ensure(rows_pad)) || (rc = ix->d_bias.ensure(rows_pad)))
       return rc;
+    if (center) {
+      if ((rc = ix->d_mu.ensure(size_t(MU_PARTS + 1) * dim + MU_PARTS))) return rc;
+      float* partial = ix->d_mu.p + dim;
+      uint32_t* cnt = reinterpret_cast<uint32_t*>(ix->d_mu.p + size_t(MU_PARTS + 1) * dim);
+      const uint32_t span = end_id - first_id;
+      const uint32_t stride = std::max<uint32_t>(1, span / 65536);
+      const uint32_t per_part = ((span + stride - 1) / stride + MU_PARTS - 1) / MU_PARTS;
+      mean_partial_kernel<<<dim3((dim + 127) / 128, MU_PARTS), 128, 0, stream>>>(ix->d_vec, ix->vec_pitch, dim, ix->d_exists, first_id,
+                                                                                 end_id, stride, per_part, partial, cnt);
+      mean_final_kernel<<<(dim + 127) / 128, 128, 0, stream>>>(partial, cnt, dim, ix->d_mu.p);
+      ix->launches += 2;
+    }
+    ix->tc_centered = center;
     to_bf16_kernel<<<(rows_pad + 7) / 8, 256, 0, stream>>>(ix->d_vec, ix->vec_pitch, dim, ix->rows, rows_pad,
-                                                          reinterpret_cast<__nv_bfloat16*>(ix->d_x16.p), kp, pitch, 1.0f, ix->d_xn.p);
+                                                          reinterpret_cast<__nv_bfloat16*>(ix->d_x16.p), kp, pitch, 1.0f, ix->d_xn.p,
+                                                          center ? ix->d_mu.p : nullptr);
     bias_kernel<<<(rows_pad + 255) / 256, 256, 0, stream>>>(ix->d_xn.p, ix->d_exists, ix->rows, rows_pad, l2 ? 1 : 0, ix->d_bias.p,
                                                             reinterpret_cast<__nv_bfloat16*>(ix->d_x16.p), kp, pitch);
-    ix->launches += 2;
+    // largest squared norm of a stored row (of the centred rows if centred): part of the candidate bound
+    if ((rc = ix->d_xmax.ensure(1))) return rc;
+    SDB_CUDA(cudaMemsetAsync(ix->d_xmax.p, 0, sizeof(uint32_t), stream));
+    xmax_kernel<<<(end_id - first_id + 255) / 256, 256, 0, stream>>>(ix->d_xn.p, ix->d_exists, first_id, end_id, ix->d_xmax.p);
+    ix->launches += 3;
     SDB_CUDA(cudaGetLastError());
     ix->tc_epoch = ix->vec_epoch;
   }
+  const uint32_t* d_xmax = ix->d_xmax.p;
   if ((rc = ix->d_q16.ensure(size_t(B_pad) * pitch)) || (rc = ix->d_qn.ensure(B_pad)) || (rc = ix->d_thr.ensure(B_pad)) ||
       (rc = ix->d_cand.ensure(size_t(B) * CAND_CAP)) || (rc = ix->d_candcnt.ensure(size_t(B) * 3 + 8)) ||
       (rc = ix->d_sample_ids.ensure(size_t(B) * k)) || (rc = ix->d_sample_d.ensure(size_t(B) * k)) ||
@@ -1287,13 +1479,12 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
     return rc;
   uint32_t* d_cnt = ix->d_candcnt.p;            // [B] candidate counts
   uint32_t* d_ovf_list = ix->d_candcnt.p + B;   // [B] overflowed queries
-  uint32_t* d_misc = ix->d_candcnt.p + 2 * size_t(B);  // [0] xmax bits, [1] overflow count
+  uint32_t* d_misc = ix->d_candcnt.p + 2 * size_t(B);  // [1] overflow count, [2..3] candidates of the last level
   uint32_t* d_ovf_flag = d_misc + 8;                   // [B] query already on the overflow list
   SDB_CUDA(cudaMemsetAsync(d_misc, 0, (8 + size_t(B)) * sizeof(uint32_t), stream));
   to_bf16_kernel<<<(B_pad + 7) / 8, 256, 0, stream>>>(d_queries, dim, dim, B, B_pad, reinterpret_cast<__nv_bfloat16*>(ix->d_q16.p),
-                                                     kp, pitch, l2 ? -2.0f : -1.0f, ix->d_qn.p);
-  xmax_kernel<<<(end_id - first_id + 255) / 256, 256, 0, stream>>>(ix->d_xn.p, ix->d_exists, first_id, end_id, d_misc);
-  ix->launches += 2;
+                                                     kp, pitch, l2 ? -2.0f : -1.0f, ix->d_qn.p, center ? ix->d_mu.p : nullptr);
+  ix->launches += 1;
   SDB_CUDA(cudaGetLastError());
   static bool attr_set_dev[64] = {};  // cudaFuncSetAttribute is per device
   bool& attr_set = attr_set_dev[ix->device & 63];
@@ -1304,26 +1495,79 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
   // ---- level 0: exact scan of the first LEVEL0 points bounds every query's k-th distance
   const bool warp_rescore = getenv("SDB_FLAT_RESCORE_CTA") == nullptr;
   const size_t wsmem = size_t(RW_WARPS) * ((dim + 3) & ~3u) * sizeof(float);
+  unsigned long long* d_cand_total = reinterpret_cast<unsigned long long*>(d_misc + 2);  // summed by the last re-score
   auto rescore_warp = [&](uint64_t* o_ids, float* o_d, uint32_t* o_c, int last, uint32_t impl_first, uint32_t impl_n) {
     const uint32_t grid = (B + RW_WARPS - 1) / RW_WARPS;
+    unsigned long long* tot = last ? d_cand_total : nullptr;
+#define SDB_RW_LAUNCH(M, NS)                                                                                                   \
+  rescore_warp_kernel<M, NS><<<grid, 32 * RW_WARPS, wsmem, stream>>>(ix->d_vec, ix->vec_pitch, dim, d_queries, B, ix->d_cand.p, d_cnt, k, \
+                                                                     o_ids, o_d, o_c, d_ovf_list, d_misc + 1, d_ovf_flag, last,  \
+                                                                     impl_first, impl_n, ix->d_exists, tot)
+    const bool small = k <= 32;
     switch (ix->store_metric) {
       case SDB_METRIC_EUCLIDEAN:
-        rescore_warp_kernel<METRIC_EUCLIDEAN><<<grid, 32 * RW_WARPS, wsmem, stream>>>(
-            ix->d_vec, ix->vec_pitch, dim, d_queries, B, ix->d_cand.p, d_cnt, k, o_ids, o_d, o_c, d_ovf_list, d_misc + 1, d_ovf_flag,
-            last, impl_first, impl_n, ix->d_exists);
+        if (small) SDB_RW_LAUNCH(METRIC_EUCLIDEAN, 1); else SDB_RW_LAUNCH(METRIC_EUCLIDEAN, 3);
         break;
       case SDB_METRIC_DOT:
-        rescore_warp_kernel<METRIC_DOT><<<grid, 32 * RW_WARPS, wsmem, stream>>>(
-            ix->d_vec, ix->vec_pitch, dim, d_queries, B, ix->d_cand.p, d_cnt, k, o_ids, o_d, o_c, d_ovf_list, d_misc + 1, d_ovf_flag,
-            last, impl_first, impl_n, ix->d_exists);
+        if (small) SDB_RW_LAUNCH(METRIC_DOT, 1); else SDB_RW_LAUNCH(METRIC_DOT, 3);
         break;
       default:
-        rescore_warp_kernel<METRIC_COSINE><<<grid, 32 * RW_WARPS, wsmem, stream>>>(
-            ix->d_vec, ix->vec_pitch, dim, d_queries, B, ix->d_cand.p, d_cnt, k, o_ids, o_d, o_c, d_ovf_list, d_misc + 1, d_ovf_flag,
-            last, impl_first, impl_n, ix->d_exists);
+        if (small) SDB_RW_LAUNCH(METRIC_COSINE, 1); else SDB_RW_LAUNCH(METRIC_COSINE, 3);
         break;
     }
+#undef SDB_RW_LAUNCH
   };
+  const uint32_t npts = end_id - first_id;
+  // ---- two-pass form (tcgen05 path, the default): a minimum-mode pass over a sample prefix gives
+  // every query an upper bound of its k-th distance without any exact work (kth_thresh_kernel),
+  // then ONE candidate pass over all points and ONE exact re-score. The level scheme below (exact
+  // top-k of a growing prefix, four candidate passes + five re-scores at 1M points) remains for
+  // the mma.sync pass and as SDB_FLAT_LEVELS=1.
+  uint32_t tiles_a = 0, fold = 1;
+  const uint32_t whole_tiles = npts / T5_N;
+  if (t5_eligible(kp) && warp_rescore && !getenv("SDB_FLAT_LEVELS")) {
+    uint32_t div = 8;  // sample = 1/8 of the points: ~8 k candidates per query before the error margin
+    if (const char* e = getenv("SDB_FLAT_SAMPLE_DIV")) { const int v = atoi(e); if (v >= 1 && v <= 4096) div = uint32_t(v); }
+    const uint32_t whole = whole_tiles;  // whole tiles only
+    tiles_a = std::min(whole, std::max<uint32_t>({whole / div, 2 * k, 32u}));
+    fold = (2 * tiles_a + KTH_MAX_GROUPS - 1) / KTH_MAX_GROUPS;
+    if (fold) tiles_a = tiles_a / fold * fold;
+    if (tiles_a < k) tiles_a = 0;  // fewer groups than k: no bound from the minima
+  }
+  if (tiles_a) {
+    const uint32_t G = 2 * tiles_a / fold;
+    if ((rc = ix->d_gmin.ensure(size_t(G) * B_pad))) return rc;
+    ext_zero_kernel<<<(B_pad + 127) / 128, 128, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(ix->d_q16.p), kp, pitch, B_pad);
+    TcArgs ta{};
+    ta.q16 = reinterpret_cast<const __nv_bfloat16*>(ix->d_q16.p);
+    ta.x16 = reinterpret_cast<const __nv_bfloat16*>(ix->d_x16.p);
+    ta.xn = ix->d_xn.p; ta.thr = ix->d_thr.p; ta.exists = ix->d_exists;
+    ta.kp = kp; ta.pitch = pitch; ta.l2 = l2;
+    ta.cand = ix->d_cand.p; ta.cand_cnt = d_cnt; ta.B = B;
+    ta.rows_alloc = rows_pad; ta.bias = ix->d_bias.p;
+    ta.first_id = first_id; ta.end_id = first_id + tiles_a * T5_N;
+    ta.gmin = ix->d_gmin.p; ta.gmin_pitch = B_pad; ta.fold = fold;
+    ta.tile_stride = whole_tiles / tiles_a;  // the sample tiles are spread over the whole id range
+    if ((rc = launch_tc5_filter(ix, ta, B_pad, stream))) return rc;
+    kth_thresh_kernel<<<(B_pad + 3) / 4, 128, 0, stream>>>(ix->d_gmin.p, B_pad, G, k, ix->d_qn.p, d_xmax, ix->store_metric, dim, B, B_pad,
+                                                          ix->d_thr.p, reinterpret_cast<__nv_bfloat16*>(ix->d_q16.p), kp, pitch, d_cnt);
+    ta.end_id = end_id;
+    ta.gmin = nullptr; ta.gmin_pitch = 0; ta.fold = 1; ta.tile_stride = 1;
+    if ((rc = launch_tc5_filter(ix, ta, B_pad, stream))) return rc;
+    rescore_warp(d_out_ids, d_out_dists, d_out_counts, 1, 0, 0);
+    ix->launches += 5;
+    SDB_CUDA(cudaGetLastError());
+    if (debug) {
+      std::vector<uint32_t> h(B);
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(h.data(), d_cnt, B * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+      uint64_t tot = 0;
+      uint32_t mx = 0;
+      for (uint32_t v : h) { tot += v; mx = std::max(mx, v); }
+      fprintf(stderr, "[sdb] flat tc two-pass: sample %u points in %u groups, %.1f candidates/query (max %u, cap %u)\n",
+              tiles_a * T5_N, G, double(tot) / B, mx, CAND_CAP);
+    }
+  } else {
   if (warp_rescore) {
     rescore_warp(ix->d_sample_ids.p, ix->d_sample_d.p, ix->d_sample_cnt.p, 0, first_id,
                  std::min<uint32_t>(level0_points(), end_id - first_id));
@@ -1333,7 +1577,6 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
                                      first_id, first_id + level0_points())))
     return rc;
   // ---- levels 1..: tensor-core pass over a 32x larger prefix, thresholds from the level before
-  const uint32_t npts = end_id - first_id;
   const uint32_t qtiles = B_pad / TM;
   const size_t qsmem = size_t((dim + 3) & ~3u) * sizeof(float);
   uint64_t covered = level0_points();
@@ -1348,7 +1591,7 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
     const uint32_t lvl_end = last ? end_id : lvl_begin + uint32_t(span);
     covered = lvl_end - first_id;
     // thresholds from the previous level's exact top-k
-    thresh_kernel<<<(B_pad + 127) / 128, 128, 0, stream>>>(ix->d_sample_d.p, ix->d_sample_cnt.p, k, ix->d_qn.p, d_misc,
+    thresh_kernel<<<(B_pad + 127) / 128, 128, 0, stream>>>(ix->d_sample_d.p, ix->d_sample_cnt.p, k, ix->d_qn.p, d_xmax,
                                                            ix->store_metric, dim, B, B_pad, ix->d_thr.p,
                                                            reinterpret_cast<__nv_bfloat16*>(ix->d_q16.p), kp, pitch);
     seed_cand_kernel<<<(B + 127) / 128, 128, 0, stream>>>(ix->d_sample_ids.p, ix->d_sample_cnt.p, k, B, ix->d_cand.p, d_cnt);
@@ -1406,21 +1649,21 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
     }
     lvl_begin = lvl_end;
   }
+  }  // level scheme
   // ---- queries whose candidate list overflowed at some level: exact scan
-  uint32_t h_ovf = 0;
-  SDB_CUDA(cudaMemcpyAsync(&h_ovf, d_misc + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-  {
-    // diagnostic (sdb_flat_last_stats): candidates the last level kept, summed over the batch
-    static thread_local std::vector<uint32_t> h_cnt;
-    h_cnt.resize(B);
-    SDB_CUDA(cudaMemcpyAsync(h_cnt.data(), d_cnt, size_t(B) * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    SDB_CUDA(cudaStreamSynchronize(stream));
-    uint64_t tot = 0;
-    for (uint32_t v : h_cnt) tot += v;
-    ix->flat_last_candidates = tot;
-    ix->flat_last_overflow = h_ovf;
-    ix->flat_last_path = t5_eligible(kp) ? 2 : 1;
+  // [1] overflow count, [2..3] diagnostic (sdb_flat_last_stats): candidates the last level kept, summed
+  // over the batch on the device (a 16-byte read-back instead of the B counts)
+  if (!warp_rescore) {  // (the warp re-score of the last level has summed them already)
+    sum_counts_kernel<<<1, 256, 0, stream>>>(d_cnt, B, reinterpret_cast<unsigned long long*>(d_misc + 2));
+    ix->launches++;
   }
+  uint32_t h_misc[4] = {0, 0, 0, 0};
+  SDB_CUDA(cudaMemcpyAsync(h_misc, d_misc, sizeof(h_misc), cudaMemcpyDeviceToHost, stream));
+  SDB_CUDA(cudaStreamSynchronize(stream));
+  const uint32_t h_ovf = h_misc[1];
+  ix->flat_last_candidates = uint64_t(h_misc[2]) | (uint64_t(h_misc[3]) << 32);
+  ix->flat_last_overflow = h_ovf;
+  ix->flat_last_path = t5_eligible(kp) ? 2 : 1;
   if (debug) fprintf(stderr, "[sdb] flat tc: %u of %u queries overflowed -> exact scan\n", h_ovf, B);
   if (h_ovf) {
     DevBuf<float> d_q2, d_d2;

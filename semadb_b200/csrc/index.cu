@@ -277,7 +277,7 @@ void sdb_index_destroy(sdb_index* ix) {
   cudaFree(ix->d_exists);
   cudaFree(ix->d_dirty);
   ix->d_start_extra.release();
-  ix->d_x16.release(); ix->d_q16.release(); ix->d_xn.release(); ix->d_bias.release(); ix->d_qn.release(); ix->d_thr.release();
+  ix->d_x16.release(); ix->d_q16.release(); ix->d_xn.release(); ix->d_bias.release(); ix->d_mu.release(); ix->d_gmin.release(); ix->d_xmax.release(); ix->d_qn.release(); ix->d_thr.release();
   ix->d_sample_d.release(); ix->d_cand.release(); ix->d_candcnt.release(); ix->d_sample_cnt.release(); ix->d_sample_ids.release();
   cudaFree(ix->d_bq_thr);
   cudaFree(ix->d_pq_centroids);

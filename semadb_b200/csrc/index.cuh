@@ -141,6 +141,10 @@ struct sdb_index {
   sdb::DevBuf<uint16_t> d_x16, d_q16;
   sdb::DevBuf<float> d_xn, d_qn, d_thr, d_sample_d;
   sdb::DevBuf<float> d_bias;  // tcgen05 flat pass: per-point score bias (|x|^2 or 0; +inf = no such point)
+  sdb::DevBuf<float> d_mu;    // squared-L2: translation applied to the bf16 shadow and the queries (+ partial sums)
+  sdb::DevBuf<float> d_gmin;  // tcgen05 flat pass, minimum mode: [groups][B_pad] smallest approximate scores
+  int tc_centered = -1;       // whether the current shadow is centred
+  sdb::DevBuf<uint32_t> d_xmax;  // bits of the largest squared norm of a (centred) stored row
   sdb::DevBuf<uint32_t> d_cand, d_candcnt, d_sample_cnt;
   sdb::DevBuf<uint64_t> d_sample_ids;
   uint32_t last_B = 0;

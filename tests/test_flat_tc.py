@@ -81,18 +81,24 @@ def test_tcgen05_candidate_pass_matches_mma_sync_pass(metric, dim):
     g = IndexFlat(IndexVectorFlatParameters(dim, metric))
     g.set_vectors(np.arange(2, n + 2, dtype=np.uint64), X)
     os.environ.pop("SDB_FLAT_MMA_SYNC", None)
-    a = g.flat_search_batch(Q, 10)
-    pa, ca, oa = g.flat_last_stats()
-    os.environ["SDB_FLAT_MMA_SYNC"] = "1"
+    d = g.flat_search_batch(Q, 10)  # the default: two-pass form of the tcgen05 path
+    pd, cd, od = g.flat_last_stats()
+    os.environ["SDB_FLAT_LEVELS"] = "1"  # the level scheme on both kernels: same algorithm, same candidate sets
     try:
+        a = g.flat_search_batch(Q, 10)
+        pa, ca, oa = g.flat_last_stats()
+        os.environ["SDB_FLAT_MMA_SYNC"] = "1"
         b = g.flat_search_batch(Q, 10)
         pb, cb, ob = g.flat_last_stats()
     finally:
         os.environ.pop("SDB_FLAT_MMA_SYNC", None)
-    assert pa == 2 and pb == 1
-    assert oa == 0 and ob == 0
+        os.environ.pop("SDB_FLAT_LEVELS", None)
+    assert pa == 2 and pb == 1 and pd == 2
+    assert oa == 0 and ob == 0 and od == 0
     assert ca >= 10 * len(Q) and abs(ca - cb) <= 0.01 * cb + 5
+    assert cd >= 10 * len(Q)
     assert (a[0] == b[0]).all() and a[1].tobytes() == b[1].tobytes()
+    assert (d[0] == b[0]).all() and d[1].tobytes() == b[1].tobytes()
 
 
 def test_two_sm_variant_matches(monkeypatch):
@@ -111,4 +117,48 @@ def test_two_sm_variant_matches(monkeypatch):
     pb, cb, ob = g.flat_last_stats()
     assert pa == 2 and pb == 2 and oa == 0 and ob == 0
     assert abs(ca - cb) <= 0.01 * ca + 5
+    assert (a[0] == b[0]).all() and a[1].tobytes() == b[1].tobytes()
+
+
+@pytest.mark.parametrize("variant", ["levels", "no_center", "sample_all", "sample_small"])
+def test_flat_tc_variants_equal_exact_scan(variant, monkeypatch):
+    """Every form of the candidate generation returns the exact scan's lists: the level scheme
+    (SDB_FLAT_LEVELS=1), the two-pass form without centring, with the whole store as the sample and
+    with a sample so small that the bound is loose."""
+    env = {"levels": ("SDB_FLAT_LEVELS", "1"), "no_center": ("SDB_FLAT_NO_CENTER", "1"), "sample_all": ("SDB_FLAT_SAMPLE_DIV", "1"),
+           "sample_small": ("SDB_FLAT_SAMPLE_DIV", "64")}[variant]
+    n, dim = 70_000, 128
+    X, Q = synth.sift_shaped(n, dim, 3), synth.sift_shaped(400, dim, 4, w_seed=3)
+    g = IndexFlat(IndexVectorFlatParameters(dim, "euclidean"))
+    g.set_vectors(np.arange(2, n + 2, dtype=np.uint64), X)
+    monkeypatch.setenv(*env)
+    for k in (10, 75):
+        ti, td, tc = g.flat_search_batch(Q, k)
+        path, cand, ovf = g.flat_last_stats()
+        assert path == 2 and ovf == 0 and cand >= k * len(Q)
+        monkeypatch.setenv("SDB_FLAT_EXACT", "1")
+        ei, ed, ec = g.flat_search_batch(Q, k)
+        monkeypatch.delenv("SDB_FLAT_EXACT")
+        assert (tc == ec).all() and (ti == ei).all() and td.tobytes() == ed.tobytes()
+
+
+def test_flat_tc_clustered_insertion_order():
+    """Points stored in an order that follows their position (sorted along one coordinate, as a
+    collection filled region by region would be): the sample of the minimum-mode pass is spread
+    over the whole id range, so the bound stays useful — nobody overflows into the exact scan —
+    and the lists are the exact scan's."""
+    n, dim = 80_000, 64
+    X = synth.latent_gaussian(n, dim, seed=21, latent=8)
+    X = np.ascontiguousarray(X[np.argsort(X[:, 0], kind="stable")])
+    Q = synth.latent_gaussian(300, dim, seed=22, w_seed=21, latent=8)
+    g = IndexFlat(IndexVectorFlatParameters(dim, "euclidean"))
+    g.set_vectors(np.arange(2, n + 2, dtype=np.uint64), X)
+    a = g.flat_search_batch(Q, 10)
+    path, cand, ovf = g.flat_last_stats()
+    assert path == 2 and ovf == 0 and cand < 2000 * len(Q)
+    os.environ["SDB_FLAT_EXACT"] = "1"
+    try:
+        b = g.flat_search_batch(Q, 10)
+    finally:
+        os.environ.pop("SDB_FLAT_EXACT", None)
     assert (a[0] == b[0]).all() and a[1].tobytes() == b[1].tobytes()
