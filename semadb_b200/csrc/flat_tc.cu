@@ -103,12 +103,19 @@ __device__ __forceinline__ void split3(float v, __nv_bfloat16& hi, __nv_bfloat16
 constexpr float T5_NO_POINT = 3.0e38f;   // bias of a row that holds no point: never passes
 constexpr float T5_PASS_ALL = 1.0e38f;   // threshold of a query without a bound yet: every point passes
 constexpr float T5_PASS_NONE = -1.0e38f; // padding query rows
+// bf16 unit round-off 2^-8 on both factors of a product: |fl(q_i) fl(x_i) - q_i x_i| <= (2u + u^2) |q_i x_i|, summed with
+// Cauchy-Schwarz: <= 0.007828 |q| |x| for the dot product, twice that for the -2 q.x of the squared-L2 score
+constexpr float T5_C1 = 0.0157f;
+constexpr float T5_UP = 1.00001f;  // covers the fp32 rounding of the norms and of the square roots
 
 // tcgen05 pass: the per-point bias and the per-query threshold ride in the GEMM as a K extension,
 //   x~ = [ x (bf16) | b_hi b_mid b_lo  1 1 1 | 0 ... ]      b = |x|^2 (squared-L2) or 0 (dot, cosine)
 //   q~ = [ s*q      |  1    1     1   -t_hi -t_mid -t_lo | 0 ... ]   s = -2 or -1, t = threshold
 // so the accumulator is score - threshold and the filter is its sign bit. Rows that hold no point
 // (deleted, never set, beyond the last id) get b = 3e38: never negative against any threshold.
+// Seventh extension column (two-pass form): x~ carries |x_j| (rounded up), q~ carries +-c |q| (rounded
+// up in magnitude): the accumulator becomes score +- c |q| |x_j|, the bf16 error bound of THIS pair
+// instead of the one of the largest row.
 __global__ void bias_kernel(const float* xn, const uint8_t* exists, uint32_t rows, uint32_t rows_pad, int l2, float* bias,
                             __nv_bfloat16* x16, uint32_t kp, uint32_t pitch) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -120,6 +127,8 @@ __global__ void bias_kernel(const float* xn, const uint8_t* exists, uint32_t row
   __nv_bfloat16* e = x16 + size_t(i) * pitch + kp;
   const __nv_bfloat16 one = __float2bfloat16_rn(1.0f);
   e[0] = h; e[1] = m; e[2] = l; e[3] = one; e[4] = one; e[5] = one;
+  // the row's norm, rounded up: the two-pass form charges every point its own share c |q| |x_j| of the error bound
+  e[6] = b < T5_NO_POINT ? __float2bfloat16_ru(sqrtf(xn[i]) * T5_UP) : __float2bfloat16_rn(0.0f);
 }
 
 __global__ void xmax_kernel(const float* xn, const uint8_t* exists, uint32_t first, uint32_t end, uint32_t* out_bits) {
@@ -143,13 +152,14 @@ __global__ void thresh_kernel(const float* sample_d, const uint32_t* sample_cnt,
     __nv_bfloat16* e = q16 + size_t(q) * pitch + kp;
     const __nv_bfloat16 one = __float2bfloat16_rn(1.0f);
     e[0] = one; e[1] = one; e[2] = one; e[3] = h; e[4] = m; e[5] = l;
+    e[6] = __float2bfloat16_rn(0.0f);  // level scheme: the bound of the largest row, inside t
   };
   if (q >= B) { put(-INFINITY, T5_PASS_NONE); return; }  // padding rows never pass
   if (sample_cnt[q] < k) { put(INFINITY, T5_PASS_ALL); return; }
   const float tau = sample_d[size_t(q) * k + (k - 1)];
   const float x2 = __uint_as_float(*xmax_bits), q2 = qn[q];
   const float nq = sqrtf(q2), nx = sqrtf(x2);
-  const float c1 = 0.02f;                         // > 2 * 2.01 * 2^-8: bf16 unit roundoff 2^-8 on both factors of -2 q.x
+  const float c1 = T5_C1;                         // bf16 unit roundoff 2^-8 on both factors of -2 q.x
   const float c2 = float(dim + 32) * 4.8e-7f;     // fp32 accumulation of the GEMM (tensor cores may truncate), the K
                                                   // extension, the norms and the exact kernel
   float t;
@@ -187,21 +197,25 @@ __global__ void mean_final_kernel(const float* partial, const uint32_t* cnt, uin
   mu[d] = c ? s / float(c) : 0.0f;
 }
 
-// K extension of the query rows for the minimum-mode pass: threshold 0 (the accumulator is the score)
-__global__ void ext_zero_kernel(__nv_bfloat16* q16, uint32_t kp, uint32_t pitch, uint32_t B_pad) {
+// K extension of the query rows for the minimum-mode pass: threshold 0 and +c |q| against the
+// points' norms, so the accumulator is approximate score + c |q| |x_j| >= exact score - (fp32 terms)
+__global__ void ext_min_kernel(__nv_bfloat16* q16, uint32_t kp, uint32_t pitch, uint32_t B, uint32_t B_pad, const float* qn, int l2) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= B_pad) return;
   __nv_bfloat16* e = q16 + size_t(q) * pitch + kp;
   const __nv_bfloat16 one = __float2bfloat16_rn(1.0f), zero = __float2bfloat16_rn(0.0f);
   e[0] = one; e[1] = one; e[2] = one; e[3] = zero; e[4] = zero; e[5] = zero;
+  e[6] = q < B ? __float2bfloat16_ru((l2 ? T5_C1 : 0.5f * T5_C1) * sqrtf(qn[q]) * T5_UP) : zero;
 }
 
-// Threshold of the candidate pass from the minimum-mode pass over a sample prefix. The k smallest of
-// a query's group minima belong to k different points (the groups are disjoint point sets), each
-// with an exact score <= approximate score + E (E = the bf16 / fp32 error bound thresh_kernel
-// uses): the k-th true score over ALL points is <= m_k + E, and every point that good has an
-// approximate score <= m_k + 2E. One warp per query: k rounds of warp-wide minimum extraction
-// over the <= 512 group minima held in registers.
+// Threshold of the candidate pass from the minimum-mode pass over a sample of the points. With
+// a_j the approximate score, e_j = c |q| |x_j| the bf16 share of the error bound of the pair and
+// F the fp32 share (accumulation, norms, the exact kernel): exact_j <= a_j + e_j + F. The minimum
+// mode kept m = min (a_j + e_j) per group; the k smallest group minima belong to k different
+// points (the groups are disjoint), so the k-th exact score over ALL points is <= m_k + F, and
+// every point that good has a_j - e_j <= m_k + 2F = t: the candidate pass keeps a_j - e_j - t < 0.
+// One warp per query: k rounds of warp-wide minimum extraction over the <= 512 group minima
+// held in registers.
 constexpr uint32_t KTH_MAX_GROUPS = 512;
 __global__ void __launch_bounds__(128) kth_thresh_kernel(const float* gmin, uint32_t gmin_pitch, uint32_t G, uint32_t k, const float* qn,
                                                          const uint32_t* xmax_bits, int metric, uint32_t dim, uint32_t B,
@@ -244,9 +258,9 @@ __global__ void __launch_bounds__(128) kth_thresh_kernel(const float* gmin, uint
     } else {
       const float x2 = __uint_as_float(*xmax_bits), q2 = qn[q];
       const float nq = sqrtf(q2), nx = sqrtf(x2);
-      const float c1 = 0.02f, c2 = float(dim + 32) * 4.8e-7f;  // as in thresh_kernel
-      const float E = metric == METRIC_EUCLIDEAN ? c1 * nq * nx + c2 * (q2 + x2) : (0.5f * c1 + c2) * nq * nx;
-      const float t = mk + 2.0f * E;
+      const float c2 = float(dim + 32) * 4.8e-7f;  // as in thresh_kernel
+      const float F = metric == METRIC_EUCLIDEAN ? c2 * (q2 + x2) : c2 * nq * nx;
+      const float t = mk + 2.0f * F;
       t_out = fminf(t + fabsf(t) * 1e-6f + 1e-30f, T5_PASS_ALL);
     }
   }
@@ -257,6 +271,8 @@ __global__ void __launch_bounds__(128) kth_thresh_kernel(const float* gmin, uint
     __nv_bfloat16* e = q16 + size_t(q) * pitch + kp;
     const __nv_bfloat16 one = __float2bfloat16_rn(1.0f);
     e[0] = one; e[1] = one; e[2] = one; e[3] = h; e[4] = m; e[5] = l;
+    const float ce = (metric == METRIC_EUCLIDEAN ? T5_C1 : 0.5f * T5_C1) * sqrtf(q < B ? qn[q] : 0.0f) * T5_UP;
+    e[6] = __hneg(__float2bfloat16_ru(ce));
     if (q < B) cand_cnt[q] = 0;
   }
 }
@@ -1537,7 +1553,8 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
   if (tiles_a) {
     const uint32_t G = 2 * tiles_a / fold;
     if ((rc = ix->d_gmin.ensure(size_t(G) * B_pad))) return rc;
-    ext_zero_kernel<<<(B_pad + 127) / 128, 128, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(ix->d_q16.p), kp, pitch, B_pad);
+    ext_min_kernel<<<(B_pad + 127) / 128, 128, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(ix->d_q16.p), kp, pitch, B, B_pad,
+                                                            ix->d_qn.p, l2 ? 1 : 0);
     TcArgs ta{};
     ta.q16 = reinterpret_cast<const __nv_bfloat16*>(ix->d_q16.p);
     ta.x16 = reinterpret_cast<const __nv_bfloat16*>(ix->d_x16.p);
