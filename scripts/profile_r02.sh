@@ -11,6 +11,10 @@ done
 python bench.py --workload c4 --points 10000000 --extra none --steps 5 --no-probe > gpurun_out/bench_c4_10m_r02.json 2> gpurun_out/bench_c4_10m_r02.err
 python bench.py --workload c5a --steps 3 > gpurun_out/bench_c5a_r02.json 2> gpurun_out/bench_c5a_r02.err
 SDB_FLAT_SKIP_EXACT=1 python scripts/bench_configs.py flat > gpurun_out/flat_r02.json 2> /dev/null
+python scripts/flat_timeline.py --reps 7 --timeline --tag two-pass > gpurun_out/r02_flat_timeline.json 2> /dev/null
+SDB_FLAT_LEVELS=1 SDB_FLAT_NO_CENTER=1 python scripts/flat_timeline.py --reps 7 --tag "level scheme, no centring" > gpurun_out/r02_flat_levels.json 2> /dev/null
+ncu --set full --clock-control none --import-source on -k regex:'tc5_filter|kth_thresh|rescore_warp' --launch-skip 8 -c 4 -f -o gpurun_out/prof_flat_r02 \
+    python scripts/flat_timeline.py --reps 1 > gpurun_out/ncu_flat.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r02_bench.csv \
     python bench.py --steps 2 --warmup 1 > gpurun_out/ncu_bench_r02.log 2>&1
 SDB_PROFILE=1 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:beam_search -c 1 -f \

@@ -3,17 +3,21 @@
 //
 // bf16 products cannot be final distances (1e-5 tolerance, SURVEY.md §7.3-⑥), so the tensor
 // cores only *generate candidates*, with a guarantee:
-//   1. exact top-k of every query over the first 128 points (the exact CUDA-core scan, flat.cu)
-//      gives tau_q >= the true k-th smallest distance; steps 2-3 then run level by level over
-//      disjoint point ranges (each ending x32 further: 4k points, 131k, 4M, ...). A level's
-//      candidate list is seeded with the exact top-k of everything before it, so its re-score is
-//      the exact top-k of the whole prefix and tau tightens from level to level (~32 k
-//      candidates per query and level);
+//   1. an upper bound tau_q of every query's k-th smallest distance. Default (tcgen05 path, "two-pass
+//      form"): the GEMM runs in minimum mode over a sample of the point tiles spread over the id
+//      range; the k smallest of a query's per-group minima belong to k different points, so the
+//      k-th of them plus the error bound is such a tau_q (kth_thresh_kernel) — no exact work, one
+//      candidate pass over all points, one re-score. Level scheme (mma.sync pass, SDB_FLAT_LEVELS=1):
+//      exact top-k over the first 128 points, then steps 2-3 level by level over disjoint point
+//      ranges growing x8 (last level up to x16); a level's candidate list is seeded with the exact
+//      top-k of everything before it, so its re-score is the exact top-k of the whole prefix;
 //   2. a bf16 GEMM (fp32 accumulate) scores every (query, point) pair: a(q,x) = |x|^2 - 2 q~.x~
 //      (+|q|^2) for squared-L2, -q~.x~ for dot/cosine. |a - d| <= eps_q, a bound from the bf16
-//      unit roundoff 2^-8 and the largest point norm: eps_q = c1 |q| xmax + c2 (|q|^2 + xmax^2).
-//      Every pair with a < tau_q + eps_q is appended to the query's candidate list — a superset
-//      of the true top-k, because a true top-k member has d <= tau_q;
+//      unit roundoff 2^-8 and the largest point norm: eps_q = c1 |q| xmax + c2 (|q|^2 + xmax^2)
+//      (two-pass form: the c1 term per pair, c1 |q| |x_j|, carried by the GEMM itself; squared-L2
+//      stores are centred first, which shrinks both norms). Every pair with a < tau_q + eps_q is
+//      appended to the query's candidate list — a superset of the true top-k, because a true
+//      top-k member has d <= tau_q;
 //   3. candidates are re-scored with the reference's exact summation order (common.cuh) and the
 //      top-k taken by (distance asc, id asc) — flat.go:99,117 with ascending-id iteration.
 // A query whose candidate list overflows at any level falls back to the exact scan. The result is
@@ -1674,6 +1678,16 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
     sum_counts_kernel<<<1, 256, 0, stream>>>(d_cnt, B, reinterpret_cast<unsigned long long*>(d_misc + 2));
     ix->launches++;
   }
+  // host-buffer call (sdb_flat_search_batch): the result copies go in front of the one synchronisation
+  auto copy_out = [&]() -> int {
+    const auto& ho = ix->flat_host_out;
+    if (!ho.armed) return SDB_OK;
+    SDB_CUDA(cudaMemcpyAsync(ho.ids, d_out_ids, size_t(B) * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    SDB_CUDA(cudaMemcpyAsync(ho.dists, d_out_dists, size_t(B) * k * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    SDB_CUDA(cudaMemcpyAsync(ho.counts, d_out_counts, size_t(B) * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    return SDB_OK;
+  };
+  if ((rc = copy_out())) return rc;
   uint32_t h_misc[4] = {0, 0, 0, 0};
   SDB_CUDA(cudaMemcpyAsync(h_misc, d_misc, sizeof(h_misc), cudaMemcpyDeviceToHost, stream));
   SDB_CUDA(cudaStreamSynchronize(stream));
@@ -1695,8 +1709,10 @@ int launch_flat_tc(sdb_index* ix, uint32_t B, const float* d_queries, uint32_t k
     scatter_results_kernel<<<h_ovf, 128, 0, stream>>>(d_ovf_list, h_ovf, k, d_i2.p, d_d2.p, d_c2.p, d_out_ids, d_out_dists, d_out_counts);
     ix->launches += 2;
     SDB_CUDA(cudaGetLastError());
+    if ((rc = copy_out())) return rc;  // again, with the exact lists of the overflowed queries
     SDB_CUDA(cudaStreamSynchronize(stream));
   }
+  if (ix->flat_host_out.armed) ix->flat_host_out.done = true;
   return SDB_OK;
 }
 

@@ -762,8 +762,12 @@ int sdb_flat_search_batch(sdb_index* ix, uint32_t B, const float* queries, uint3
   if ((rc = ix->d_q.ensure(size_t(B) * ix->p.dim))) return rc;
   if ((rc = ensure_out_scratch(ix, B, k))) return rc;
   SDB_CUDA(cudaMemcpyAsync(ix->d_q.p, queries, size_t(B) * ix->p.dim * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+  ix->flat_host_out.ids = out_ids; ix->flat_host_out.dists = out_dists; ix->flat_host_out.counts = out_counts;
+  ix->flat_host_out.armed = true; ix->flat_host_out.done = false;
   rc = launch_flat(ix, B, ix->d_q.p, k, filtered ? ix->d_filter_bits.p : nullptr, ix->d_oid.p, ix->d_od.p, ix->d_oc.p, ix->stream);
+  ix->flat_host_out.armed = false;
   if (rc) return rc;
+  if (ix->flat_host_out.done) return SDB_OK;  // copied and synchronised by the tensor-core path
   SDB_CUDA(cudaMemcpyAsync(out_ids, ix->d_oid.p, size_t(B) * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, ix->stream));
   SDB_CUDA(cudaMemcpyAsync(out_dists, ix->d_od.p, size_t(B) * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
   SDB_CUDA(cudaMemcpyAsync(out_counts, ix->d_oc.p, size_t(B) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ix->stream));

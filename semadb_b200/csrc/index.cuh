@@ -134,6 +134,9 @@ struct sdb_index {
   sdb::DevBuf<uint8_t> d_tmp8;
   sdb::PinBuf<uint8_t> h_stage;
   // tensor-core flat scan (flat_tc.cu): bf16 shadow of the store + per-call scratch
+  // sdb_flat_search_batch arms this with the caller's host buffers: the tensor-core path then queues the
+  // result copies itself, in front of its one synchronisation (flat_tc.cu), and sets done
+  struct FlatHostOut { uint64_t* ids = nullptr; float* dists = nullptr; uint32_t* counts = nullptr; bool armed = false, done = false; } flat_host_out;
   uint64_t flat_last_candidates = 0;  // tensor-core flat scan: candidates kept by the last level, all queries
   uint32_t flat_last_overflow = 0;    // ... and queries that fell back to the exact scan
   int flat_last_path = 0;             // 0 exact scan, 1 mma.sync candidate pass, 2 tcgen05 candidate pass

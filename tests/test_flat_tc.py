@@ -162,3 +162,25 @@ def test_flat_tc_clustered_insertion_order():
     finally:
         os.environ.pop("SDB_FLAT_EXACT", None)
     assert (a[0] == b[0]).all() and a[1].tobytes() == b[1].tobytes()
+
+
+def test_flat_tc_overflow_falls_back_to_exact_scan():
+    """10 000 near-copies of each of seven vectors: every query has thousands of points within the
+    bf16 error bound of its k-th distance, the candidate lists overflow (cap 4 096) and those
+    queries are answered by the exact scan — same lists, through the host-buffer call."""
+    n, dim = 70_000, 96
+    rng = np.random.default_rng(11)
+    base = rng.normal(size=(7, dim)).astype(np.float32)
+    X = (base[np.arange(n) % 7] + rng.normal(size=(n, dim)).astype(np.float32) * np.float32(1e-4)).astype(np.float32)
+    Q = (base[rng.integers(0, 7, 200)] + rng.normal(size=(200, dim)).astype(np.float32) * np.float32(1e-3)).astype(np.float32)
+    g = IndexFlat(IndexVectorFlatParameters(dim, "euclidean"))
+    g.set_vectors(np.arange(2, n + 2, dtype=np.uint64), X)
+    a = g.flat_search_batch(Q, 10)
+    path, cand, ovf = g.flat_last_stats()
+    assert path == 2 and ovf > 0
+    os.environ["SDB_FLAT_EXACT"] = "1"
+    try:
+        b = g.flat_search_batch(Q, 10)
+    finally:
+        os.environ.pop("SDB_FLAT_EXACT", None)
+    assert (a[2] == b[2]).all() and (a[0] == b[0]).all() and a[1].tobytes() == b[1].tobytes()
