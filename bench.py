@@ -322,6 +322,8 @@ def build_device_generated(cx, name, n, Qr):
     torch = cx.torch
     g, start = new_index(name, cx.rank, cx.local_rank)
     g.reserve(n + 2)
+    if os.environ.get("SDB_INSERT_CONFIG"):  # "min,max,growth_div": A/B of the mini-batch schedule
+        g.insert_config(*[int(x) for x in os.environ["SDB_INSERT_CONFIG"].split(",")])
     t_ins = 0.0
     fit_s = None
     truth = None
@@ -704,6 +706,8 @@ def run_build(cx, n, steps, warmup):
             g.close()
         g, _ = new_index("c2", cx.rank, cx.local_rank)
         g.reserve(n + 2)
+        if os.environ.get("SDB_INSERT_CONFIG"):  # "min,max,growth_div": A/B of the mini-batch schedule
+            g.insert_config(*[int(x) for x in os.environ["SDB_INSERT_CONFIG"].split(",")])
         cx.barrier()
         t = time.perf_counter()
         g.insert_batch_device(ids, d_x)

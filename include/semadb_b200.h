@@ -212,7 +212,9 @@ int sdb_index_set_start_overflow(sdb_index* ix, uint64_t n, const uint64_t* ids)
  * copies min(*n, cap); flags are cleared only if clear != 0 and everything fitted. */
 int sdb_index_dirty_edges(sdb_index* ix, uint64_t cap, uint64_t* ids_out, uint64_t* n_out, int32_t clear);
 /* Mini-batch schedule of the batched insert: batch b has min(max_batch, max(min_batch,
- * inserted_so_far / growth_div)) points. 0 keeps a field's default. */
+ * inserted_so_far / growth_div)) points. 0 keeps a field's default (min 1; max / growth_div
+ * 32768 / 8 while the rows the searches read are at most 512 bytes wide, else 16384 / 16).
+ * 1, 1, x is the reference's sequential schedule (the oracle's graph edge for edge). */
 int sdb_insert_config(sdb_index* ix, uint32_t min_batch, uint32_t max_batch, uint32_t growth_div);
 
 /* ---- quantizers: replaces VectorStore.Fit (vamana.go:258): binaryQuantizer.Fit

@@ -856,7 +856,7 @@ int sdb_insert_config(sdb_index* ix, uint32_t min_batch, uint32_t max_batch, uin
   if (min_batch) ix->ins_min_batch = min_batch;
   if (max_batch) ix->ins_max_batch = max_batch;
   if (growth_div) ix->ins_growth_div = growth_div;
-  if (ix->ins_max_batch < ix->ins_min_batch) ix->ins_max_batch = ix->ins_min_batch;
+  if (ix->ins_max_batch && ix->ins_max_batch < ix->ins_min_batch) ix->ins_max_batch = ix->ins_min_batch;
   return SDB_OK;
 }
 

@@ -164,7 +164,17 @@ struct sdb_index {
   uint64_t insert_truncated = 0;  // inserts whose visited list was cut to MAX_CAND candidates (insert.cu)
 
   // insert schedule
-  uint32_t ins_min_batch = 1, ins_max_batch = 16384, ins_growth_div = 16;  // 4096 -> 16384: 1M x 128 builds in 1.87 s instead of 2.39 s, same recall (profiles/r01_ab_insert.txt)
+  // 1M x 128 build, same recall@10 (0.9992) at every setting: 1..4096 /16 2.39 s and 1..16384 /16 1.87 s with round 1's
+  // kernels (profiles/r01_ab_insert.txt); with round 2's kernels 1..16384 /16 0.81 s, 1..32768 /8 0.70 s (profiles/r02_ab_insert.txt)
+  // while the store's distance rows are wider than 512 bytes (C3: 384 floats) the larger batches cost more in the back-edge
+  // prunes than they save: 1.25M x 384 builds in 2.8-3.7 s at 1..16384 /16 and 4.7-5.4 s at either larger setting. 0 = choose
+  // by the width of the rows the searches read (insert.cu), sdb_insert_config overrides.
+  uint32_t ins_min_batch = 1, ins_max_batch = 0, ins_growth_div = 0;
+  uint32_t distance_row_bytes() const {
+    if (p.quantizer == SDB_QUANT_BINARY && bq_fitted) return bits_pitch * 8;
+    if (p.quantizer == SDB_QUANT_PRODUCT && pq_fitted) return codes_pitch;
+    return vec_pitch * 4;
+  }
 
   bool quant_active() const {
     return (p.quantizer == SDB_QUANT_BINARY && bq_fitted) || (p.quantizer == SDB_QUANT_PRODUCT && pq_fitted);

@@ -305,7 +305,11 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
   const uint32_t vis_cap = MAX_CAND;
   // updated points are re-inserted one by one (vamana.go:249-253) unless the index is relaxed
   const bool one_by_one = reinsert && !ix->p.relaxed;
-  const uint32_t max_batch = one_by_one ? 1u : std::max<uint32_t>(1, ix->ins_max_batch);
+  // mini-batch schedule: explicit (sdb_insert_config) or by the width of the distance rows (index.cuh)
+  const bool narrow_rows = ix->distance_row_bytes() <= 512;
+  const uint32_t cfg_max_batch = ix->ins_max_batch ? ix->ins_max_batch : (narrow_rows ? 32768u : 16384u);
+  const uint32_t cfg_growth_div = ix->ins_growth_div ? ix->ins_growth_div : (narrow_rows ? 8u : 16u);
+  const uint32_t max_batch = one_by_one ? 1u : std::max<uint32_t>(1, std::max(cfg_max_batch, ix->ins_min_batch));
 
   // device copies of ids and vectors for the whole call (chunked to bound staging)
   const uint64_t chunk_pts = std::max<uint64_t>(max_batch, (uint64_t(512) << 20) / (dim * sizeof(float)));
@@ -506,7 +510,7 @@ int insert_batch_locked(sdb_index* ix, uint64_t n, const uint64_t* ids, const fl
     uint64_t stat_unlinked[2] = {0, 0};
     while (done < cn) {
       uint64_t total_in = inserted_before + c0 + done;
-      uint64_t want = std::max<uint64_t>(ix->ins_min_batch, total_in / std::max<uint32_t>(1, ix->ins_growth_div));
+      uint64_t want = std::max<uint64_t>(ix->ins_min_batch, total_in / cfg_growth_div);
       uint32_t m = uint32_t(std::min<uint64_t>(std::min<uint64_t>(want, max_batch), cn - done));
       if (m == 0) m = 1;
       const uint32_t* b_ids = d_ids.p + done;
