@@ -28,6 +28,9 @@ NVLink + flag barrier) and the merge kernel (K6).
             own 1M x 128 shard) and, at --gpus 8, c3 (10M x 384 cosine, 1.25M per GPU) and c5b
             (50M x 1024-bit hamming, 6.25M per GPU) with merged recall, per-GPU HBM fraction and
             a 1k-query oracle parity probe at shard size. `--workload X` makes X the headline.
+            At N = 1 also `flat` (K5): IndexFlat.Search of the whole batch over the headline
+            shard through sdb_flat_search_batch with page-locked buffers, lists compared with
+            the exact scan's, useful TFLOP/s against the measured bf16 peak.
 
 Nothing on a timed GPU path touches oracle/: it builds the C2 graph during untimed input
 preparation ("searching the reference-built graph"), serves as the parity checker in the
@@ -693,6 +696,59 @@ def extra_block(r, world, B):
     return d
 
 
+def run_flat(cx, g, Q, n, reps=7):
+    """K5: IndexFlat.Search of the whole query batch over the headline shard through
+    sdb_flat_search_batch with page-locked host buffers (copies inside the timed calls); the
+    first 2000 lists are compared with the exact CUDA-core scan's."""
+    import ctypes as C
+    torch = cx.torch
+    from semadb_b200 import _capi
+    lib = _capi.lib()
+    B, dim = Q.shape
+    h_q = torch.from_numpy(Q).pin_memory()
+    h_ids = torch.zeros((B, K), dtype=torch.int64).pin_memory()
+    h_d = torch.zeros((B, K), dtype=torch.float32).pin_memory()
+    h_c = torch.zeros((B,), dtype=torch.int32).pin_memory()
+
+    def call(nq=B):
+        _capi.check(lib.sdb_flat_search_batch(g._h, nq, C.cast(h_q.data_ptr(), _capi.f32p), K, None, 0,
+                                              C.cast(h_ids.data_ptr(), _capi.u64p), C.cast(h_d.data_ptr(), _capi.f32p),
+                                              C.cast(h_c.data_ptr(), _capi.u32p)))
+
+    for _ in range(2):
+        call()
+    times = []
+    for _ in range(reps):
+        t = time.perf_counter()
+        call()
+        times.append(time.perf_counter() - t)
+    path, cand, ovf = g.flat_last_stats()
+    tc_ids, tc_d = h_ids.numpy().copy(), h_d.numpy().copy()
+    nx = min(B, 2000)
+    os.environ["SDB_FLAT_EXACT"] = "1"
+    try:
+        call(nx)
+    finally:
+        os.environ.pop("SDB_FLAT_EXACT", None)
+    same = bool((tc_ids[:nx] == h_ids.numpy()[:nx]).all() and tc_d[:nx].tobytes() == h_d.numpy()[:nx].tobytes())
+    dt = float(np.median(times))
+    peak_tf = None
+    try:
+        peak_tf = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["bf16_tflops"])
+    except Exception:
+        pass
+    tf = 2.0 * B * n * dim / dt / 1e12
+    return {"workload": f"IndexFlat.Search (K5): {B} queries x {n} x {dim} f32, k={K}, through sdb_flat_search_batch with "
+                        f"page-locked host buffers (tcgen05 sample pass + candidate pass + exact re-score)",
+            "ms_per_batch": dt * 1e3, "ms_each": [round(x * 1e3, 3) for x in times], "queries_per_s": B / dt,
+            "path": {0: "exact CUDA-core scan", 1: "mma.sync candidate pass", 2: "tcgen05 candidate pass"}.get(path, path),
+            "candidates_per_query": cand / B, "fell_back_to_exact_scan": ovf,
+            "lists_identical_to_exact_scan": {"queries": nx, "identical": same},
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": (tf / peak_tf) if peak_tf else None,
+                         "note": "useful FLOP (2 x queries x points x dim) / whole call incl. copies, sample pass and re-score"}}
+
+
 def run_build(cx, n, steps, warmup):
     """C5a: batched graph build (K8) of one n x 128 shard per GPU from empty; points/s over all GPUs."""
     torch = cx.torch
@@ -827,6 +883,15 @@ def main():
         cpu = {"value": B / cdt, "unit": "queries/s", "cores": threads, "kind": "port",
                "sample": f"all {B} queries x {reps} passes, {threads} threads, one query per thread",
                "single_thread_qps": qps1}
+    # ---- K5 on the same shard (rank-local, N = 1): IndexFlat.Search of the whole batch
+    flat = None
+    if name == "c2" and world == 1 and args.extra != "none" and h.get("g") is not None:
+        try:
+            flat = run_flat(cx, h["g"], h["Q"], n)
+        except Exception as e:  # noqa: BLE001 — an extra block must never cost the headline line
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            flat = {"error": repr(e)[:300]}
     # release the headline index before the extra workloads need the memory
     for k_ in ("g", "oix", "X", "searcher", "k_ids", "k_d"):
         h[k_] = None
@@ -842,6 +907,8 @@ def main():
         extra_names = [x for x in args.extra.split(",") if x]
     extra_n = dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in args.extra_n.split(",") if kv)
     extras = {}
+    if flat is not None:
+        extras["flat"] = flat
     for en in extra_names:
         if en == name:
             continue

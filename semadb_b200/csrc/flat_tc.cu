@@ -187,7 +187,10 @@ __global__ void mean_partial_kernel(const float* vec, uint32_t vec_pitch, uint32
     if (r >= end) break;
     if (!exists[r]) continue;
     ++c;
-    if (d < dim) s += vec[size_t(r) * vec_pitch + d];
+    if (d < dim) {
+      const float v = vec[size_t(r) * vec_pitch + d];
+      if (isfinite(v)) s += v;  // a stray inf / NaN row must not poison the translation of every row
+    }
   }
   if (d < dim) partial[size_t(part) * dim + d] = s;
   if (d == 0) cnt[part] = c;
@@ -198,7 +201,8 @@ __global__ void mean_final_kernel(const float* partial, const uint32_t* cnt, uin
   float s = 0.0f;
   uint32_t c = 0;
   for (uint32_t p = 0; p < MU_PARTS; ++p) { s += partial[size_t(p) * dim + d]; c += cnt[p]; }
-  mu[d] = c ? s / float(c) : 0.0f;
+  const float m = c ? s / float(c) : 0.0f;
+  mu[d] = isfinite(m) ? m : 0.0f;
 }
 
 // K extension of the query rows for the minimum-mode pass: threshold 0 and +c |q| against the

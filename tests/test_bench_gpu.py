@@ -33,6 +33,10 @@ def test_bench_line_contract_small():
     # the other BASELINE configs measured in the same run (reduced sizes here), each with its own
     # oracle parity probe on the GPU-built graph
     ex = d["extra_configs"]
+    fl = ex["flat"]  # K5 on the headline shard: tensor-core path, lists equal to the exact scan's
+    assert "error" not in fl, fl
+    assert fl["path"] == "tcgen05 candidate pass" and fl["lists_identical_to_exact_scan"]["identical"] is True
+    assert fl["ms_per_batch"] > 0 and fl["roofline"]["bound"] == "tensor" and fl["candidates_per_query"] >= 10
     assert ex["c5a"]["points_per_s"] > 0 and ex["c5a"]["recall_at_10_of_built_graph"] >= 0.95
     assert ex["c5a"]["insert_stats"]["points"] == 40000 and 0 < ex["c5a"]["roofline"]["frac"] < 1.5
     for name in ("c3", "c5b"):
