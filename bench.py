@@ -749,8 +749,10 @@ def run_flat(cx, g, Q, n, reps=7):
                          "note": "useful FLOP (2 x queries x points x dim) / whole call incl. copies, sample pass and re-score"}}
 
 
-def run_build(cx, n, steps, warmup):
-    """C5a: batched graph build (K8) of one n x 128 shard per GPU from empty; points/s over all GPUs."""
+def run_build(cx, n, steps, warmup, stat="mean"):
+    """C5a: batched graph build (K8) of one n x 128 shard per GPU from empty; points/s over all GPUs.
+    stat: how the timed builds are summarised — "mean" (the headline contract) or "median" (the
+    extra block: one build in a few runs long on some hosts; every time is listed)."""
     torch = cx.torch
     from semadb_b200 import synth
     X = synth.sift_shaped(n, 128, seed=3 + 1000 * cx.rank, w_seed=3)
@@ -773,7 +775,7 @@ def run_build(cx, n, steps, warmup):
         if it >= warmup:
             times.append(dt)
             stats = g.insert_stats()
-    dt = float(np.mean(times))
+    dt = float(np.median(times)) if stat == "median" else float(np.mean(times))
     # algorithmic bytes of the build: the searches' gathers, the candidate rows of
     # robustPrune(new), the adjacency rows of the back-edge targets (read + write) and the
     # candidate rows of robustPrune(B) on saturated targets
@@ -788,7 +790,8 @@ def run_build(cx, n, steps, warmup):
     g.close()
     return {"workload": f"C5a: batched graph build from empty, {n}x128 f32 L2 per GPU (greedySearch + robustPrune + "
                         f"back-edges, K8), vectors resident in HBM",
-            "points_per_s": cx.world * n / dt, "build_s": dt, "builds_timed": len(times), "build_s_each": [round(t, 4) for t in times],
+            "points_per_s": cx.world * n / dt, "build_s": dt, "build_s_is": stat + f" of {len(times)} builds",
+            "builds_timed": len(times), "build_s_each": [round(t, 4) for t in times],
             "n_gpus": cx.world,
             "recall_at_10_of_built_graph": rec, "insert_stats": stats,
             "roofline": {"bound": "hbm", "achieved": by / dt / 1e9, "peak": peak, "unit": "GB/s", "frac": by / dt / 1e9 / peak,
@@ -923,7 +926,7 @@ def main():
             continue
         try:
             if en == "c5a":
-                extras[en] = run_build(cx, extra_n.get(en, 1_000_000), 1, 1)
+                extras[en] = run_build(cx, extra_n.get(en, 1_000_000), 3, 1, stat="median")
             else:
                 en_n = extra_n.get(en, WORKLOADS[en]["n"])
                 r = run_search(cx, en, en_n, B, max(5, args.steps // 2), 3, "gpu", headline=False)
